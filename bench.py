@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — masklet-frames/s of the masklet-scoring hot path on BASELINE.json config 2
+("Grid-prompt track dedup: 64 synthetic SAM2 masklets x 80 frames at 720x1280 with stability score and miou_thresh 0.7").
+
+One step = one video's pass over the path, inputs already in HBM:
+    K1  binarise + bit-pack + stability counts over 64 x 80 fp32 logit planes      (dominant, HBM bound)
+    R1  bilinear resize to 540 x 960 + > 0.5 of all 5120 packed planes             (seg_utils.reshape_masklet)
+    R2  nearest resize + pack of the 64 prompt masks
+    G1  reference-order greedy filter: K2-gather IoU per tracked batch + host suppression
+    K2  64 x 64 spatio-temporal intersection matrix at native resolution + index-order greedy (compute_masklet_iou semantics)
+    one D2H of the stability counts -> float64 scores
+`value` = masklet-frames processed by all ranks / max-over-ranks device time (weak scaling: one video per GPU per step, no
+data-path collective).  `e2e` = the same step with the logits and prompt masks starting in pinned HOST memory (H2D inside the
+timed region, results read back).  `--impl reference` times the oracle port of the reference's CPU path on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "masklet-frames/s (dedup+J&F)"
+UNIT = "masklet-frames/s"
+CFG = dict(n_tracks=64, n_frames=80, H=720, W=1280, miou_thresh=0.7, n_max_tracks=64, batch_size=4, bin_size=4)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sola_b200", choices=["sola_b200", "reference"])
+    ap.add_argument("--tracks", type=int, default=CFG["n_tracks"], help="override for quick local checks only")
+    ap.add_argument("--frames", type=int, default=CFG["n_frames"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples if len(s) >= 6 for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the step (product path)
+# ---------------------------------------------------------------------------------------------------------------
+class Workload:
+    def __init__(self, device, seed, n_tracks, n_frames):
+        import sola_b200 as S
+        from sola_b200 import synth
+        self.S, self.device = S, device
+        self.N, self.T, self.H, self.W = n_tracks, n_frames, CFG["H"], CFG["W"]
+        self.logits, prompts = synth.dedup_candidates(self.N, self.T, self.H, self.W, seed=seed, device=device, bin_size=CFG["bin_size"])
+        self.prompt_meta = [{"prompt_id": p["prompt_id"], "frame_idx": p["frame_idx"]} for p in prompts]
+        self.prompt_masks_host = np.stack([p["segmentation"] for p in prompts])                       # (N, H, W) uint8
+        self.prompt_masks_dev = torch.from_numpy(self.prompt_masks_host).to(device)
+        self.packed = S.PackedMasks.empty((self.N, self.T), self.H, self.W, device)                   # reused outputs
+        self.counts = torch.empty((3, self.N * self.T), dtype=torch.int32, device=device)
+        self.k1_events = []
+        self.k1_bytes = self.N * self.T * (self.H * self.W * 4 + self.H * ((self.W + 31) // 32) * 4 + 12)
+
+    def step(self, logits=None, prompt_masks=None, record_k1=False, k1_done=False):
+        S = self.S
+        from sola_b200 import dedup
+        logits = self.logits if logits is None else logits
+        prompt_masks = self.prompt_masks_dev if prompt_masks is None else prompt_masks
+        if k1_done:                          # e2e: K1 already ran chunk by chunk behind the H2D copies
+            packed, counts = self.packed, self.counts
+        else:
+            if record_k1:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            packed, counts = S.binarize_pack_stability(logits, 0.0, 1.0, out=self.packed, counts_out=self.counts)   # K1
+            if record_k1:
+                e1.record()
+                self.k1_events.append((e0, e1))
+        resized = S.resize_bilinear_bin(packed)                                                                     # R1
+        dd = dedup.TrackDedup(self.prompt_meta, self.T, mode="grid", prompt_masks=prompt_masks, bin_size=CFG["bin_size"],
+                              n_max_tracks=CFG["n_max_tracks"], batch_size=CFG["batch_size"], miou_thresh=CFG["miou_thresh"])   # R2
+        while (batch := dd.next_batch()) is not None:                                                               # G1
+            dd.submit_resized(batch, resized[batch])
+        greedy = dd.result()
+        kept, by, iou, inter = dedup.dedup_matrix(packed, CFG["miou_thresh"])                                       # K2 + greedy
+        stab = S.packed.stability_from_counts(counts.view(3, self.N, self.T))                                       # D2H
+        return {"tracked": greedy["tracked"], "filtered": greedy["filtered"], "kept_st": kept, "stability": stab, "inter": inter}
+
+
+def checks(w: Workload, out) -> dict:
+    """Size-independent properties at full size + oracle comparison on a sub-sample (untimed)."""
+    from oracle import maskpath_oracle as O
+    inter = out["inter"]
+    assert np.array_equal(inter, inter.T), "intersection matrix not symmetric"
+    area = np.diag(inter)
+    c = w.counts.view(3, w.N, w.T).cpu().numpy()
+    assert np.array_equal(c[1].sum(1, dtype=np.int64), area), "diag(inter) != sum of K1 areas (checksum of checksums)"
+    assert (c[0] <= c[1]).all() and (c[1] <= c[2]).all(), "stability counts not nested"
+    assert (inter <= np.minimum(area[:, None], area[None, :])).all()
+    # sub-sample vs the oracle: 2 tracks x 3 frames of planes + their pair intersection
+    sub = w.logits[:2, :3].float().cpu()
+    planes = w.packed.words[:2, :3].cpu().numpy().view(np.uint32)
+    assert np.array_equal(planes, O.pack_bits(sub.numpy() > 0)), "K1 planes differ from the oracle on the sub-sample"
+    s = O.get_stability_score(sub.numpy())
+    assert np.array_equal(np.nan_to_num(s, nan=-1), np.nan_to_num(out["stability"][:2, :3], nan=-1)), "stability differs"
+    return {"tracked": len(out["tracked"]), "filtered": len(out["filtered"]), "kept_spatiotemporal": len(out["kept_st"])}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference's own CPU path), bounded sample scaled to the full step
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference_step(logits_cpu: torch.Tensor, prompts, n_pairs_st: int):
+    """The reference's operations on a sample: per-track linear stages, greedy IoU pairs, spatio-temporal pairs.
+    Returns seconds (t_linear_per_track, t_gather_pair, t_st_pair)."""
+    from oracle import maskpath_oracle as O
+    S_, T = logits_cpu.shape[:2]
+    t0 = time.perf_counter()
+    masklets, resized = [], []
+    for i in range(S_):
+        frames = [O.binarize(logits_cpu[i, t][None]) for t in range(T)]                  # generate_tokens_grid.py:219 per frame
+        m = torch.cat(frames, 0)                                                         # :224
+        masklets.append(m)
+        _ = [O.get_stability_score(logits_cpu[i, t].numpy()) for t in range(T)]          # prompt_generator.py:169 (per plane)
+        resized.append(O.reshape_masklet(m))                                             # seg_utils.py:145
+    t_lin = (time.perf_counter() - t0) / S_
+    t0 = time.perf_counter()
+    n_g = 0
+    for i in range(S_):
+        for p in prompts[: 2 * S_]:
+            pm = O.resize_prompt_nearest(p["segmentation"], resized[i].shape[1], resized[i].shape[2])       # :271-272
+            O.compute_mask_iou(resized[i][p["frame_idx"]], pm)                                                # :273
+            n_g += 1
+    t_g = (time.perf_counter() - t0) / max(n_g, 1)
+    t0 = time.perf_counter()
+    n_st = 0
+    for i in range(S_):
+        for j in range(i + 1, S_):
+            if n_st >= n_pairs_st:
+                break
+            O.compute_masklet_iou(masklets[i], masklets[j])                                                  # seg_utils.py:110
+            n_st += 1
+    t_st = (time.perf_counter() - t0) / max(n_st, 1)
+    return t_lin, t_g, t_st
+
+
+def cpu_arm(n_tracks, n_frames, steps, warmup, sample_tracks=4):
+    from sola_b200 import synth
+    logits, prompts = synth.dedup_candidates(sample_tracks, n_frames, CFG["H"], CFG["W"], seed=1234 + 2, device="cpu", bin_size=CFG["bin_size"])
+    n_pairs = sample_tracks * (sample_tracks - 1) // 2
+    times = []
+    for it in range(warmup + steps):
+        t = cpu_reference_step(logits, prompts, n_pairs)
+        if it >= warmup:
+            times.append(t)
+    t_lin, t_g, t_st = (float(np.mean([x[k] for x in times])) for k in range(3))
+    N = n_tracks
+    # full step on the CPU: N linear stages, ~N*N/2 greedy pairs (every tracked masklet vs the remaining prompts), N(N-1)/2 volume pairs
+    full = N * t_lin + (N * (N - 1) // 2) * t_g + (N * (N - 1) // 2) * t_st
+    value = N * n_frames / full
+    sample = (f"{sample_tracks} tracks x {n_frames} frames x {CFG['H']}x{CFG['W']} through binarise+cat+stability+reshape_masklet "
+              f"({t_lin * 1e3:.0f} ms/track), {2 * sample_tracks * sample_tracks} greedy mask-IoU pairs ({t_g * 1e6:.0f} us/pair), "
+              f"{n_pairs} compute_masklet_iou pairs ({t_st * 1e3:.0f} ms/pair); scaled to {N} tracks: "
+              f"{N}*t_track + {N * (N - 1) // 2}*(t_gather + t_masklet_pair) = {full:.1f} s/step")
+    return value, full, sample
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_tracks, n_frames = args.tracks, args.frames
+    workload = f"config2: grid-prompt track dedup, {n_tracks} masklets x {n_frames} frames x {CFG['H']}x{CFG['W']} fp32 logits, " \
+               f"stability score, miou_thresh {CFG['miou_thresh']} (one video per GPU per step)"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        value, full, sample = cpu_arm(n_tracks, n_frames, max(1, args.steps), max(0, args.warmup))
+        cores = torch.get_num_threads()
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": full * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "note": "oracle port of the reference's CPU path (the reference is Python; /root/reference does "
+                           "not exist on the GPU box), torch-CPU ops with all host threads; one rank regardless of --gpus"},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=device)
+    import sola_b200 as S
+    S.load_library()
+
+    w = Workload(device, seed=1234 + 2 + 1000 * rank, n_tracks=n_tracks, n_frames=n_frames)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = None
+    for _ in range(max(args.warmup, 3)):
+        out = w.step()
+    info = checks(w, out)
+    barrier()
+    launches0 = S.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        ev0.record()
+        for _ in range(args.steps):
+            out = w.step(record_k1=True)
+        ev1.record()
+        barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = S.launch_count() - launches0
+    k1_ms = float(np.mean([a.elapsed_time(b) for a, b in w.k1_events]))
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    units = world * n_tracks * n_frames * args.steps
+    value = units / (max_ms * 1e-3)
+
+    # ---- e2e: logits + prompt masks start in pinned host memory; H2D in the timed region; results read back -------
+    e2e = None
+    if not args.no_e2e:
+        try:
+            chunk = 4
+            host_chunks = []
+            for s in range(0, n_tracks, chunk):
+                h = torch.empty((min(chunk, n_tracks - s), n_frames, CFG["H"], CFG["W"]), dtype=torch.float32, pin_memory=True)
+                h.copy_(w.logits[s:s + chunk])
+                host_chunks.append(h)
+            host_prompts = torch.from_numpy(w.prompt_masks_host).pin_memory()
+            dev_logits = torch.empty_like(w.logits)
+            copy_stream = torch.cuda.Stream(device=device)
+
+            def e2e_step():
+                # chunked H2D on a copy stream, K1 of chunk c overlaps the copy of chunk c+1
+                evs = []
+                with torch.cuda.stream(copy_stream):
+                    for c, h in enumerate(host_chunks):
+                        dev_logits[c * chunk: c * chunk + h.shape[0]].copy_(h, non_blocking=True)
+                        e = torch.cuda.Event()
+                        e.record(copy_stream)
+                        evs.append(e)
+                    pm = host_prompts.to(device, non_blocking=True)
+                    e = torch.cuda.Event()
+                    e.record(copy_stream)
+                    evs.append(e)
+                cview = w.counts.view(3, n_tracks, n_frames)
+                for c, h in enumerate(host_chunks):
+                    torch.cuda.current_stream().wait_event(evs[c])
+                    sl = slice(c * chunk, c * chunk + h.shape[0])
+                    _, cc = S.binarize_pack_stability(dev_logits[sl], 0.0, 1.0, out=w.packed[sl])       # K1 on the chunk that just landed
+                    cview[:, sl] = cc
+                torch.cuda.current_stream().wait_event(evs[-1])
+                return w.step(logits=dev_logits, prompt_masks=pm, k1_done=True)                         # R1, R2, G1, K2, read-backs
+
+            e2e_step()
+            barrier()
+            n_e2e = max(1, min(args.e2e_steps, args.steps))
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n_e2e):
+                res = e2e_step()
+            b.record()
+            barrier()
+            te = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            h2d = w.logits.numel() * 4 + host_prompts.numel()
+            d2h = int(3 * n_tracks * n_frames * 4 + n_tracks * n_tracks * 8 + 3 * n_tracks * n_tracks * 4)
+            e2e = {"value": world * n_tracks * n_frames * n_e2e / (float(te.item()) * 1e-3), "unit": UNIT,
+                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h, "steps": n_e2e,
+                   "note": "pinned host fp32 logits + uint8 prompt masks copied H2D every step (chunked, overlapped with K1); "
+                           "stability counts, IoU count matrices and the N x N intersection matrix read back"}
+            del host_chunks, dev_logits
+        except Exception as ex:  # e.g. pinned allocation refused on a small host
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(ex)[:200]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    achieved = w.k1_bytes / (k1_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": workload, "l2_policy": "inputs larger than L2 (18.9 GB fp32 logits per step vs 126 MB L2)",
+                   "kept_sets": info, "parallelism": f"video-sharded x{world}, no data-path collective"},
+        "clocks": clk.summary(),
+        "gpu_launches": int(launches),
+        "e2e": e2e,
+        "roofline": {"bound": "hbm", "kernel": "pack_flat_kernel<float, THRESH3> (K1 binarise+pack+stability)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                     "bytes_per_launch": w.k1_bytes, "ms_per_launch": k1_ms, "share_of_step": k1_ms / (max_ms / args.steps),
+                     "traffic": None},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        v, full, sample = cpu_arm(n_tracks, n_frames, 1, 1)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
+    traffic_path = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.isfile(traffic_path):
+        with open(traffic_path) as f:
+            line["roofline"]["traffic"] = json.load(f).get("dram_bytes_per_launch")
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,118 @@
+/* sola_maskpath.h — C ABI of libsola_maskpath.so: B200 (sm_100a) kernels for SOLA's masklet-scoring path.
+ *
+ * The reference (cvlab-kaist/SOLA) has no FFI layer: the path is plain Python/ATen.  Each entry point below
+ * names the reference code it replaces (file:line under the reference tree); the Python mirror in
+ * sola_b200/ keeps the reference signatures and calls these through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a caller-owned DEVICE pointer unless it says "host"; outputs are pre-allocated by the caller;
+ *   - all work is enqueued on `stream` (a cudaStream_t; 0 = legacy default stream); no implicit synchronisation,
+ *     no global state, re-entrant across streams / devices (the current CUDA device must own the pointers);
+ *   - return value: 0 = ok, <0 = error (SOLA_ERR_*); sola_last_error_string() describes the last error of the
+ *     calling thread; nothing throws;
+ *   - bit-packed plane layout: a mask (H, W) is (H, Wp) uint32, Wp = (W + 31) / 32, bit b of word w of a row is
+ *     pixel 32*w + b, pad bits of the last word are 0.  frame_words = H * Wp.
+ *   - counts are exact integers: int32 per frame, int64 per volume.
+ */
+#ifndef SOLA_MASKPATH_H
+#define SOLA_MASKPATH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOLA_OK 0
+#define SOLA_ERR_INVALID (-1)
+#define SOLA_ERR_CUDA (-2)
+#define SOLA_ERR_UNSUPPORTED (-3)
+
+typedef void* sola_stream_t; /* cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+int sola_version(void);
+const char* sola_last_error_string(void);
+const char* sola_build_arch(void);               /* "sm_100a" */
+unsigned long long sola_launch_count(void);      /* kernels launched through this library so far (process-wide) */
+
+/* ---- K1: binarise + bit-pack + stability popcounts ---------------------------------------------------------
+ * replaces  (out_mask_logits > 0.0).float() + torch.cat      track_generation/generate_tokens_grid.py:215,219,222,224
+ *                                                            track_generation/generate_tokens_gdino.py:232,237,240,241
+ *           PromptGenerator.get_stability_score              track_generation/prompt_generator.py:169-186
+ * logits (n_frames, H, W); packed_out (n_frames, H, Wp) = logits > thr (strict; NaN -> 0);
+ * cnt_hi/cnt_mid/cnt_lo [n_frames] = #(logit > thr+off), #(logit > thr), #(logit > thr-off); any output may be NULL.
+ * Thresholds are rounded to fp32 before comparing, as numpy/torch do for a Python scalar. */
+int sola_binarize_pack_f32(const float* logits, long long n_frames, int H, int W, double thr, double off,
+                           uint32_t* packed_out, int* cnt_hi, int* cnt_mid, int* cnt_lo, sola_stream_t stream);
+int sola_binarize_pack_bf16(const void* logits_bf16, long long n_frames, int H, int W, double thr, double off,
+                            uint32_t* packed_out, int* cnt_hi, int* cnt_mid, int* cnt_lo, sola_stream_t stream);
+/* single threshold (x > thr) -> packed + area; used for `interpolate(...) > 0.5` style binarisation of float planes */
+int sola_threshold_pack_f32(const float* x, long long n_frames, int H, int W, double thr,
+                            uint32_t* packed_out, int* area, sola_stream_t stream);
+/* {0,1} masks (nonzero = foreground) -> packed + area.   fp32: masks as every reference function receives them;
+ * u8: masks as dataloader.py:353-369 rle_masklet_decode yields them */
+int sola_pack_mask_f32(const float* mask, long long n_frames, int H, int W, uint32_t* packed_out, int* area, sola_stream_t stream);
+int sola_pack_mask_u8(const uint8_t* mask, long long n_frames, int H, int W, uint32_t* packed_out, int* area, sola_stream_t stream);
+/* packed -> {0,1} planes, for drop-in return types (reshape_masklet returns fp32; get_sam2_masklet returns uint8) */
+int sola_unpack_f32(const uint32_t* packed, long long n_frames, int H, int W, float* out, sola_stream_t stream);
+int sola_unpack_u8(const uint32_t* packed, long long n_frames, int H, int W, uint8_t* out, sola_stream_t stream);
+
+/* ---- K3: per-frame |A∩B|, |A|, |B| ------------------------------------------------------------------------
+ * replaces the mul/add/sum/.item() chains of
+ *           Evaluator.compute_J / compute_F                  evaluator.py:227-247
+ *           compute_mask_iou / compute_masklet_iou           track_generation/seg_utils.py:110-142
+ *           compute_mask_iou_torch / compute_mask_metrics    track_generation/utils.py:65-75,132-174
+ * raw planes: a, b (n_frames, frame_px) with nonzero = foreground; outputs int32 [n_frames]. */
+int sola_frame_counts_f32(const float* a, const float* b, long long n_frames, long long frame_px,
+                          int* inter, int* area_a, int* area_b, sola_stream_t stream);
+int sola_frame_counts_u8(const uint8_t* a, const uint8_t* b, long long n_frames, long long frame_px,
+                         int* inter, int* area_a, int* area_b, sola_stream_t stream);
+/* packed, batched: a (Na, T, frame_words), b (Nb, T, frame_words) -> inter (Na, Nb, T), area_a (Na, T), area_b (Nb, T).
+ * One launch labels every track against every GT object (generate_tokens_grid.py:253-264). */
+int sola_frame_counts_packed(const uint32_t* a, const uint32_t* b, int Na, int Nb, int T, long long frame_words,
+                             int* inter, int* area_a, int* area_b, sola_stream_t stream);
+/* packed, ragged: frame f = words [word_offsets[f], word_offsets[f+1]) of both buffers (device int64 [n_frames+1]).
+ * One launch covers a whole J&F sweep of differently-shaped units (evaluator.py:174-225). */
+int sola_frame_counts_packed_ragged(const uint32_t* a, const uint32_t* b, const long long* word_offsets, int n_frames,
+                                    int* inter, int* area_a, int* area_b, sola_stream_t stream);
+/* OR over the selected packed tracks: tracks (K, words), select u8 [K] (NULL = all) -> out (words).
+ * replaces np.logical_or accumulation in dataloader.py:285-299 (GT objects) and :319-350 (selected SAM2 tracks). */
+int sola_or_merge(const uint32_t* tracks, const uint8_t* select, int K, long long words, uint32_t* out, sola_stream_t stream);
+
+/* ---- K2: pairwise mask IoU ---------------------------------------------------------------------------------
+ * spatio-temporal N x N: packed (N, words_per_track) -> inter_out int64 (N, N) (symmetric, diagonal = area),
+ * area_out int64 [N] (may be NULL).  Semantics of seg_utils.compute_masklet_iou (seg_utils.py:110-125) per pair. */
+int sola_pair_iou_st(const uint32_t* packed, int N, long long words_per_track, long long* inter_out, long long* area_out,
+                     sola_stream_t stream);
+/* gathered single-frame: tracks (N, T, frame_words), prompts (P, frame_words), frame_idx int32 [P] ->
+ * inter (N, P) = |track_i[frame_idx[j]] ∩ prompt_j|, area_t (N, P) = |track_i[frame_idx[j]]|, area_p [P].
+ * This is the matrix walked by generate_tokens_grid.py:266-278 / generate_tokens_gdino.py:288-300. */
+int sola_pair_iou_gather(const uint32_t* tracks, const uint32_t* prompts, const int* frame_idx, int N, int P, int T,
+                         long long frame_words, int* inter, int* area_t, int* area_p, sola_stream_t stream);
+
+/* ---- R1 / R2: resizes that feed the greedy filter ----------------------------------------------------------
+ * R1 replaces seg_utils.reshape_masklet (seg_utils.py:145-160): bilinear (align_corners=False) to (oh, ow) then > 0.5,
+ * reproducing ATen's CUDA upsample_bilinear2d fp32 arithmetic.  Input either bit-packed or fp32 planes.
+ * out_packed (n_frames, oh, owp) and/or out_f32 (n_frames, oh, ow) {0,1}; area int32 [n_frames] (may be NULL). */
+int sola_resize_bilinear_bin_packed(const uint32_t* in_packed, long long n_frames, int H, int W, int oh, int ow,
+                                    uint32_t* out_packed, int* area, sola_stream_t stream);
+int sola_resize_bilinear_bin_f32(const float* in, long long n_frames, int H, int W, int oh, int ow,
+                                 uint32_t* out_packed, float* out_f32, int* area, sola_stream_t stream);
+/* R2 replaces F.interpolate(prompt[None,None], (h,w), 'nearest') (generate_tokens_grid.py:271-272,
+ * generate_tokens_gdino.py:293-294): legacy nearest, src = min(floor(dst * in/out), in-1); u8 or packed input. */
+int sola_resize_nearest_u8(const uint8_t* in, long long n_frames, int H, int W, int oh, int ow,
+                           uint32_t* out_packed, int* area, sola_stream_t stream);
+int sola_resize_nearest_packed(const uint32_t* in_packed, long long n_frames, int H, int W, int oh, int ow,
+                               uint32_t* out_packed, int* area, sola_stream_t stream);
+
+/* ---- boundary F (extension; no reference implementation — DAVIS definition, see oracle/boundary_oracle.py) --
+ * pred, gt packed (n_frames, H, Wp); radius = bound_pix; counts int32 [n_frames] each:
+ * n_fg = |bmap(pred)|, n_gt = |bmap(gt)|, fg_match = |bmap(pred) & dilate(bmap(gt))|, gt_match = |bmap(gt) & dilate(bmap(pred))|. */
+int sola_boundary_counts(const uint32_t* pred, const uint32_t* gt, long long n_frames, int H, int W, int radius,
+                         int* n_fg, int* n_gt, int* fg_match, int* gt_match, sola_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOLA_MASKPATH_H */

@@ -1,0 +1,363 @@
+// K1 — read-once binarise + bit-pack + stability popcounts, and the {0,1}-mask packers / unpackers.
+//
+// Replaces, on the device and in one pass over the logits:
+//   (out_mask_logits > 0.0).float()                 generate_tokens_grid.py:215,219,222 ; generate_tokens_gdino.py:232,237,240
+//   torch.cat(list, 0)                              generate_tokens_grid.py:224
+//   PromptGenerator.get_stability_score             track_generation/prompt_generator.py:169-186
+//
+// Layout: a mask plane (H, W) becomes (H, Wp) uint32 words, Wp = ceil(W/32); bit b of word w is
+// pixel 32*w + b; pad bits of the last word of a row are zero.  When W % 32 == 0 the plane is simply the flat
+// bit string of the pixels and the "flat" kernel below is used; otherwise the per-row kernel.
+//
+// Flat kernel, per warp iteration ("chunk" = 1024 pixels = 32 output words):
+//   * every lane issues L = 32/E 128-bit streaming loads (E = elements per 16 B: 4 fp32 / 8 bf16 / 16 u8), lane-
+//     contiguous so each load instruction covers 512 contiguous bytes;
+//   * each load yields E predicate bits per threshold; L loads fill one private 32-bit register per threshold.
+//     For the two stability thresholds only the popcount matters, so those registers are consumed as they are;
+//   * for the stored plane the L x L slot matrix held by each group of L lanes is transposed with log2(L)
+//     shuffle+select steps, after which every lane owns one finished word, and the warp stores 128 contiguous bytes.
+// HBM traffic is exactly the algorithmic minimum: each logit is read once, each packed word written once.
+#include "common.cuh"
+
+namespace sola {
+
+enum PackMode { MODE_THRESH3 = 0, MODE_THRESH1 = 1, MODE_NONZERO = 2 };
+
+struct Thresholds {
+  float mid, hi, lo;
+};
+
+template <typename T> struct ElemTraits;
+template <> struct ElemTraits<float> { static constexpr int E = 4; };
+template <> struct ElemTraits<__nv_bfloat16> { static constexpr int E = 8; };
+template <> struct ElemTraits<uint8_t> { static constexpr int E = 16; };
+
+__device__ __forceinline__ uint32_t gt_bit(float x, float t) { return x > t ? 1u : 0u; }   // NaN -> 0
+
+// ---- per-128-bit-load predicate extraction -------------------------------------------------------------------
+// Returns E bits (element c of the vector -> bit c) for mid, and (MODE_THRESH3 only) hi / lo.
+template <int MODE>
+__device__ __forceinline__ void vec_bits(const uint4& raw, const Thresholds& th, float, uint32_t& mid, uint32_t& hi, uint32_t& lo) {
+  const float v[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
+  mid = hi = lo = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (MODE == MODE_NONZERO) {
+      mid |= (v[c] != 0.0f ? 1u : 0u) << c;
+    } else {
+      mid |= gt_bit(v[c], th.mid) << c;
+      if (MODE == MODE_THRESH3) {
+        hi |= gt_bit(v[c], th.hi) << c;
+        lo |= gt_bit(v[c], th.lo) << c;
+      }
+    }
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void vec_bits(const uint4& raw, const Thresholds& th, __nv_bfloat16, uint32_t& mid, uint32_t& hi, uint32_t& lo) {
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  mid = hi = lo = 0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    // bf16 -> fp32 is exact: the 16 bits are the high half of the fp32 pattern
+    const float x = __uint_as_float((c & 1) ? (w[c >> 1] & 0xffff0000u) : (w[c >> 1] << 16));
+    if (MODE == MODE_NONZERO) {
+      mid |= (x != 0.0f ? 1u : 0u) << c;
+    } else {
+      mid |= gt_bit(x, th.mid) << c;
+      if (MODE == MODE_THRESH3) {
+        hi |= gt_bit(x, th.hi) << c;
+        lo |= gt_bit(x, th.lo) << c;
+      }
+    }
+  }
+}
+
+// 4 bytes -> 4 bits "byte != 0" (byte k -> bit k).
+__device__ __forceinline__ uint32_t nonzero_bytes4(uint32_t w) {
+  const uint32_t m = __vcmpne4(w, 0u) & 0x01010101u;
+  return (m * 0x01020408u) >> 24;
+}
+__device__ __forceinline__ uint32_t gt_bytes4(uint32_t w, uint32_t thr_rep) {
+  const uint32_t m = __vcmpgtu4(w, thr_rep) & 0x01010101u;
+  return (m * 0x01020408u) >> 24;
+}
+
+template <int MODE>
+__device__ __forceinline__ void vec_bits(const uint4& raw, const Thresholds& th, uint8_t, uint32_t& mid, uint32_t& hi, uint32_t& lo) {
+  hi = lo = 0;
+  if (MODE == MODE_NONZERO) {
+    mid = nonzero_bytes4(raw.x) | (nonzero_bytes4(raw.y) << 4) | (nonzero_bytes4(raw.z) << 8) | (nonzero_bytes4(raw.w) << 12);
+  } else {
+    // u8 "logits": integer compare against floor(threshold), clamped to [0,255]; x > t  <=>  x > floor(t) for integers x
+    const int ti = th.mid < 0.f ? -1 : (th.mid >= 255.f ? 255 : (int)floorf(th.mid));
+    if (ti < 0) { mid = 0xffffu; return; }
+    const uint32_t rep = 0x01010101u * (uint32_t)ti;
+    mid = gt_bytes4(raw.x, rep) | (gt_bytes4(raw.y, rep) << 4) | (gt_bytes4(raw.z, rep) << 8) | (gt_bytes4(raw.w, rep) << 12);
+  }
+}
+
+// ---- L x L slot transpose inside groups of L lanes -----------------------------------------------------------
+template <int E>
+__host__ __device__ constexpr uint32_t keep_mask(int d) {
+  uint32_t m = 0;
+  const uint32_t slot = (E >= 32) ? 0xffffffffu : ((1u << E) - 1u);
+  for (int j = 0; j < 32 / E; ++j)
+    if (!(j & d)) m |= slot << (E * j);
+  return m;
+}
+
+template <int E>
+__device__ __forceinline__ uint32_t transpose_slots(uint32_t x, int lane) {
+  constexpr int L = 32 / E;
+#pragma unroll
+  for (int d = L / 2; d >= 1; d >>= 1) {
+    const uint32_t lo = keep_mask<E>(d);
+    const uint32_t v = __shfl_xor_sync(FULL, x, d);
+    x = (lane & d) ? ((x & ~lo) | ((v >> (E * d)) & lo)) : ((x & lo) | ((v << (E * d)) & ~lo));
+  }
+  return x;
+}
+
+// ---- flat kernel ---------------------------------------------------------------------------------------------
+constexpr int K1_THREADS = 256;
+constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int K1_CHUNK_PX = 1024;
+constexpr int K1_CHUNKS_PER_CTA = 32;
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(K1_THREADS)
+pack_flat_kernel(const T* __restrict__ in, int frame_px, int ctas_per_frame, Thresholds th,
+                 uint32_t* __restrict__ packed, int* __restrict__ cnt_hi, int* __restrict__ cnt_mid, int* __restrict__ cnt_lo) {
+  constexpr int E = ElemTraits<T>::E;
+  constexpr int L = 32 / E;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long frame = blockIdx.x / ctas_per_frame;
+  const int cta = blockIdx.x - (int)(frame * ctas_per_frame);
+  const int n_chunks = (frame_px + K1_CHUNK_PX - 1) / K1_CHUNK_PX;
+  const int c_begin = (int)((long long)cta * n_chunks / ctas_per_frame);
+  const int c_end = (int)((long long)(cta + 1) * n_chunks / ctas_per_frame);
+  const T* src = in + frame * (long long)frame_px;
+  uint32_t* dst = packed ? packed + frame * (long long)(frame_px >> 5) : nullptr;
+  const int frame_words = frame_px >> 5;
+  const int out_word_in_chunk = E * (lane % L) + lane / L;
+
+  int n_mid = 0, n_hi = 0, n_lo = 0;
+  for (int c = c_begin + warp; c < c_end; c += K1_WARPS) {
+    const int px0 = c * K1_CHUNK_PX;
+    uint4 raw[L];
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      const int px = px0 + E * (j * 32 + lane);
+      raw[j] = (px < frame_px) ? ld_stream_u4(src + px) : make_uint4(0, 0, 0, 0);
+    }
+    uint32_t xm = 0, xh = 0, xl = 0;
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+      uint32_t m, h, l;
+      vec_bits<MODE>(raw[j], th, T(), m, h, l);
+      // out-of-frame vectors were loaded as zeros; a zero passes a negative threshold, so mask them out
+      const bool inside = px0 + E * (j * 32 + lane) < frame_px;
+      if (!inside) m = h = l = 0;
+      xm |= m << (E * j);
+      if (MODE == MODE_THRESH3) { xh |= h << (E * j); xl |= l << (E * j); }
+    }
+    n_mid += __popc(xm);
+    if (MODE == MODE_THRESH3) { n_hi += __popc(xh); n_lo += __popc(xl); }
+    if (dst) {
+      const uint32_t word = transpose_slots<E>(xm, lane);
+      const int wi = (px0 >> 5) + out_word_in_chunk;
+      if (wi < frame_words) dst[wi] = word;
+    }
+  }
+
+  __shared__ int red[3][K1_WARPS];
+  n_mid = warp_sum(n_mid);
+  if (MODE == MODE_THRESH3) { n_hi = warp_sum(n_hi); n_lo = warp_sum(n_lo); }
+  if (lane == 0) { red[0][warp] = n_mid; red[1][warp] = n_hi; red[2][warp] = n_lo; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    int s = 0;
+#pragma unroll
+    for (int w = 0; w < K1_WARPS; ++w) s += red[threadIdx.x][w];
+    int* out = threadIdx.x == 0 ? cnt_mid : (threadIdx.x == 1 ? cnt_hi : cnt_lo);
+    if (out && (threadIdx.x == 0 || MODE == MODE_THRESH3) && s) atomicAdd(out + frame, s);
+  }
+}
+
+// ---- per-row kernel (any W, any alignment): one warp per image row, ballot per 32 pixels ---------------------
+template <typename T> __device__ __forceinline__ float load_as_float(const T* p);
+template <> __device__ __forceinline__ float load_as_float<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __uint_as_float(((uint32_t) __ldg(reinterpret_cast<const unsigned short*>(p))) << 16);
+}
+template <> __device__ __forceinline__ float load_as_float<uint8_t>(const uint8_t* p) { return (float)__ldg(p); }
+
+constexpr int ROWS_PER_CTA = 8;
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(ROWS_PER_CTA * 32)
+pack_rows_kernel(const T* __restrict__ in, int H, int W, int row_blocks, Thresholds th,
+                 uint32_t* __restrict__ packed, int* __restrict__ cnt_hi, int* __restrict__ cnt_mid, int* __restrict__ cnt_lo) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long frame = blockIdx.x / row_blocks;
+  const int row = (blockIdx.x - (int)(frame * row_blocks)) * ROWS_PER_CTA + warp;
+  const int Wp = (W + 31) >> 5;
+  int n_mid = 0, n_hi = 0, n_lo = 0;
+  if (row < H) {
+    const T* src = in + (frame * H + row) * (long long)W;
+    uint32_t* dst = packed ? packed + (frame * H + row) * (long long)Wp : nullptr;
+    for (int w0 = 0; w0 < Wp; w0 += 4) {
+      float v[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int x = (w0 + u) * 32 + lane;
+        ok[u] = x < W;
+        v[u] = ok[u] ? load_as_float(src + x) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (w0 + u >= Wp) break;                       // warp-uniform
+        const bool pm = ok[u] && (MODE == MODE_NONZERO ? (v[u] != 0.f) : (v[u] > th.mid));
+        const uint32_t bm = __ballot_sync(FULL, pm);
+        n_mid += __popc(bm);
+        if (MODE == MODE_THRESH3) {
+          n_hi += __popc(__ballot_sync(FULL, ok[u] && v[u] > th.hi));
+          n_lo += __popc(__ballot_sync(FULL, ok[u] && v[u] > th.lo));
+        }
+        if (dst && lane == u) dst[w0 + u] = bm;
+      }
+    }
+  }
+  // counts are warp-uniform here (every lane saw the same ballots)
+  __shared__ int red[3][ROWS_PER_CTA];
+  if (lane == 0) { red[0][warp] = n_mid; red[1][warp] = n_hi; red[2][warp] = n_lo; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    int s = 0;
+#pragma unroll
+    for (int w = 0; w < ROWS_PER_CTA; ++w) s += red[threadIdx.x][w];
+    int* out = threadIdx.x == 0 ? cnt_mid : (threadIdx.x == 1 ? cnt_hi : cnt_lo);
+    if (out && (threadIdx.x == 0 || MODE == MODE_THRESH3) && s) atomicAdd(out + frame, s);
+  }
+}
+
+template <typename T, int MODE>
+static int launch_pack(const T* in, long long n_frames, int H, int W, Thresholds th, uint32_t* packed,
+                       int* cnt_hi, int* cnt_mid, int* cnt_lo, cudaStream_t stream) {
+  SOLA_REQUIRE(in != nullptr, "pack: input pointer is null");
+  SOLA_REQUIRE(n_frames >= 0 && H > 0 && W > 0, "pack: bad shape n_frames=%lld H=%d W=%d", n_frames, H, W);
+  SOLA_REQUIRE((long long)H * W < (1ll << 31), "pack: frame larger than 2^31 pixels");
+  if (n_frames == 0) return SOLA_OK;
+  if (cnt_mid) SOLA_CUDA(cudaMemsetAsync(cnt_mid, 0, sizeof(int) * n_frames, stream));
+  if (MODE == MODE_THRESH3) {
+    if (cnt_hi) SOLA_CUDA(cudaMemsetAsync(cnt_hi, 0, sizeof(int) * n_frames, stream));
+    if (cnt_lo) SOLA_CUDA(cudaMemsetAsync(cnt_lo, 0, sizeof(int) * n_frames, stream));
+  }
+  const int frame_px = H * W;
+  const bool flat = (W % 32 == 0) && aligned16(in);
+  if (flat) {
+    const int n_chunks = (frame_px + K1_CHUNK_PX - 1) / K1_CHUNK_PX;
+    const int ctas_per_frame = (n_chunks + K1_CHUNKS_PER_CTA - 1) / K1_CHUNKS_PER_CTA;
+    const long long grid = n_frames * ctas_per_frame;
+    SOLA_REQUIRE(grid < (1ll << 31), "pack: grid too large (%lld CTAs); split the batch", grid);
+    pack_flat_kernel<T, MODE><<<(unsigned)grid, K1_THREADS, 0, stream>>>(in, frame_px, ctas_per_frame, th, packed, cnt_hi, cnt_mid, cnt_lo);
+  } else {
+    const int row_blocks = (H + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+    const long long grid = n_frames * row_blocks;
+    SOLA_REQUIRE(grid < (1ll << 31), "pack: grid too large (%lld CTAs); split the batch", grid);
+    pack_rows_kernel<T, MODE><<<(unsigned)grid, ROWS_PER_CTA * 32, 0, stream>>>(in, H, W, row_blocks, th, packed, cnt_hi, cnt_mid, cnt_lo);
+  }
+  return check_launch("pack kernel");
+}
+
+// ---- unpack: packed (n, H, Wp) -> fp32 / u8 {0,1} planes (drop-in return types) ------------------------------
+// warp-cooperative variant: each warp takes one word at a time, lane b writes pixel b (coalesced 128 B fp32 stores)
+template <typename T>
+__global__ void __launch_bounds__(256)
+unpack_warp_kernel(const uint32_t* __restrict__ packed, long long n_rows, int W, int Wp, T* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long total_words = n_rows * Wp;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long base = warp0 * 32; base < total_words; base += n_warps * 32) {
+    const long long mine = base + lane;
+    const uint32_t my_bits = mine < total_words ? packed[mine] : 0u;
+    const int n_here = (int)min(32ll, total_words - base);
+    for (int k = 0; k < n_here; ++k) {
+      const uint32_t bits = __shfl_sync(FULL, my_bits, k);
+      const long long wi = base + k;
+      const long long row = wi / Wp;
+      const int w = (int)(wi - row * Wp);
+      const int x = w * 32 + lane;
+      if (x < W) out[row * W + x] = (T)((bits >> lane) & 1u);
+    }
+  }
+}
+
+template <typename T>
+static int launch_unpack(const uint32_t* packed, long long n_frames, int H, int W, T* out, cudaStream_t stream) {
+  SOLA_REQUIRE(packed && out, "unpack: null pointer");
+  SOLA_REQUIRE(n_frames >= 0 && H > 0 && W > 0, "unpack: bad shape");
+  if (n_frames == 0) return SOLA_OK;
+  const int Wp = (W + 31) >> 5;
+  const long long n_rows = n_frames * H;
+  const long long warps_needed = (n_rows * Wp + 31) / 32;
+  long long blocks = (warps_needed + 7) / 8;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  unpack_warp_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(packed, n_rows, W, Wp, out);
+  return check_launch("unpack kernel");
+}
+
+}  // namespace sola
+
+using namespace sola;
+
+static Thresholds make_thresholds(double thr, double off) {
+  // numpy compares float32 arrays against the Python scalar cast to float32 (prompt_generator.py:177,182)
+  Thresholds t;
+  t.mid = (float)thr;
+  t.hi = (float)(thr + off);
+  t.lo = (float)(thr - off);
+  return t;
+}
+
+extern "C" {
+
+int sola_binarize_pack_f32(const float* logits, long long n_frames, int H, int W, double thr, double off,
+                           uint32_t* packed_out, int* cnt_hi, int* cnt_mid, int* cnt_lo, cudaStream_t stream) {
+  return launch_pack<float, MODE_THRESH3>(logits, n_frames, H, W, make_thresholds(thr, off), packed_out, cnt_hi, cnt_mid, cnt_lo, stream);
+}
+
+int sola_binarize_pack_bf16(const void* logits, long long n_frames, int H, int W, double thr, double off,
+                            uint32_t* packed_out, int* cnt_hi, int* cnt_mid, int* cnt_lo, cudaStream_t stream) {
+  return launch_pack<__nv_bfloat16, MODE_THRESH3>(reinterpret_cast<const __nv_bfloat16*>(logits), n_frames, H, W,
+                                                  make_thresholds(thr, off), packed_out, cnt_hi, cnt_mid, cnt_lo, stream);
+}
+
+int sola_threshold_pack_f32(const float* x, long long n_frames, int H, int W, double thr,
+                            uint32_t* packed_out, int* area, cudaStream_t stream) {
+  return launch_pack<float, MODE_THRESH1>(x, n_frames, H, W, make_thresholds(thr, 0.0), packed_out, nullptr, area, nullptr, stream);
+}
+
+int sola_pack_mask_f32(const float* mask, long long n_frames, int H, int W, uint32_t* packed_out, int* area, cudaStream_t stream) {
+  return launch_pack<float, MODE_NONZERO>(mask, n_frames, H, W, Thresholds{0, 0, 0}, packed_out, nullptr, area, nullptr, stream);
+}
+
+int sola_pack_mask_u8(const uint8_t* mask, long long n_frames, int H, int W, uint32_t* packed_out, int* area, cudaStream_t stream) {
+  return launch_pack<uint8_t, MODE_NONZERO>(mask, n_frames, H, W, Thresholds{0, 0, 0}, packed_out, nullptr, area, nullptr, stream);
+}
+
+int sola_unpack_f32(const uint32_t* packed, long long n_frames, int H, int W, float* out, cudaStream_t stream) {
+  return launch_unpack<float>(packed, n_frames, H, W, out, stream);
+}
+
+int sola_unpack_u8(const uint32_t* packed, long long n_frames, int H, int W, uint8_t* out, cudaStream_t stream) {
+  return launch_unpack<uint8_t>(packed, n_frames, H, W, out, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,257 @@
+// K2 — AND-popcount pairwise mask IoU on bit-packed tracks.
+//
+//   sola_pair_iou_st      full spatio-temporal N x N intersection matrix; semantics of
+//                         seg_utils.compute_masklet_iou (track_generation/seg_utils.py:110-125) for every pair,
+//                         with exact int64 counts instead of the reference's fp32 sums.
+//   sola_pair_iou_gather  the matrix the reference greedy actually walks (generate_tokens_grid.py:266-278,
+//                         generate_tokens_gdino.py:288-300): inter[i][j] = |track_i[frame_idx[j]] ∩ prompt_j|.
+//
+// The N x N kernel is integer-pipe bound for N >~ 16 (each word is used by N-1 pairs), so it is organised like a
+// register-tiled GEMM whose multiply-add is LOP3+POPC+IADD:
+//   * a CTA owns one 64 x 64 tile of pairs and a contiguous range of the word (k) axis; K-ranges are split so
+//     that the grid fills every SM several times even when N = 64 gives a single tile;
+//   * rows are staged global -> shared with 16-byte cp.async in a 4-stage ring, stored k-quad-major
+//     ([k/4][row] uint4) so that the 16 lanes that read 16 consecutive rows hit 16 distinct bank groups;
+//   * each of the 256 threads accumulates a strided 4 x 4 micro-tile (rows ty+16r, cols tx+16r) in int32
+//     registers; diagonal tiles stage their 64 rows once and skip the strictly-lower micro-tile entries;
+//   * partial sums leave the CTA as 64-bit atomics on the N x N output (a few hundred adds per address).
+#include "common.cuh"
+
+namespace sola {
+
+constexpr int PT = 64;            // tile side (tracks)
+constexpr int KQ = 8;             // uint4 per row per stage -> 32 words = 128 B per row per stage
+constexpr int STAGE_WORDS = KQ * 4;
+constexpr int NSTAGE = 4;
+constexpr int ST_THREADS = 256;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+__device__ __forceinline__ int popc4_and(const uint4& a, const uint4& b) {
+  return __popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w);
+}
+
+// tile list: (ti, tj) with ti <= tj, enumerated row-major over the upper triangle
+__device__ __forceinline__ void tile_from_index(int idx, int nt, int& ti, int& tj) {
+  int i = 0;
+  while (idx >= nt - i) { idx -= nt - i; ++i; }
+  ti = i; tj = i + idx;
+}
+
+template <bool DIAG>
+__device__ __forceinline__ void st_tile_body(const uint32_t* __restrict__ packed, int N, long long words, int ti, int tj,
+                                             long long s_begin, long long s_end, uint4* smem,
+                                             unsigned long long* __restrict__ inter) {
+  constexpr int ROWS = DIAG ? PT : 2 * PT;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  int acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0;
+
+  // stage loader: ROWS*KQ 16-byte copies, thread t copies (row = c / KQ, q = c % KQ) for c = t, t+256, ...
+  auto issue = [&](long long stage, int buf) {
+    uint4* dst = smem + (size_t)buf * (2 * PT) * KQ;
+    const long long w0 = stage * STAGE_WORDS;
+#pragma unroll
+    for (int c = tid; c < ROWS * KQ; c += ST_THREADS) {
+      const int row = c / KQ, q = c % KQ;
+      const int track = (row < PT) ? ti * PT + row : tj * PT + (row - PT);
+      const long long w = w0 + q * 4;
+      long long remain = (words - w) * 4;               // bytes left in this track row
+      int nbytes = (track < N && remain > 0) ? (int)(remain < 16 ? remain : 16) : 0;
+      const uint32_t* src = packed + (long long)(track < N ? track : 0) * words + (nbytes ? w : 0);
+      cp_async16(dst + q * ROWS + row, src, nbytes);
+    }
+  };
+
+  const long long n_st = s_end - s_begin;
+#pragma unroll
+  for (int p = 0; p < NSTAGE - 1; ++p) {
+    if (p < n_st) issue(s_begin + p, p);
+    cp_async_commit();
+  }
+  for (long long s = 0; s < n_st; ++s) {
+    cp_async_wait<NSTAGE - 2>();
+    __syncthreads();
+    if (s + NSTAGE - 1 < n_st) issue(s_begin + s + NSTAGE - 1, (int)((s + NSTAGE - 1) % NSTAGE));
+    cp_async_commit();
+    const uint4* buf = smem + (size_t)(s % NSTAGE) * (2 * PT) * KQ;
+#pragma unroll
+    for (int q = 0; q < KQ; ++q) {
+      uint4 a[4], b[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        a[r] = buf[q * ROWS + ty + 16 * r];
+        b[r] = buf[q * ROWS + (DIAG ? 0 : PT) + tx + 16 * r];
+      }
+#pragma unroll
+      for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+        for (int rj = 0; rj < 4; ++rj) {
+          if (DIAG && rj < ri) continue;               // mirror entry is produced by another (ri, rj)
+          acc[ri][rj] += popc4_and(a[ri], b[rj]);
+        }
+    }
+  }
+  cp_async_wait<0>();
+
+#pragma unroll
+  for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+    for (int rj = 0; rj < 4; ++rj) {
+      if (DIAG && rj < ri) continue;
+      const int i = ti * PT + ty + 16 * ri, j = tj * PT + tx + 16 * rj;
+      if (i >= N || j >= N) continue;
+      if (DIAG && ri == rj && tx < ty) continue;       // lower half of the 16x16 diagonal blocks
+      const unsigned long long v = (unsigned long long)acc[ri][rj];
+      if (v == 0) continue;
+      atomicAdd(inter + (long long)i * N + j, v);
+      if (i != j) atomicAdd(inter + (long long)j * N + i, v);
+    }
+}
+
+__global__ void __launch_bounds__(ST_THREADS)
+pair_iou_st_kernel(const uint32_t* __restrict__ packed, int N, long long words, int nt, int n_tiles, int splits,
+                   unsigned long long* __restrict__ inter) {
+  extern __shared__ uint4 smem_st[];
+  const int tile = blockIdx.x % n_tiles, split = blockIdx.x / n_tiles;
+  int ti, tj;
+  tile_from_index(tile, nt, ti, tj);
+  const long long stages = (words + STAGE_WORDS - 1) / STAGE_WORDS;
+  const long long s_begin = stages * split / splits, s_end = stages * (split + 1) / splits;
+  if (ti == tj) st_tile_body<true>(packed, N, words, ti, tj, s_begin, s_end, smem_st, inter);
+  else st_tile_body<false>(packed, N, words, ti, tj, s_begin, s_end, smem_st, inter);
+}
+
+// Fallback for track rows that are not 16-byte aligned (words % 4 != 0 or odd base): one CTA per pair.
+__global__ void __launch_bounds__(256)
+pair_iou_st_simple_kernel(const uint32_t* __restrict__ packed, int N, long long words, unsigned long long* __restrict__ inter) {
+  const int i = blockIdx.y, j = blockIdx.x;
+  if (j < i) return;
+  const uint32_t* a = packed + (long long)i * words;
+  const uint32_t* b = packed + (long long)j * words;
+  unsigned long long acc = 0;
+  for (long long w = threadIdx.x; w < words; w += blockDim.x) acc += __popc(a[w] & b[w]);
+  __shared__ unsigned long long red[8];
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(FULL, acc, d);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long s = 0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    inter[(long long)i * N + j] = s;
+    inter[(long long)j * N + i] = s;
+  }
+}
+
+// ---- gathered single-frame IoU ------------------------------------------------------------------------------
+constexpr int GT_TILE = 4;   // tracks per CTA
+
+__global__ void __launch_bounds__(128)
+pair_iou_gather_kernel(const uint32_t* __restrict__ tracks, const uint32_t* __restrict__ prompts, const int* __restrict__ frame_idx,
+                       int N, int P, int T, int FW, int* __restrict__ inter, int* __restrict__ area_t, int* __restrict__ area_p) {
+  const int j = blockIdx.x, i0 = blockIdx.y * GT_TILE;
+  int f = frame_idx[j];
+  f = f < 0 ? 0 : (f >= T ? T - 1 : f);
+  const uint32_t* pp = prompts + (long long)j * FW;
+  const uint32_t* pt[GT_TILE];
+#pragma unroll
+  for (int k = 0; k < GT_TILE; ++k) pt[k] = tracks + ((long long)min(i0 + k, N - 1) * T + f) * FW;
+  int ni[GT_TILE] = {0, 0, 0, 0}, na[GT_TILE] = {0, 0, 0, 0}, np = 0;
+  for (int w = threadIdx.x; w < FW; w += blockDim.x) {
+    const uint32_t p = pp[w];
+    np += __popc(p);
+#pragma unroll
+    for (int k = 0; k < GT_TILE; ++k) {
+      const uint32_t t = pt[k][w];
+      ni[k] += __popc(p & t);
+      na[k] += __popc(t);
+    }
+  }
+  __shared__ int red[2 * GT_TILE + 1][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  np = warp_sum(np);
+#pragma unroll
+  for (int k = 0; k < GT_TILE; ++k) { ni[k] = warp_sum(ni[k]); na[k] = warp_sum(na[k]); }
+  if (lane == 0) {
+    red[2 * GT_TILE][warp] = np;
+#pragma unroll
+    for (int k = 0; k < GT_TILE; ++k) { red[k][warp] = ni[k]; red[GT_TILE + k][warp] = na[k]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * GT_TILE + 1) {
+    const int k = threadIdx.x;
+    const int s = red[k][0] + red[k][1] + red[k][2] + red[k][3];
+    if (k < GT_TILE) {
+      if (i0 + k < N) inter[(long long)(i0 + k) * P + j] = s;
+    } else if (k < 2 * GT_TILE) {
+      if (i0 + k - GT_TILE < N) area_t[(long long)(i0 + k - GT_TILE) * P + j] = s;
+    } else if (blockIdx.y == 0) {
+      area_p[j] = s;
+    }
+  }
+}
+
+}  // namespace sola
+
+using namespace sola;
+
+extern "C" {
+
+int sola_pair_iou_st(const uint32_t* packed, int N, long long words_per_track, long long* inter_out, long long* area_out,
+                     cudaStream_t stream) {
+  SOLA_REQUIRE(packed && inter_out, "pair_iou_st: null pointer");
+  SOLA_REQUIRE(N >= 0 && words_per_track > 0, "pair_iou_st: bad shape N=%d words=%lld", N, words_per_track);
+  if (N == 0) return SOLA_OK;
+  SOLA_CUDA(cudaMemsetAsync(inter_out, 0, sizeof(long long) * (size_t)N * N, stream));
+  const bool fast = (words_per_track % 4 == 0) && aligned16(packed);
+  if (fast) {
+    const int nt = (N + PT - 1) / PT;
+    const int n_tiles = nt * (nt + 1) / 2;
+    const long long stages = (words_per_track + STAGE_WORDS - 1) / STAGE_WORDS;
+    long long splits = ((long long)num_sms() * 4 + n_tiles - 1) / n_tiles;
+    if (splits > stages) splits = stages;
+    const long long min_splits = (stages + (1 << 20) - 1) >> 20;     // keep int32 partial sums below 2^31
+    if (splits < min_splits) splits = min_splits;
+    if (splits < 1) splits = 1;
+    const size_t smem = (size_t)NSTAGE * (2 * PT) * KQ * sizeof(uint4);
+    static bool attr_set = false;
+    if (!attr_set) {
+      SOLA_CUDA(cudaFuncSetAttribute(pair_iou_st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    SOLA_REQUIRE(splits * n_tiles < (1ll << 31), "pair_iou_st: grid too large");
+    pair_iou_st_kernel<<<(unsigned)(splits * n_tiles), ST_THREADS, smem, stream>>>(
+        packed, N, words_per_track, nt, n_tiles, (int)splits, reinterpret_cast<unsigned long long*>(inter_out));
+  } else {
+    SOLA_REQUIRE(N <= 65535, "pair_iou_st: unaligned fallback supports N <= 65535");
+    dim3 grid(N, N);
+    pair_iou_st_simple_kernel<<<grid, 256, 0, stream>>>(packed, N, words_per_track, reinterpret_cast<unsigned long long*>(inter_out));
+  }
+  int rc = check_launch("pair_iou_st kernel");
+  if (rc != SOLA_OK) return rc;
+  if (area_out)   // area[i] = inter[i][i]; strided device-to-device copy of the diagonal
+    SOLA_CUDA(cudaMemcpy2DAsync(area_out, sizeof(long long), inter_out, sizeof(long long) * ((size_t)N + 1), sizeof(long long), N,
+                                cudaMemcpyDeviceToDevice, stream));
+  return SOLA_OK;
+}
+
+int sola_pair_iou_gather(const uint32_t* tracks, const uint32_t* prompts, const int* frame_idx, int N, int P, int T,
+                         long long frame_words, int* inter, int* area_t, int* area_p, cudaStream_t stream) {
+  SOLA_REQUIRE(tracks && prompts && frame_idx && inter && area_t && area_p, "pair_iou_gather: null pointer");
+  SOLA_REQUIRE(N >= 0 && P >= 0 && T > 0 && frame_words > 0 && frame_words < (1ll << 26), "pair_iou_gather: bad shape");
+  if (N == 0 || P == 0) return SOLA_OK;
+  SOLA_REQUIRE((N + GT_TILE - 1) / GT_TILE <= 65535, "pair_iou_gather: too many tracks for one launch");
+  dim3 grid(P, (N + GT_TILE - 1) / GT_TILE);
+  pair_iou_gather_kernel<<<grid, 128, 0, stream>>>(tracks, prompts, frame_idx, N, P, T, (int)frame_words, inter, area_t, area_p);
+  return check_launch("pair_iou_gather kernel");
+}
+
+}  // extern "C"

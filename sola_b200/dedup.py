@@ -1,0 +1,230 @@
+"""Greedy `miou_thresh` track de-duplication — the filtering logic of `generate_tokens_grid.py` and
+`generate_tokens_gdino.py`, with SAM2 propagation left to the caller.
+
+Two layers:
+  * `GreedyState` — pure host logic (no GPU): candidate selection, batching rules and in-order suppression, a
+    restatement of generate_tokens_grid.py:133-139,148-195,266-278,287-292 and
+    generate_tokens_gdino.py:155-206,288-300,311-313.  It consumes rows of the gathered IoU matrix.
+  * `TrackDedup` — the device session: prompt masks are nearest-resized and bit-packed ONCE (the reference redoes
+    the H2D copy + resize for every (tracked, remaining) pair, generate_tokens_grid.py:271-272); every tracked batch
+    is binarised/packed (K1), bilinear-resized (R1) and compared against all prompts in one launch (K2 gather);
+    one small D2H per batch feeds `GreedyState`.
+Also `dedup_matrix` — the spatio-temporal N x N variant (seg_utils.compute_masklet_iou semantics) that BASELINE
+configs 2 and 5 name.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import packed as P
+
+NOT_TRACKED, TRACKED, FILTERED, NOT_USED = 0, 1, 2, 3      # generate_tokens_grid.py:136
+
+
+class GreedyState:
+    """Host-side state machine.  `prompts`: list of dicts with at least prompt_id, frame_idx (and, for mode
+    'gdino', expression_id and stability_score), in file order (area-descending, generate_prompts_grid.py:131-133)."""
+
+    def __init__(self, prompts: Sequence[dict], n_frames: int, *, mode: str = "grid", bin_size: int = 4,
+                 n_max_tracks: Optional[int] = None, batch_size: int = 4, miou_thresh: float = 0.7,
+                 stability_score_thresh: float = 0.85, expression_id=None):
+        assert mode in ("grid", "gdino")
+        self.mode = mode
+        self.n_frames = n_frames
+        self.bin_size = bin_size
+        self.n_max_tracks = n_max_tracks if n_max_tracks is not None else (64 if mode == "grid" else 16)
+        self.batch_size = batch_size
+        self.miou_thresh = miou_thresh
+        self.n_tracked = self.n_filtered = self.n_not_used = 0
+        self.batches: List[List] = []
+        self.filtered_by: Dict = {}
+        self.filtered_iou: Dict = {}
+        # candidate list (indices into `prompts`) and per-prompt status
+        self.prompts = list(prompts)
+        self.status = np.full(len(self.prompts), NOT_USED, dtype=np.int8)
+        self.members: List[int] = []          # prompts taking part in batching / suppression, in order
+        for k, p in enumerate(self.prompts):
+            if mode == "grid":
+                # every prompt of the video takes part; off-bin ones are marked not-used (grid :134-139)
+                self.members.append(k)
+                if p["frame_idx"] % bin_size != 0:
+                    self.n_not_used += 1
+                else:
+                    self.status[k] = NOT_TRACKED
+            else:
+                if p["expression_id"] != expression_id:
+                    continue
+                # gdino :162 — `score < thresh` is False for NaN and for score == thresh: both are kept
+                if p["frame_idx"] % bin_size != 0 or p["stability_score"] < stability_score_thresh:
+                    self.n_not_used += 1
+                else:
+                    self.status[k] = NOT_TRACKED
+                    self.members.append(k)
+        self.frame_idx = np.array([p["frame_idx"] for p in self.prompts], dtype=np.int64)
+
+    # -- batching ------------------------------------------------------------------------------------------------
+    def next_batch(self) -> Optional[List[int]]:
+        """Indices (into `prompts`) of the next same-frame batch to hand to SAM2, or None when finished.
+        Members are marked tracked immediately, so batch-mates never suppress each other."""
+        if self.n_tracked >= self.n_max_tracks:
+            return None
+        cap = 2 if self.n_frames > 200 else self.batch_size
+        frame, batch = None, []
+        for k in self.members:
+            if self.status[k] != NOT_TRACKED:
+                continue
+            if frame is None:
+                frame = self.frame_idx[k]
+            elif self.frame_idx[k] != frame:
+                if self.mode == "grid":
+                    continue                               # grid :178-179 keeps scanning the whole list
+                break                                      # gdino :194-196 stops at the first other-frame candidate
+            batch.append(k)
+            self.status[k] = TRACKED
+            if self.mode == "grid":
+                if len(batch) >= cap or self.n_tracked + len(batch) >= self.n_max_tracks:       # grid :181-186
+                    break
+            else:
+                self.n_tracked += 1                        # gdino :187,193 — counted at append time
+                if self.n_frames > 200 and len(batch) >= 2:
+                    break
+                if len(batch) >= self.batch_size:
+                    break
+                if len(batch) + self.n_tracked >= self.n_max_tracks:                            # gdino :201 (double count)
+                    break
+        if frame is None:
+            return None
+        if self.mode == "grid":
+            self.n_tracked += len(batch)                   # grid :194
+        self.batches.append([self.prompts[k]["prompt_id"] for k in batch])
+        return batch
+
+    # -- suppression -----------------------------------------------------------------------------------------------
+    def apply_iou_rows(self, batch: Sequence[int], iou_rows: np.ndarray) -> int:
+        """iou_rows[b, k] = IoU(resized track of batch[b] at frame_idx[k], nearest-resized prompt k) for every
+        prompt k (float64).  Walks batch members in order and candidates in list order, strict `>` (grid :266-278)."""
+        n = 0
+        for b, member in enumerate(batch):
+            row = iou_rows[b]
+            member_id = self.prompts[member]["prompt_id"]
+            for k in self.members:
+                if self.status[k] != NOT_TRACKED:
+                    continue
+                if row[k] > self.miou_thresh:
+                    self.status[k] = FILTERED
+                    pid = self.prompts[k]["prompt_id"]
+                    self.filtered_by[pid] = member_id
+                    self.filtered_iou[pid] = float(row[k])
+                    n += 1
+        self.n_filtered += n
+        return n
+
+    def result(self) -> dict:
+        ids = lambda s: [self.prompts[k]["prompt_id"] for k in self.members if self.status[k] == s]
+        res = {
+            "status": {self.prompts[k]["prompt_id"]: int(self.status[k]) for k in self.members},
+            "tracked": ids(TRACKED), "filtered": ids(FILTERED), "not_tracked": ids(NOT_TRACKED),
+            # gdino :311 lists status==3 among the *candidates*, which is empty by construction
+            "not_used": ids(NOT_USED) if self.mode == "grid" else [],
+            "batches": self.batches, "n_tracked": self.n_tracked, "n_filtered": self.n_filtered,
+            "n_not_used": self.n_not_used,
+            "filtered_by": dict(self.filtered_by), "filtered_iou": dict(self.filtered_iou),
+        }
+        if self.mode == "grid" and len(res["tracked"]) < self.n_max_tracks:
+            assert not res["not_tracked"], f"NOT TRACKED PROMPT MASKS ARE FOUND: {res['not_tracked']}"     # grid :291-292
+        return res
+
+
+def iou_from_counts(inter, area_a, area_b) -> np.ndarray:
+    """float64 inter/union with the reference's empty rule (union == 0 -> 1.0, seg_utils.py:139-140)."""
+    inter = np.asarray(inter, dtype=np.int64)
+    union = np.asarray(area_a, dtype=np.int64) + np.asarray(area_b, dtype=np.int64) - inter
+    with np.errstate(divide="ignore", invalid="ignore"):
+        iou = inter / union
+    return np.where(union == 0, 1.0, iou)
+
+
+class TrackDedup:
+    """Device session around `GreedyState` for one video (grid) or one expression (gdino).
+
+    prompts[k]['segmentation'] is the decoded (H, W) uint8 prompt mask.  Typical loop:
+
+        dd = TrackDedup(prompts, n_frames, mode='grid')
+        while (batch := dd.next_batch()) is not None:
+            logits = sam2_propagate([dd.prompts[k] for k in batch])      # (B, T, H, W) fp32, stays on the GPU
+            packed, counts = dd.submit_logits(batch, logits)             # K1 + R1 + K2-gather + suppression
+        result = dd.result()
+    """
+
+    def __init__(self, prompts: Sequence[dict], n_frames: int, *, device=None, target_shape=None,
+                 prompt_masks: Optional[torch.Tensor] = None, **rules):
+        """`prompt_masks`: optional (P, H, W) uint8 tensor (host or device) holding every prompt's mask in list order;
+        when omitted the masks are taken from prompts[k]['segmentation']."""
+        self.state = GreedyState(prompts, n_frames, **rules)
+        self.prompts = self.state.prompts
+        self.n_frames = n_frames
+        if prompt_masks is None and self.prompts:
+            prompt_masks = np.stack([np.asarray(p["segmentation"]) for p in self.prompts]).astype(np.uint8, copy=False)
+        if prompt_masks is not None and len(prompt_masks):
+            self.device = prompt_masks.device if isinstance(prompt_masks, torch.Tensor) and prompt_masks.is_cuda else P._dev(device)
+            H, W = int(prompt_masks.shape[-2]), int(prompt_masks.shape[-1])
+            self.native_shape = (H, W)
+            self.target_shape = tuple(target_shape) if target_shape is not None else P.default_target_shape(H, W)
+            # R2 hoisted: one H2D of uint8 (1 B/px) and one nearest-resize launch for all prompts of the unit
+            self.prompt_planes = P.resize_nearest(P.to_device(prompt_masks, device=self.device), *self.target_shape)
+            self.frame_idx_dev = P.to_device(self.state.frame_idx.astype(np.int32), device=self.device)
+        else:
+            self.device = P._dev(device)
+            self.native_shape = self.target_shape = None
+            self.prompt_planes = self.frame_idx_dev = None
+
+    def next_batch(self):
+        return self.state.next_batch()
+
+    def submit_logits(self, batch, logits, mask_threshold: float = 0.0, threshold_offset: float = 1.0):
+        """logits (B, T, H, W) fp32/bf16 of the batch members, in batch order.  Returns (native-resolution packed
+        masklets, stability counts) so the caller can RLE-encode / store them."""
+        packed, counts = P.binarize_pack_stability(logits, mask_threshold, threshold_offset)
+        self.submit_packed(batch, packed)
+        return packed, counts
+
+    def submit_masks(self, batch, masklets):
+        """masklets (B, T, H, W) {0,1} fp32 / uint8 (what `torch.cat(...)` holds in the reference, grid :223-225)."""
+        packed = P.pack_masks(masklets)
+        self.submit_packed(batch, packed)
+        return packed
+
+    def submit_packed(self, batch, packed: P.PackedMasks) -> np.ndarray:
+        resized = P.resize_bilinear_bin(packed, self.target_shape)                   # R1 (seg_utils.reshape_masklet)
+        return self.submit_resized(batch, resized)
+
+    def submit_resized(self, batch, resized: P.PackedMasks) -> np.ndarray:
+        c = P.gathered_inter(resized, self.prompt_planes, self.frame_idx_dev).cpu().numpy()     # one D2H per batch
+        rows = iou_from_counts(c[0], c[1], c[2])
+        self.state.apply_iou_rows(batch, rows)
+        return rows
+
+    def result(self) -> dict:
+        return self.state.result()
+
+
+def dedup_matrix(tracks: P.PackedMasks, miou_thresh: float = 0.7):
+    """Spatio-temporal de-duplication of N candidate tracks (BASELINE configs 2 / 5): full N x N IoU from exact
+    integer intersections, then index-order greedy suppression with the same strict `>`.
+    Returns (kept ids, {suppressed: suppressor}, float64 IoU matrix, int64 intersection matrix)."""
+    inter = P.pairwise_inter_matrix(tracks).cpu().numpy()
+    iou = P.iou_matrix_from_inter(inter)
+    n = iou.shape[0]
+    alive = np.ones(n, dtype=bool)
+    by = {}
+    for i in range(n):
+        if not alive[i]:
+            continue
+        hit = np.nonzero(alive[i + 1:] & (iou[i, i + 1:] > miou_thresh))[0] + i + 1
+        alive[hit] = False
+        for j in hit.tolist():
+            by[j] = i
+    return [i for i in range(n) if alive[i]], by, iou, inter

@@ -1,0 +1,193 @@
+"""Drop-in mirror of the J / F part of `evaluator.py` (Evaluator.compute_J, compute_F, compute_JF_metrics).
+
+`F` here is what the reference computes: a volumetric pixel F1 over the whole (T, H, W) masklet
+(evaluator.py:239-247).  The boundary F-measure that BASELINE.json's north-star also names has no reference
+implementation; it is provided separately as `compute_F_boundary` (DAVIS definition, parity unpinned)."""
+from __future__ import annotations
+
+import json
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import packed as P
+
+
+# ---- host formulas over exact integer counts -------------------------------------------------------------------
+
+def J_from_counts(inter, n_pred, n_gt):
+    """evaluator.py:227-237 — mean over frames of inter/union (1.0 for an empty union), numpy float64."""
+    Js = []
+    for i, p, g in zip(np.asarray(inter).tolist(), np.asarray(n_pred).tolist(), np.asarray(n_gt).tolist()):
+        union = p + g - i
+        Js.append(1.0 if union == 0 else i / union)
+    return np.mean(Js)
+
+
+def F_from_counts(inter, n_pred, n_gt) -> float:
+    """evaluator.py:239-247 — tp/fp/fn summed over the volume; 0.0 when tp == 0."""
+    tp = int(np.sum(inter, dtype=np.int64))
+    fp = int(np.sum(n_pred, dtype=np.int64)) - tp
+    fn = int(np.sum(n_gt, dtype=np.int64)) - tp
+    if tp == 0:
+        return 0.0
+    precision = tp / (tp + fp)
+    recall = tp / (tp + fn)
+    return 2 * precision * recall / (precision + recall)
+
+
+def F_boundary_from_counts(n_fg, n_gt, fg_match, gt_match) -> float:
+    """DAVIS boundary F per frame, averaged over frames (oracle/boundary_oracle.py is the spec)."""
+    vals = []
+    for a, b, fm, gm in zip(*(np.asarray(x).tolist() for x in (n_fg, n_gt, fg_match, gt_match))):
+        if a == 0 and b > 0:
+            p, r = 1.0, 0.0
+        elif a > 0 and b == 0:
+            p, r = 0.0, 1.0
+        elif a == 0 and b == 0:
+            p, r = 1.0, 1.0
+        else:
+            p, r = fm / float(a), gm / float(b)
+        vals.append(0.0 if p + r == 0 else 2 * p * r / (p + r))
+    return float(np.mean(vals))
+
+
+# ---- per-call drop-ins -----------------------------------------------------------------------------------------
+
+def jf_counts(pred_masklet, gt_masklet) -> np.ndarray:
+    """(3, T) int32 host array [inter, n_pred, n_gt] for {0,1} masklets (fp32 / uint8; device, CPU or numpy)."""
+    return P.frame_counts(pred_masklet, gt_masklet).cpu().numpy()
+
+
+def compute_J(pred_masklet, gt_masklet):
+    c = jf_counts(pred_masklet, gt_masklet)
+    return J_from_counts(c[0], c[1], c[2])
+
+
+def compute_F(pred_masklet, gt_masklet) -> float:
+    c = jf_counts(pred_masklet, gt_masklet)
+    return F_from_counts(c[0], c[1], c[2])
+
+
+def compute_JF(pred_masklet, gt_masklet):
+    """J and F from ONE pass over the two masklets (the reference reads them 2*T + 8 times)."""
+    c = jf_counts(pred_masklet, gt_masklet)
+    return J_from_counts(c[0], c[1], c[2]), F_from_counts(c[0], c[1], c[2])
+
+
+def compute_F_boundary(pred_masklet, gt_masklet, bound_th: float = 0.008) -> float:
+    pp = pred_masklet if isinstance(pred_masklet, P.PackedMasks) else P.pack_masks(pred_masklet)
+    gp = gt_masklet if isinstance(gt_masklet, P.PackedMasks) else P.pack_masks(gt_masklet)
+    c = P.boundary_counts(pp, gp, bound_th).cpu().numpy()
+    return F_boundary_from_counts(c[0], c[1], c[2], c[3])
+
+
+class JFSweep:
+    """Batched J&F over many (video, expression) units of different shapes: masks are uploaded as uint8 (1 B/px
+    instead of the reference's fp32 4 B/px, evaluator.py:199-200), counted on the device, and read back ONCE.
+
+    add() enqueues; finish() synchronises and returns the per-unit results in insertion order plus the integer
+    accumulators that make multi-GPU reductions bit-reproducible."""
+
+    def __init__(self, device=None, with_boundary: bool = False, bound_th: float = 0.008):
+        self.device = P._dev(device)
+        self.with_boundary = with_boundary
+        self.bound_th = bound_th
+        self._keys, self._counts, self._bcounts = [], [], []
+
+    def add(self, key, pred_masklet, gt_masklet) -> None:
+        """pred_masklet None reproduces evaluator.py:194-197 (J = F = JF = 0)."""
+        self._keys.append(key)
+        if pred_masklet is None:
+            self._counts.append(None)
+            self._bcounts.append(None)
+            return
+        p = P.to_device(pred_masklet, device=self.device)
+        g = P.to_device(gt_masklet, device=self.device)
+        self._counts.append(P.frame_counts(p, g))
+        if self.with_boundary:
+            self._bcounts.append(P.boundary_counts(P.pack_masks(p), P.pack_masks(g), self.bound_th))
+        else:
+            self._bcounts.append(None)
+
+    def finish(self):
+        live = [c for c in self._counts if c is not None]
+        flat = torch.cat(live, dim=1).cpu().numpy() if live else np.zeros((3, 0), np.int32)
+        bflat = None
+        if self.with_boundary:
+            blive = [c for c in self._bcounts if c is not None]
+            bflat = torch.cat(blive, dim=1).cpu().numpy() if blive else np.zeros((4, 0), np.int32)
+        results, pos = [], 0
+        totals = np.zeros(3, dtype=np.int64)
+        for key, c in zip(self._keys, self._counts):
+            if c is None:
+                results.append((key, {"J": 0.0, "F": 0.0, "JF": 0.0}))
+                continue
+            T = c.shape[1]
+            u = flat[:, pos:pos + T]
+            J, F = float(J_from_counts(u[0], u[1], u[2])), float(F_from_counts(u[0], u[1], u[2]))
+            rec = {"J": J, "F": F, "JF": (J + F) / 2}
+            if bflat is not None:
+                b = bflat[:, pos:pos + T]
+                rec["F_boundary"] = F_boundary_from_counts(b[0], b[1], b[2], b[3])
+            totals += u.sum(axis=1, dtype=np.int64)
+            results.append((key, rec))
+            pos += T
+        self._keys, self._counts, self._bcounts = [], [], []
+        return results, totals
+
+
+class Evaluator:
+    """J&F half of the reference `Evaluator` (evaluator.py:174-247) with the same method names.  Model inference
+    (`evaluate`, evaluator.py:54-172) is out of scope: construct this with the `pred_dict` it produced, or graft the
+    three methods onto a reference Evaluator instance."""
+
+    def __init__(self, loader_dict=None, pred_dict=None, eval_output_dir: Optional[str] = None, data_type: str = "valid",
+                 eval_weight_epoch: int = 0, device=None):
+        self.loader_dict = loader_dict
+        self.pred_dict = pred_dict or {}
+        self.eval_output_dir = eval_output_dir
+        self.data_type = data_type
+        self.eval_weight_epoch = eval_weight_epoch
+        self.device = P._dev(device) if torch.cuda.is_available() else device
+        self.metrics = {}
+
+    def compute_J(self, pred_masklet, gt_masklet):
+        return compute_J(pred_masklet, gt_masklet)
+
+    def compute_F(self, pred_masklet, gt_masklet):
+        return compute_F(pred_masklet, gt_masklet)
+
+    def compute_JF_metrics(self):
+        """evaluator.py:174-225 — same traversal order, same JSON schema, same float64 means; masks are counted by
+        the batched sweep, one device read-back per video instead of 2*T + 3 `.item()` per expression."""
+        dataset = self.loader_dict["valid"].dataset
+        JF_dict, Js, Fs, JFs = {}, [], [], []
+        for video_id in self.pred_dict:
+            JF_dict[video_id] = {}
+            dataset.set_video(video_id)
+            sweep = JFSweep(self.device)
+            for expression_id, pred_info in self.pred_dict[video_id].items():
+                gt_masklet = dataset.get_gt_masklet(video_id, expression_id)
+                pred_masklet = dataset.get_sam2_masklet(
+                    video_id=video_id, expression_id=expression_id, preds=pred_info["pred"],
+                    root_types=pred_info["root_type"], prompt_types=pred_info["prompt_type"],
+                    sam2_anno_ids=pred_info["sam2_anno_id"])
+                sweep.add(expression_id, pred_masklet, gt_masklet)
+            results, _ = sweep.finish()
+            for expression_id, rec in results:
+                JF_dict[video_id][expression_id] = {
+                    "expression": self.pred_dict[video_id][expression_id]["expression"],
+                    "J": rec["J"], "F": rec["F"], "JF": rec["JF"],
+                }
+                Js.append(rec["J"]), Fs.append(rec["F"]), JFs.append(rec["JF"])
+        self.metrics["mean_J"] = np.mean(Js)
+        self.metrics["mean_F"] = np.mean(Fs)
+        self.metrics["mean_JF"] = np.mean(JFs)
+        if self.eval_output_dir is not None:
+            path = os.path.join(self.eval_output_dir, f"{self.data_type}_JF_metrics_{self.eval_weight_epoch}epoch.json")
+            with open(path, "w") as f:
+                json.dump(JF_dict, f, indent=4)
+        return JF_dict

@@ -1,0 +1,119 @@
+"""CPU: host-side logic of the product (greedy state machine, count->metric formulas, sharding) against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import greedy_oracle as GO
+from oracle import maskpath_oracle as O
+from sola_b200 import dedup, evaluator, utils, metric, sharding
+from conftest import GREEDY_CASES, greedy_prompts, greedy_table
+
+
+def _oracle_iou_rows(masklets_f32, batch, prompts):
+    """What the device computes per batch, restated with the oracle: IoU(resized track[frame_k], nearest prompt_k)."""
+    rows = np.zeros((len(batch), len(prompts)))
+    for b, k in enumerate(batch):
+        rt = O.reshape_masklet(masklets_f32[k])
+        for j, p in enumerate(prompts):
+            pm = O.resize_prompt_nearest(p["segmentation"], rt.shape[1], rt.shape[2])
+            rows[b, j] = O.compute_mask_iou(rt[p["frame_idx"]], pm)
+    return rows
+
+
+@pytest.mark.parametrize("case", sorted(GREEDY_CASES))
+def test_greedy_state_matches_golden(golden, case):
+    mode, kw, n_frames = GREEDY_CASES[case]
+    masklets, _, _ = greedy_table(golden)
+    mt = torch.from_numpy(masklets).float()
+    for eid in (("0", "1") if mode == "gdino" else (None,)):
+        key = case if eid is None else f"{case}_exp{eid}"
+        exp = golden.greedy[key]
+        prompts = greedy_prompts(golden)
+        st = dedup.GreedyState(prompts, n_frames, mode=mode, bin_size=4, expression_id=eid, **kw)
+        while (batch := st.next_batch()) is not None:
+            st.apply_iou_rows(batch, _oracle_iou_rows(mt, batch, prompts))
+        res = st.result()
+        for k in ("tracked", "filtered", "batches"):
+            assert res[k] == exp[k], (key, k)
+        for k in ("n_tracked", "n_filtered", "n_not_used"):
+            if k in exp:
+                assert res[k] == exp[k], (key, k)
+        if "filtered_by" in exp:
+            assert {str(a): b for a, b in res["filtered_by"].items()} == exp["filtered_by"]
+        if "filtered_iou" in exp:
+            assert {str(a): b for a, b in res["filtered_iou"].items()} == exp["filtered_iou"]      # float64 bit-equal
+
+
+def test_greedy_state_random_tables_vs_oracle():
+    """Random IoU tables (no pixels): the state machine and the restated script loops must agree on every field.
+    The oracle loops are driven through their `impl` hook: a 'masklet' is a (T,1,1) tensor holding the member id, a
+    prompt 'segmentation' is a 1x1 array holding the candidate id, and compute_mask_iou looks the pair up."""
+    rng = np.random.default_rng(7)
+    for trial in range(80):
+        n = int(rng.integers(1, 40))
+        T = int(rng.choice([8, 40, 260]))
+        bin_size = int(rng.choice([1, 4]))
+        frame_idx = rng.integers(0, 5, n) * int(rng.choice([1, 2, 4]))
+        iou = rng.random((n, n))
+        iou[rng.random((n, n)) < 0.1] = 0.7                      # exactly-at-threshold entries must NOT suppress
+        stab = rng.random(n) * 0.3 + 0.7
+        stab[rng.random(n) < 0.1] = np.nan
+        stab[rng.random(n) < 0.1] = 0.85
+        mode = "grid" if trial % 2 == 0 else "gdino"
+        kw = dict(bin_size=bin_size, n_max_tracks=int(rng.choice([3, 16, 64])), batch_size=int(rng.choice([1, 2, 4])), miou_thresh=0.7)
+
+        def mk():
+            return [{"prompt_id": k, "frame_idx": int(frame_idx[k]), "segmentation": np.full((1, 1), k, np.uint8),
+                     "expression_id": "e", "stability_score": float(stab[k])} for k in range(n)]
+
+        class TableImpl:
+            reshape_masklet = staticmethod(lambda m: m)
+            compute_mask_iou = staticmethod(lambda a, b: float(iou[int(a[0, 0]), int(b[0, 0])]))
+
+        track_fn = lambda frame, batch: {p["prompt_id"]: torch.full((32, 1, 1), float(p["prompt_id"])) for p in batch}
+        if mode == "grid":
+            ro = GO.grid_greedy(mk(), T, track_fn, impl=TableImpl, **kw)
+        else:
+            ro = GO.gdino_greedy(mk(), "e", T, track_fn, stability_score_thresh=0.85, impl=TableImpl, **kw)
+        st = dedup.GreedyState(mk(), T, mode=mode, expression_id="e", stability_score_thresh=0.85, **kw)
+        while (batch := st.next_batch()) is not None:
+            st.apply_iou_rows(batch, iou[batch])
+        rs = st.result()
+        for k in ("tracked", "filtered", "batches", "n_tracked", "n_filtered", "filtered_by", "filtered_iou", "not_used"):
+            assert rs[k] == ro[k], (trial, mode, k)
+
+
+def test_count_formulas_match_oracle():
+    rng = np.random.default_rng(11)
+    pred = (rng.random((9, 30, 45)) > 0.5).astype(np.uint8)
+    gt = (rng.random((9, 30, 45)) > 0.4).astype(np.uint8)
+    pred[2] = 0; gt[2] = 0; pred[3] = 0; gt[4] = 0
+    c = O.jf_counts_exact(pred, gt)
+    pt, gtt = torch.from_numpy(pred).float(), torch.from_numpy(gt).float()
+    assert evaluator.J_from_counts(*c) == O.compute_J(pt, gtt)
+    assert evaluator.F_from_counts(*c) == O.compute_F(pt, gtt)
+    assert evaluator.F_from_counts(*O.jf_counts_exact(np.zeros_like(gt), gt)) == 0.0
+    for got, exp in zip(utils.mask_metrics_from_counts(*c), O.compute_mask_metrics(pt, gtt, "none")):
+        assert torch.equal(got, exp)
+    rows = dedup.iou_from_counts([0, 5, 3], [0, 5, 4], [0, 5, 6])
+    assert rows.tolist() == [1.0, 1.0, 3 / 7]
+
+
+def test_metric_mirror(golden):
+    gt_ids, corr = [3, 5, 9], [3, 3, 5, 5, 7, 9]
+    preds, labels = torch.tensor([1.0, 0.0, 1.0, 0.0, 1.0, 0.0]), torch.tensor([1, 1, 0, 1, 1, 0])
+    assert metric.recall_per_track(gt_ids, preds, labels, corr) == golden["x1_recall_per_track"].tolist()
+    assert metric.recall_per_exp(gt_ids, preds, labels, corr) == golden["x1_recall_per_exp"][0]
+    assert metric.recall_per_track(gt_ids, preds, labels, corr) == O.recall_per_track(gt_ids, preds, labels, corr)
+
+
+def test_shard_partitions():
+    for n, world in ((10, 1), (10, 2), (7, 4), (3, 8), (0, 2)):
+        parts = [sharding.shard_indices(n, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(n))
+        assert all(i % world == r for r, p in enumerate(parts) for i in p)       # the reference's modulo rule
+    costs = [5, 1, 9, 3, 3, 7, 2, 8]
+    parts = [sharding.shard_balanced(costs, r, 3) for r in range(3)]
+    assert sorted(sum(parts, [])) == list(range(len(costs)))
+    loads = [sum(costs[i] for i in p) for p in parts]
+    assert max(loads) - min(loads) <= max(costs)
