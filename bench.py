@@ -133,9 +133,7 @@ class Workload:
         resized = S.resize_bilinear_bin(packed)                                                                     # R1
         dd = dedup.TrackDedup(self.prompt_meta, self.T, mode="grid", prompt_masks=prompt_masks, bin_size=CFG["bin_size"],
                               n_max_tracks=CFG["n_max_tracks"], batch_size=CFG["batch_size"], miou_thresh=CFG["miou_thresh"])   # R2
-        while (batch := dd.next_batch()) is not None:                                                               # G1
-            dd.submit_resized(batch, resized[batch])
-        greedy = dd.result()
+        greedy = dd.run_offline(resized)                                                                            # G1 (K2 gather, one launch)
         kept, by, iou, inter = dedup.dedup_matrix(packed, CFG["miou_thresh"])                                       # K2 + greedy
         stab = S.packed.stability_from_counts(counts.view(3, self.N, self.T))                                       # D2H
         return {"tracked": greedy["tracked"], "filtered": greedy["filtered"], "kept_st": kept, "stability": stab, "inter": inter}

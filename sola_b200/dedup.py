@@ -207,6 +207,16 @@ class TrackDedup:
         self.state.apply_iou_rows(batch, rows)
         return rows
 
+    def run_offline(self, resized: P.PackedMasks) -> dict:
+        """All candidates' (resized, packed) masklets are already known — `resized` is (P, T, h, wp) in prompt order.
+        The outcome of the reference loop is a pure function of M[i][j] = IoU(track_i[frame_j], prompt_j) and the
+        batching rules, so M is computed in ONE launch and read back once; the host then replays the loop."""
+        c = P.gathered_inter(resized, self.prompt_planes, self.frame_idx_dev).cpu().numpy()
+        M = iou_from_counts(c[0], c[1], c[2])
+        while (batch := self.state.next_batch()) is not None:
+            self.state.apply_iou_rows(batch, M[batch])
+        return self.state.result()
+
     def result(self) -> dict:
         return self.state.result()
 

@@ -135,7 +135,7 @@ def binarize_pack_stability(logits, mask_threshold: float = 0.0, threshold_offse
                   _ptr(counts[0]) if counts is not None else None,
                   _ptr(counts[1]) if counts is not None else None,
                   _ptr(counts[2]) if counts is not None else None, _stream(x))
-    if counts is not None and lead:
+    if counts is not None:
         counts = counts.view(3, *lead)
     return packed, counts
 
