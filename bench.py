@@ -268,11 +268,13 @@ def main():
     launches0 = S.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
+        torch.cuda.nvtx.range_push("timed")
         ev0.record()
         for _ in range(args.steps):
             out = w.step(record_k1=True)
         ev1.record()
         barrier()
+        torch.cuda.nvtx.range_pop()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = S.launch_count() - launches0
     k1_ms = float(np.mean([a.elapsed_time(b) for a, b in w.k1_events]))

@@ -18,6 +18,7 @@
 //     shuffle+select steps, after which every lane owns one finished word, and the warp stores 128 contiguous bytes.
 // HBM traffic is exactly the algorithmic minimum: each logit is read once, each packed word written once.
 #include "common.cuh"
+#include <type_traits>
 
 namespace sola {
 
@@ -35,7 +36,17 @@ template <> struct ElemTraits<uint8_t> { static constexpr int E = 16; };
 __device__ __forceinline__ uint32_t gt_bit(float x, float t) { return x > t ? 1u : 0u; }   // NaN -> 0
 
 // ---- per-128-bit-load predicate extraction -------------------------------------------------------------------
-// Returns E bits (element c of the vector -> bit c) for mid, and (MODE_THRESH3 only) hi / lo.
+// Threshold modes use the sign of (t - x): with IEEE subtraction (denormals kept, canonical positive NaN on sm_100)
+// sign(t - x) == 1  <=>  x > t, for every input including +-0, +-inf, denormals and NaN (-> 0, as `NaN > t` is False).
+// That is one FADD on the fma pipe plus one funnel shift on the alu pipe per (element, threshold) — the shift pushes the
+// sign bit into an accumulator — instead of FSETP + SEL + shift/or, which kept the alu pipe ~70 % busy at HBM speed.
+// Elements are pushed last-to-first so that element 0 of the first vector ends up in bit 0.
+__device__ __forceinline__ uint32_t push_gt(uint32_t acc, float x, float t) {
+  return __funnelshift_l(__float_as_uint(__fsub_rn(t, x)), acc, 1);
+}
+
+
+// Returns E bits (element c of the vector -> bit c) for mid, and (MODE_THRESH3 only) hi / lo.   [MODE_NONZERO path]
 template <int MODE>
 __device__ __forceinline__ void vec_bits(const uint4& raw, const Thresholds& th, float, uint32_t& mid, uint32_t& hi, uint32_t& lo) {
   const float v[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
@@ -53,6 +64,31 @@ __device__ __forceinline__ void vec_bits(const uint4& raw, const Thresholds& th,
     }
   }
 }
+
+// push the E elements of one vector (last element first) into the three accumulators
+template <int MODE>
+__device__ __forceinline__ void vec_push(const uint4& raw, const Thresholds& th, float, uint32_t& mid, uint32_t& hi, uint32_t& lo) {
+  const float v[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
+#pragma unroll
+  for (int c = 3; c >= 0; --c) {
+    mid = push_gt(mid, v[c], th.mid);
+    if (MODE == MODE_THRESH3) { hi = push_gt(hi, v[c], th.hi); lo = push_gt(lo, v[c], th.lo); }
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void vec_push(const uint4& raw, const Thresholds& th, __nv_bfloat16, uint32_t& mid, uint32_t& hi, uint32_t& lo) {
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int c = 7; c >= 0; --c) {
+    const float x = __uint_as_float((c & 1) ? (w[c >> 1] & 0xffff0000u) : (w[c >> 1] << 16));   // bf16 -> fp32 is exact
+    mid = push_gt(mid, x, th.mid);
+    if (MODE == MODE_THRESH3) { hi = push_gt(hi, x, th.hi); lo = push_gt(lo, x, th.lo); }
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void vec_push(const uint4&, const Thresholds&, uint8_t, uint32_t&, uint32_t&, uint32_t&) {}
 
 template <int MODE>
 __device__ __forceinline__ void vec_bits(const uint4& raw, const Thresholds& th, __nv_bfloat16, uint32_t& mid, uint32_t& hi, uint32_t& lo) {
@@ -144,32 +180,45 @@ pack_flat_kernel(const T* __restrict__ in, int frame_px, int ctas_per_frame, Thr
   const int out_word_in_chunk = E * (lane % L) + lane / L;
 
   int n_mid = 0, n_hi = 0, n_lo = 0;
-  for (int c = c_begin + warp; c < c_end; c += K1_WARPS) {
+  // One chunk.  FULLCHUNK = every vector of the chunk lies inside the frame (all but possibly the last chunk of a
+  // frame): no predicates anywhere.  The tail variant loads out-of-frame vectors as "-inf" so no threshold passes.
+  auto do_chunk = [&](int c, auto full_tag) {
+    constexpr bool FULLCHUNK = decltype(full_tag)::value;
     const int px0 = c * K1_CHUNK_PX;
     uint4 raw[L];
 #pragma unroll
     for (int j = 0; j < L; ++j) {
       const int px = px0 + E * (j * 32 + lane);
-      raw[j] = (px < frame_px) ? ld_stream_u4(src + px) : make_uint4(0, 0, 0, 0);
+      if (FULLCHUNK || px < frame_px) {
+        raw[j] = ld_stream_u4(src + px);
+      } else {
+        const uint32_t ninf = (MODE == MODE_NONZERO || sizeof(T) == 1) ? 0u : (sizeof(T) == 4 ? 0xff800000u : 0xff80ff80u);
+        raw[j] = make_uint4(ninf, ninf, ninf, ninf);
+      }
     }
     uint32_t xm = 0, xh = 0, xl = 0;
+    if (MODE == MODE_NONZERO || sizeof(T) == 1) {
 #pragma unroll
-    for (int j = 0; j < L; ++j) {
-      uint32_t m, h, l;
-      vec_bits<MODE>(raw[j], th, T(), m, h, l);
-      // out-of-frame vectors were loaded as zeros; a zero passes a negative threshold, so mask them out
-      const bool inside = px0 + E * (j * 32 + lane) < frame_px;
-      if (!inside) m = h = l = 0;
-      xm |= m << (E * j);
-      if (MODE == MODE_THRESH3) { xh |= h << (E * j); xl |= l << (E * j); }
+      for (int j = 0; j < L; ++j) {
+        uint32_t m, h, l;
+        vec_bits<MODE>(raw[j], th, T(), m, h, l);
+        xm |= m << (E * j);
+      }
+    } else {
+#pragma unroll
+      for (int j = L - 1; j >= 0; --j) vec_push<MODE>(raw[j], th, T(), xm, xh, xl);
     }
     n_mid += __popc(xm);
     if (MODE == MODE_THRESH3) { n_hi += __popc(xh); n_lo += __popc(xl); }
     if (dst) {
       const uint32_t word = transpose_slots<E>(xm, lane);
       const int wi = (px0 >> 5) + out_word_in_chunk;
-      if (wi < frame_words) dst[wi] = word;
+      if (FULLCHUNK || wi < frame_words) dst[wi] = word;
     }
+  };
+  for (int c = c_begin + warp; c < c_end; c += K1_WARPS) {
+    if ((c + 1) * K1_CHUNK_PX <= frame_px) do_chunk(c, std::true_type());
+    else do_chunk(c, std::false_type());
   }
 
   __shared__ int red[3][K1_WARPS];
@@ -247,10 +296,10 @@ pack_rows_kernel(const T* __restrict__ in, int H, int W, int row_blocks, Thresho
 template <typename T, int MODE>
 static int launch_pack(const T* in, long long n_frames, int H, int W, Thresholds th, uint32_t* packed,
                        int* cnt_hi, int* cnt_mid, int* cnt_lo, cudaStream_t stream) {
-  SOLA_REQUIRE(in != nullptr, "pack: input pointer is null");
   SOLA_REQUIRE(n_frames >= 0 && H > 0 && W > 0, "pack: bad shape n_frames=%lld H=%d W=%d", n_frames, H, W);
   SOLA_REQUIRE((long long)H * W < (1ll << 31), "pack: frame larger than 2^31 pixels");
   if (n_frames == 0) return SOLA_OK;
+  SOLA_REQUIRE(in != nullptr, "pack: input pointer is null");
   if (cnt_mid) SOLA_CUDA(cudaMemsetAsync(cnt_mid, 0, sizeof(int) * n_frames, stream));
   if (MODE == MODE_THRESH3) {
     if (cnt_hi) SOLA_CUDA(cudaMemsetAsync(cnt_hi, 0, sizeof(int) * n_frames, stream));

@@ -14,6 +14,7 @@
 // R2  F.interpolate(prompt[None,None], (h, w), mode='nearest') (generate_tokens_grid.py:271-272):
 //       src = min((int)floorf(dst * scale), in - 1), scale = (float)in / out.
 #include "common.cuh"
+#include <math.h>
 
 namespace sola {
 
@@ -39,9 +40,149 @@ __device__ __forceinline__ float bilinear_val(const Axis& ax, const Axis& ay, fl
 __device__ __forceinline__ uint32_t get_bit(const uint32_t* __restrict__ row, int x) { return (__ldg(row + (x >> 5)) >> (x & 31)) & 1u; }
 
 // ---- R1 from packed planes -----------------------------------------------------------------------------------
-// One warp per output word (oy, owx); lane = output pixel.  The per-pixel geometry is frame-invariant, so each
-// warp keeps it in registers and walks a slice of the frames.  Words whose 2-row source window is uniformly 0 or
-// uniformly 1 are resolved with one vote (background / interior), only edge words evaluate the interpolation.
+// CTA = one tile of R1_TR output rows x the full output width, walked over a slice of the frames.
+//   * per-CTA tables in shared memory, built once: per output pixel (x0, x1, w0, w1), per output row (y0, y1, h0, h1);
+//   * per frame the contiguous block of input rows the tile needs is staged global -> shared with cp.async
+//     (double-buffered: frame k+1 lands while frame k is computed);
+//   * phase A, one THREAD per output word: OR / AND of the source words of both rows; an all-0 or all-1 window
+//     resolves the whole word (background / interior) with ~1 instruction per output pixel-row of the warp;
+//   * phase B, one WARP per remaining (edge) word, lane = output pixel: ATen's exact fma sequence on the 4 bits.
+// Output words are written by consecutive threads -> coalesced.
+constexpr int R1_TR = 32;
+constexpr int R1_THREADS = 256;
+
+struct __align__(16) XParam { int x0, x1; float w0, w1; };
+struct __align__(16) YParam { int y0, y1; float h0, h1; };     // rows relative to the tile's first input row
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async16_ca(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+
+__global__ void __launch_bounds__(R1_THREADS)
+resize_bilinear_tiled_kernel(const uint32_t* __restrict__ in, int n_frames, int frames_per_slice, int H, int W, int oh, int ow,
+                             float sy, float sx, int max_in_rows, uint32_t* __restrict__ out, int* __restrict__ area) {
+  extern __shared__ __align__(16) unsigned char r1_smem[];
+  const int Wp = (W + 31) >> 5, owp = (ow + 31) >> 5;
+  XParam* xtab = reinterpret_cast<XParam*>(r1_smem);                         // [owp * 32]
+  YParam* ytab = reinterpret_cast<YParam*>(xtab + owp * 32);                 // [R1_TR]
+  uint32_t* tile = reinterpret_cast<uint32_t*>(ytab + R1_TR);                // [2][max_in_rows * Wp]
+  const int tile_words_max = max_in_rows * Wp;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int oy0 = blockIdx.x * R1_TR;
+  const int nrows = min(R1_TR, oh - oy0);
+  const int f_begin = blockIdx.y * frames_per_slice;
+  const int f_end = min(n_frames, f_begin + frames_per_slice);
+
+  const int ylo = bilinear_axis(oy0, sy, H).i0;
+  const int yhi = bilinear_axis(oy0 + nrows - 1, sy, H).i1;
+  const int n_in_words = (yhi - ylo + 1) * Wp;
+  for (int i = tid; i < owp * 32; i += R1_THREADS) {
+    const Axis a = bilinear_axis(min(i, ow - 1), sx, W);
+    xtab[i] = XParam{a.i0, a.i1, a.l0, a.l1};
+  }
+  if (tid < R1_TR) {
+    const Axis a = bilinear_axis(min(oy0 + tid, oh - 1), sy, H);
+    ytab[tid] = YParam{a.i0 - ylo, a.i1 - ylo, a.l0, a.l1};
+  }
+  const long long FW = (long long)H * Wp, oFW = (long long)oh * owp;
+  const bool vec16 = ((Wp & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);   // every row block starts 16-byte aligned
+
+  auto prefetch = [&](int f, int buf) {
+    const uint32_t* src = in + f * FW + (long long)ylo * Wp;
+    uint32_t* dst = tile + buf * tile_words_max;
+    if (vec16) {
+      for (int i = tid * 4; i < n_in_words; i += R1_THREADS * 4) cp_async16_ca(dst + i, src + i);
+    } else {
+      for (int i = tid; i < n_in_words; i += R1_THREADS) cp_async4(dst + i, src + i);
+    }
+    asm volatile("cp.async.commit_group;");
+  };
+
+  int area_acc = 0;
+  if (f_begin < f_end) prefetch(f_begin, 0);
+  for (int f = f_begin; f < f_end; ++f) {
+    const int buf = (f - f_begin) & 1;
+    if (f + 1 < f_end) {
+      prefetch(f + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;");
+    } else {
+      asm volatile("cp.async.wait_group 0;");
+    }
+    __syncthreads();                                   // tile of frame f (and, first time round, the tables) visible
+    const uint32_t* t = tile + buf * tile_words_max;
+    const int n_words = nrows * owp;
+    for (int base = 0; base < n_words; base += R1_THREADS) {
+      const int i = base + tid;
+      const bool have = i < n_words;
+      uint32_t word = 0;
+      bool edge = false;
+      int r = 0, c = 0;
+      if (have) {
+        r = i / owp; c = i - r * owp;
+        const YParam yp = ytab[r];
+        const int px_first = c * 32, px_last = min(c * 32 + 31, ow - 1);
+        const int wlo = xtab[px_first].x0 >> 5, whi = xtab[px_last].x1 >> 5;
+        const uint32_t* r0 = t + yp.y0 * Wp;
+        const uint32_t* r1 = t + yp.y1 * Wp;
+        uint32_t any1 = 0u, all1 = 0xffffffffu;
+        for (int w = wlo; w <= whi; ++w) {
+          const uint32_t v0 = r0[w], v1 = r1[w];
+          any1 |= v0 | v1;
+          all1 &= v0 & v1;
+        }
+        if (any1 == 0u) word = 0u;
+        else if (all1 == 0xffffffffu) word = (px_last - px_first == 31) ? 0xffffffffu : ((1u << (px_last - px_first + 1)) - 1u);
+        else edge = true;
+      }
+      // phase B: the warp resolves its edge words one at a time, lane = output pixel
+      unsigned pending = __ballot_sync(FULL, edge);
+      while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const int rr = __shfl_sync(FULL, r, src), cc = __shfl_sync(FULL, c, src);
+        const int ox = cc * 32 + lane;
+        const XParam xp = xtab[ox];
+        const YParam yp = ytab[rr];
+        const uint32_t* r0 = t + yp.y0 * Wp;
+        const uint32_t* r1 = t + yp.y1 * Wp;
+        // v in {0,1}: w*v is w or +0 exactly, and fma(w0, v00, t) is fl(w0*v00 + t) = fl((w0 & m00) + t)
+        const uint32_t m00 = 0u - ((r0[xp.x0 >> 5] >> (xp.x0 & 31)) & 1u), m01 = 0u - ((r0[xp.x1 >> 5] >> (xp.x1 & 31)) & 1u);
+        const uint32_t m10 = 0u - ((r1[xp.x0 >> 5] >> (xp.x0 & 31)) & 1u), m11 = 0u - ((r1[xp.x1 >> 5] >> (xp.x1 & 31)) & 1u);
+        const uint32_t w0b = __float_as_uint(xp.w0), w1b = __float_as_uint(xp.w1);
+        const float top = __fadd_rn(__uint_as_float(w0b & m00), __uint_as_float(w1b & m01));
+        const float bot = __fadd_rn(__uint_as_float(w0b & m10), __uint_as_float(w1b & m11));
+        const float val = __fmaf_rn(yp.h0, top, __fmul_rn(yp.h1, bot));
+        const uint32_t wv = __ballot_sync(FULL, ox < ow && val > 0.5f);
+        if (lane == src) word = wv;
+      }
+      if (have) {
+        out[f * oFW + (long long)(oy0 + r) * owp + c] = word;
+        area_acc += __popc(word);
+      }
+    }
+    if (area) {
+      // per-frame area: block reduction, one atomic per CTA per frame
+      __shared__ int red[R1_THREADS / 32];
+      const int s = warp_sum(area_acc);
+      if (lane == 0) red[tid >> 5] = s;
+      __syncthreads();
+      if (tid == 0) {
+        int tot = 0;
+        for (int w = 0; w < R1_THREADS / 32; ++w) tot += red[w];
+        if (tot) atomicAdd(area + f, tot);
+      }
+      area_acc = 0;
+    }
+    __syncthreads();                                   // everyone done with `buf` before frame f+2 overwrites it
+  }
+}
+
+// Generic fallback (any scale factor): one warp per output word walking the frames, geometry in registers.
 constexpr int R1_WARPS = 8;
 
 __global__ void __launch_bounds__(R1_WARPS * 32)
@@ -58,45 +199,14 @@ resize_bilinear_packed_kernel(const uint32_t* __restrict__ in, int n_frames, int
   const bool live = ox < ow;
   const Axis ay = bilinear_axis(oy, sy, H);
   const Axis ax = bilinear_axis(live ? ox : ow - 1, sx, W);
-  // source word window of this output word: [wlo, whi] covers x0 of lane 0 .. x1 of the last live lane
-  const int x_first = __shfl_sync(FULL, ax.i0, 0);
-  const int x_last = __shfl_sync(FULL, ax.i1, 31);            // dead lanes replicate ow-1, so lane 31 is the max
-  const int wlo = x_first >> 5, whi = x_last >> 5;
-  const int nwin = whi - wlo + 1;                             // <= 32 for any downscale factor below ~31
   const long long FW = (long long)H * Wp, oFW = (long long)oh * owp;
-  const bool window_in_one_vote = nwin <= 16;
   for (int f = f_begin; f < f_end; ++f) {
     const uint32_t* r0 = in + f * FW + (long long)ay.i0 * Wp;
     const uint32_t* r1 = in + f * FW + (long long)ay.i1 * Wp;
-    uint32_t word;
-    bool resolved = false;
-    if (window_in_one_vote) {
-      // lanes 0..nwin-1 fetch row y0's window, lanes 16..16+nwin-1 row y1's
-      const int k = lane & 15;
-      uint32_t wv = 0;
-      const bool fetch = k < nwin;
-      if (fetch) wv = __ldg(((lane < 16) ? r0 : r1) + wlo + k);
-      // pixels outside [x_first, x_last] in the edge words do not matter; mask them to the neighbouring value
-      uint32_t care = 0xffffffffu;
-      if (fetch) {
-        if (k == 0) care &= 0xffffffffu << (x_first & 31);
-        if (k == nwin - 1) care &= 0xffffffffu >> (31 - (x_last & 31));
-      }
-      const bool any1 = fetch && (wv & care) != 0u;
-      const bool any0 = fetch && ((~wv) & care) != 0u;
-      const bool has1 = __any_sync(FULL, any1), has0 = __any_sync(FULL, any0);
-      if (!has1) { word = 0u; resolved = true; }
-      else if (!has0) { word = live ? 0xffffffffu : 0u; resolved = true; }
-    }
-    if (resolved) {
-      // all-ones: every live pixel interpolates 1-valued neighbours -> val = fma(h0, fl(w0+w1), h1*fl(w0+w1)) ~ 1 > 0.5
-      word = __ballot_sync(FULL, live && word != 0u);
-    } else {
-      const float v00 = (float)get_bit(r0, ax.i0), v01 = (float)get_bit(r0, ax.i1);
-      const float v10 = (float)get_bit(r1, ax.i0), v11 = (float)get_bit(r1, ax.i1);
-      const float val = bilinear_val(ax, ay, v00, v01, v10, v11);
-      word = __ballot_sync(FULL, live && val > 0.5f);
-    }
+    const float v00 = (float)get_bit(r0, ax.i0), v01 = (float)get_bit(r0, ax.i1);
+    const float v10 = (float)get_bit(r1, ax.i0), v11 = (float)get_bit(r1, ax.i1);
+    const float val = bilinear_val(ax, ay, v00, v01, v10, v11);
+    const uint32_t word = __ballot_sync(FULL, live && val > 0.5f);
     if (lane == 0) {
       out[f * oFW + word_id] = word;
       if (area && word) atomicAdd(area + f, __popc(word));
@@ -193,9 +303,27 @@ int sola_resize_bilinear_bin_packed(const uint32_t* in_packed, long long n_frame
   SOLA_REQUIRE(n_frames >= 0 && n_frames < (1ll << 31) && H > 0 && W > 0 && oh > 0 && ow > 0, "resize_bilinear_bin_packed: bad shape");
   if (n_frames == 0) return SOLA_OK;
   if (area) SOLA_CUDA(cudaMemsetAsync(area, 0, sizeof(int) * n_frames, stream));
-  const int owp = (ow + 31) >> 5;
+  const int Wp = (W + 31) >> 5, owp = (ow + 31) >> 5;
+  const float sy = host_scale(H, oh), sx = host_scale(W, ow);
+  // input rows one tile of R1_TR output rows can touch (+2 for the y1 row and rounding)
+  long long max_in_rows = (long long)ceil((double)R1_TR * (double)sy) + 3;
+  if (max_in_rows > H) max_in_rows = H;
+  const size_t smem = (size_t)owp * 32 * sizeof(XParam) + R1_TR * sizeof(YParam) + 2 * (size_t)max_in_rows * Wp * sizeof(uint32_t);
+  if (smem <= 200 * 1024) {
+    SOLA_CUDA(cudaFuncSetAttribute(resize_bilinear_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = (oh + R1_TR - 1) / R1_TR;
+    int slices = (num_sms() * 16 + tiles - 1) / tiles;            // ~16 CTAs per SM in flight over the launch
+    if (slices > n_frames) slices = (int)n_frames;
+    if (slices > 65535) slices = 65535;
+    if (slices < 1) slices = 1;
+    const int frames_per_slice = (int)((n_frames + slices - 1) / slices);
+    slices = (int)((n_frames + frames_per_slice - 1) / frames_per_slice);
+    dim3 grid(tiles, slices);
+    resize_bilinear_tiled_kernel<<<grid, R1_THREADS, smem, stream>>>(in_packed, (int)n_frames, frames_per_slice, H, W, oh, ow, sy, sx,
+                                                                     (int)max_in_rows, out_packed, area);
+    return check_launch("resize_bilinear_tiled kernel");
+  }
   const int word_blocks = (oh * owp + R1_WARPS - 1) / R1_WARPS;
-  // enough CTAs for ~8 per SM: split the frame axis when the plane alone is too small
   int slices = (int)((num_sms() * 8 + word_blocks - 1) / word_blocks);
   if (slices > n_frames) slices = (int)n_frames;
   if (slices < 1) slices = 1;
@@ -203,8 +331,8 @@ int sola_resize_bilinear_bin_packed(const uint32_t* in_packed, long long n_frame
   const int frames_per_slice = (int)((n_frames + slices - 1) / slices);
   slices = (int)((n_frames + frames_per_slice - 1) / frames_per_slice);
   dim3 grid(word_blocks, slices);
-  resize_bilinear_packed_kernel<<<grid, R1_WARPS * 32, 0, stream>>>(in_packed, (int)n_frames, frames_per_slice, H, W, oh, ow,
-                                                                    host_scale(H, oh), host_scale(W, ow), out_packed, area);
+  resize_bilinear_packed_kernel<<<grid, R1_WARPS * 32, 0, stream>>>(in_packed, (int)n_frames, frames_per_slice, H, W, oh, ow, sy, sx,
+                                                                    out_packed, area);
   return check_launch("resize_bilinear_packed kernel");
 }
 

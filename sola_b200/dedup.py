@@ -64,6 +64,7 @@ class GreedyState:
                     self.status[k] = NOT_TRACKED
                     self.members.append(k)
         self.frame_idx = np.array([p["frame_idx"] for p in self.prompts], dtype=np.int64)
+        self._members_arr = np.asarray(self.members, dtype=np.int64)
 
     # -- batching ------------------------------------------------------------------------------------------------
     def next_batch(self) -> Optional[List[int]]:
@@ -107,18 +108,21 @@ class GreedyState:
         """iou_rows[b, k] = IoU(resized track of batch[b] at frame_idx[k], nearest-resized prompt k) for every
         prompt k (float64).  Walks batch members in order and candidates in list order, strict `>` (grid :266-278)."""
         n = 0
+        members = self._members_arr
         for b, member in enumerate(batch):
-            row = iou_rows[b]
+            row = np.asarray(iou_rows[b])
+            # candidates still untracked, in list order; a member's hits do not depend on each other, only on the
+            # state left by the previous members, so one vectorised pass per member reproduces the reference's inner loop
+            hit = members[(self.status[members] == NOT_TRACKED) & (row[members] > self.miou_thresh)]
+            if hit.size == 0:
+                continue
+            self.status[hit] = FILTERED
             member_id = self.prompts[member]["prompt_id"]
-            for k in self.members:
-                if self.status[k] != NOT_TRACKED:
-                    continue
-                if row[k] > self.miou_thresh:
-                    self.status[k] = FILTERED
-                    pid = self.prompts[k]["prompt_id"]
-                    self.filtered_by[pid] = member_id
-                    self.filtered_iou[pid] = float(row[k])
-                    n += 1
+            for k in hit.tolist():
+                pid = self.prompts[k]["prompt_id"]
+                self.filtered_by[pid] = member_id
+                self.filtered_iou[pid] = float(row[k])
+            n += int(hit.size)
         self.n_filtered += n
         return n
 

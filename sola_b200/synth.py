@@ -71,21 +71,24 @@ def dedup_candidates(n: int, T: int, H: int, W: int, seed: int, device="cpu", *,
                      n_clusters: Optional[int] = None, jitter: int = 2) -> Tuple[torch.Tensor, List[dict]]:
     """Candidate table for the greedy filters: n candidates in ~n/3 clusters of near-duplicates.
     Returns (logits (n, T, H, W) fp32 — what SAM2 would emit when tracking each candidate —, prompts list).
-    prompt k: frame_idx on the `bin_size` grid, segmentation = its own masklet at that frame (uint8), area-sorted
-    descending with prompt_id = rank (generate_prompts_grid.py:131-133)."""
+    Each cluster is an object-like mask (a few large smooth blobs, ~5-20 % of the frame); members of a cluster are the
+    same object shifted by up to `jitter` px with their own level / edge sharpness, so IoUs straddle 0.7 and the
+    stability scores spread over ~0.8-0.99.  prompt k: frame_idx on the `bin_size` grid, segmentation = its own
+    masklet at that frame (uint8), area-sorted descending with prompt_id = rank (generate_prompts_grid.py:131-133)."""
     g = _gen(seed, device)
     K = n_clusters or max(1, n // 3)
-    cell = 32
-    base = torch.randn((K, 1, H // cell + 3, W // cell + 3), generator=g, device=device)
+    cell = max(16, min(H, W) // 5)
+    base = torch.randn((K, 1, H // cell + 4, W // cell + 4), generator=g, device=device)
     base = torch.nn.functional.interpolate(base, size=(H + 16, W + 16), mode="bicubic", align_corners=False)[:, 0]
     cluster = torch.randint(0, K, (n,), generator=g, device=device)
     shift = torch.randint(-jitter, jitter + 1, (n, 2), generator=g, device=device) + 8
-    level = 0.8 + 0.4 * torch.rand((n,), generator=g, device=device)
+    level = 0.9 + 0.5 * torch.rand((n,), generator=g, device=device)
+    sharp = 15.0 + 65.0 * torch.rand((n,), generator=g, device=device)       # logit units per field unit: soft ... crisp edges
     logits = torch.empty((n, T, H, W), dtype=torch.float32, device=device)
+    drift = torch.linspace(0, 0.15, T, device=device).view(T, 1, 1)
     for i in range(n):
         f = base[cluster[i], shift[i, 0]: shift[i, 0] + H, shift[i, 1]: shift[i, 1] + W]
-        drift = torch.linspace(0, 0.3, T, device=device).view(T, 1, 1)
-        logits[i] = 5.0 * (f[None] - level[i] - drift) + 0.3 * torch.randn((T, H, W), generator=g, device=device)
+        logits[i] = sharp[i] * (f[None] - level[i] - drift) + 0.5 * torch.randn((T, H, W), generator=g, device=device)
     n_bins = max(1, (T + bin_size - 1) // bin_size)
     frame_idx = (torch.randint(0, n_bins, (n,), generator=g, device=device) * bin_size).clamp(max=T - 1).cpu().numpy()
     segs = [(logits[i, int(frame_idx[i])] > 0).to(torch.uint8).cpu().numpy() for i in range(n)]

@@ -89,7 +89,8 @@ def test_track_dedup_matches_golden(golden, case):
         dd = dedup.TrackDedup(greedy_prompts(golden), n_frames, mode=mode, bin_size=4, expression_id=eid, **kw)
         all_rows = {}
         while (batch := dd.next_batch()) is not None:
-            rows = dd.submit_masks(batch, masklets[batch])
+            import sola_b200 as S
+            rows = dd.submit_packed(batch, S.pack_masks(masklets[batch]))
             for b, k in enumerate(batch):
                 all_rows[k] = rows[b]
         res = dd.result()
