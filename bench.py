@@ -115,28 +115,50 @@ class Workload:
         self.k1_events = []
         self.k1_bytes = self.N * self.T * (self.H * self.W * 4 + self.H * ((self.W + 31) // 32) * 4 + 12)
 
-    def step(self, logits=None, prompt_masks=None, record_k1=False, k1_done=False):
-        S = self.S
+    def make_jobs(self):
         from sola_b200 import dedup
+        mk = lambda: dedup.VideoDedupJob(self.prompt_meta, self.T, device=self.device, mode="grid", bin_size=CFG["bin_size"],
+                                         n_max_tracks=CFG["n_max_tracks"], batch_size=CFG["batch_size"], miou_thresh=CFG["miou_thresh"])
+        self.jobs = [mk(), mk()]
+
+    def enqueue(self, slot, logits=None, prompt_masks=None, record_k1=False):
+        """Device half of one step (no synchronisation): K1, R1, R2, K2-gather, K2 N x N, async read-back."""
+        job = self.jobs[slot]
         logits = self.logits if logits is None else logits
         prompt_masks = self.prompt_masks_dev if prompt_masks is None else prompt_masks
-        if k1_done:                          # e2e: K1 already ran chunk by chunk behind the H2D copies
-            packed, counts = self.packed, self.counts
+        if record_k1:
+            # K1 is the first launch of the step: bracket it with events on the launching stream
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            packed, counts = self.S.binarize_pack_stability(logits, 0.0, 1.0, out=self.packed, counts_out=self.counts)
+            e1.record()
+            self.k1_events.append((e0, e1))
+            job.enqueue_after_k1(packed, counts, prompt_masks)
         else:
-            if record_k1:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-            packed, counts = S.binarize_pack_stability(logits, 0.0, 1.0, out=self.packed, counts_out=self.counts)   # K1
-            if record_k1:
-                e1.record()
-                self.k1_events.append((e0, e1))
-        resized = S.resize_bilinear_bin(packed)                                                                     # R1
-        dd = dedup.TrackDedup(self.prompt_meta, self.T, mode="grid", prompt_masks=prompt_masks, bin_size=CFG["bin_size"],
-                              n_max_tracks=CFG["n_max_tracks"], batch_size=CFG["batch_size"], miou_thresh=CFG["miou_thresh"])   # R2
-        greedy = dd.run_offline(resized)                                                                            # G1 (K2 gather, one launch)
-        kept, by, iou, inter = dedup.dedup_matrix(packed, CFG["miou_thresh"])                                       # K2 + greedy
-        stab = S.packed.stability_from_counts(counts.view(3, self.N, self.T))                                       # D2H
-        return {"tracked": greedy["tracked"], "filtered": greedy["filtered"], "kept_st": kept, "stability": stab, "inter": inter}
+            job.enqueue(logits, prompt_masks, packed_out=self.packed, counts_out=self.counts)
+
+    def finish(self, slot):
+        """Host half: wait for that step's read-back, replay both greedy filters, stability scores."""
+        r = self.jobs[slot].finish()
+        return {"tracked": r["tracked"], "filtered": r["filtered"], "kept_st": r["kept_spatiotemporal"], "stability": r["stability"],
+                "inter": r["inter"]}
+
+    def step(self, logits=None, prompt_masks=None):
+        self.enqueue(0, logits, prompt_masks)
+        return self.finish(0)
+
+    def run_steps(self, n, record_k1=False):
+        """n steps, software-pipelined: the host post-processes step k while the GPU runs step k+1."""
+        out, prev = None, None
+        for k in range(n):
+            slot = k & 1
+            self.enqueue(slot, record_k1=record_k1)
+            if prev is not None:
+                out = self.finish(prev)
+            prev = slot
+        if prev is not None:
+            out = self.finish(prev)
+        return out
 
 
 def checks(w: Workload, out) -> dict:
@@ -253,6 +275,7 @@ def main():
     S.load_library()
 
     w = Workload(device, seed=1234 + 2 + 1000 * rank, n_tracks=n_tracks, n_frames=n_frames)
+    w.make_jobs()
     torch.cuda.synchronize()
 
     def barrier():
@@ -260,9 +283,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    out = None
-    for _ in range(max(args.warmup, 3)):
-        out = w.step()
+    out = w.run_steps(max(args.warmup, 3))
     info = checks(w, out)
     barrier()
     launches0 = S.launch_count()
@@ -270,8 +291,7 @@ def main():
     with ClockSampler(local_rank) as clk:
         torch.cuda.nvtx.range_push("timed")
         ev0.record()
-        for _ in range(args.steps):
-            out = w.step(record_k1=True)
+        out = w.run_steps(args.steps, record_k1=True)
         ev1.record()
         barrier()
         torch.cuda.nvtx.range_pop()
@@ -300,7 +320,7 @@ def main():
             copy_stream = torch.cuda.Stream(device=device)
 
             def e2e_step():
-                # chunked H2D on a copy stream, K1 of chunk c overlaps the copy of chunk c+1
+                # chunked H2D on a copy stream; K1 of chunk c runs while chunk c+1 is still crossing PCIe
                 evs = []
                 with torch.cuda.stream(copy_stream):
                     for c, h in enumerate(host_chunks):
@@ -319,7 +339,8 @@ def main():
                     _, cc = S.binarize_pack_stability(dev_logits[sl], 0.0, 1.0, out=w.packed[sl])       # K1 on the chunk that just landed
                     cview[:, sl] = cc
                 torch.cuda.current_stream().wait_event(evs[-1])
-                return w.step(logits=dev_logits, prompt_masks=pm, k1_done=True)                         # R1, R2, G1, K2, read-backs
+                w.jobs[0].enqueue_after_k1(w.packed, w.counts.view(3, n_tracks, n_frames), pm)          # R1, R2, K2-gather, K2, read-backs
+                return w.finish(0)
 
             e2e_step()
             barrier()

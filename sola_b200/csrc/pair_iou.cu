@@ -153,8 +153,11 @@ pair_iou_st_simple_kernel(const uint32_t* __restrict__ packed, int N, long long 
 
 // ---- gathered single-frame IoU ------------------------------------------------------------------------------
 constexpr int GT_TILE = 4;   // tracks per CTA
+constexpr int GT_THREADS = 128;
 
-__global__ void __launch_bounds__(128)
+// VEC = 4: planes are 16-byte aligned and FW % 4 == 0 -> 128-bit loads, 5 independent loads in flight per iteration
+template <int VEC>
+__global__ void __launch_bounds__(GT_THREADS)
 pair_iou_gather_kernel(const uint32_t* __restrict__ tracks, const uint32_t* __restrict__ prompts, const int* __restrict__ frame_idx,
                        int N, int P, int T, int FW, int* __restrict__ inter, int* __restrict__ area_t, int* __restrict__ area_p) {
   const int j = blockIdx.x, i0 = blockIdx.y * GT_TILE;
@@ -165,17 +168,34 @@ pair_iou_gather_kernel(const uint32_t* __restrict__ tracks, const uint32_t* __re
 #pragma unroll
   for (int k = 0; k < GT_TILE; ++k) pt[k] = tracks + ((long long)min(i0 + k, N - 1) * T + f) * FW;
   int ni[GT_TILE] = {0, 0, 0, 0}, na[GT_TILE] = {0, 0, 0, 0}, np = 0;
-  for (int w = threadIdx.x; w < FW; w += blockDim.x) {
-    const uint32_t p = pp[w];
-    np += __popc(p);
+  if (VEC == 4) {
+    const int nq = FW >> 2;
+#pragma unroll 2
+    for (int q = threadIdx.x; q < nq; q += GT_THREADS) {
+      const uint4 p = __ldg(reinterpret_cast<const uint4*>(pp) + q);
+      uint4 t[GT_TILE];
 #pragma unroll
-    for (int k = 0; k < GT_TILE; ++k) {
-      const uint32_t t = pt[k][w];
-      ni[k] += __popc(p & t);
-      na[k] += __popc(t);
+      for (int k = 0; k < GT_TILE; ++k) t[k] = __ldg(reinterpret_cast<const uint4*>(pt[k]) + q);
+      np += __popc(p.x) + __popc(p.y) + __popc(p.z) + __popc(p.w);
+#pragma unroll
+      for (int k = 0; k < GT_TILE; ++k) {
+        ni[k] += __popc(p.x & t[k].x) + __popc(p.y & t[k].y) + __popc(p.z & t[k].z) + __popc(p.w & t[k].w);
+        na[k] += __popc(t[k].x) + __popc(t[k].y) + __popc(t[k].z) + __popc(t[k].w);
+      }
+    }
+  } else {
+    for (int w = threadIdx.x; w < FW; w += GT_THREADS) {
+      const uint32_t p = pp[w];
+      np += __popc(p);
+#pragma unroll
+      for (int k = 0; k < GT_TILE; ++k) {
+        const uint32_t t = pt[k][w];
+        ni[k] += __popc(p & t);
+        na[k] += __popc(t);
+      }
     }
   }
-  __shared__ int red[2 * GT_TILE + 1][4];
+  __shared__ int red[2 * GT_TILE + 1][GT_THREADS / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   np = warp_sum(np);
 #pragma unroll
@@ -188,7 +208,9 @@ pair_iou_gather_kernel(const uint32_t* __restrict__ tracks, const uint32_t* __re
   __syncthreads();
   if (threadIdx.x < 2 * GT_TILE + 1) {
     const int k = threadIdx.x;
-    const int s = red[k][0] + red[k][1] + red[k][2] + red[k][3];
+    int s = 0;
+#pragma unroll
+    for (int w = 0; w < GT_THREADS / 32; ++w) s += red[k][w];
     if (k < GT_TILE) {
       if (i0 + k < N) inter[(long long)(i0 + k) * P + j] = s;
     } else if (k < 2 * GT_TILE) {
@@ -250,7 +272,10 @@ int sola_pair_iou_gather(const uint32_t* tracks, const uint32_t* prompts, const 
   if (N == 0 || P == 0) return SOLA_OK;
   SOLA_REQUIRE((N + GT_TILE - 1) / GT_TILE <= 65535, "pair_iou_gather: too many tracks for one launch");
   dim3 grid(P, (N + GT_TILE - 1) / GT_TILE);
-  pair_iou_gather_kernel<<<grid, 128, 0, stream>>>(tracks, prompts, frame_idx, N, P, T, (int)frame_words, inter, area_t, area_p);
+  if (frame_words % 4 == 0 && aligned16(tracks) && aligned16(prompts))
+    pair_iou_gather_kernel<4><<<grid, GT_THREADS, 0, stream>>>(tracks, prompts, frame_idx, N, P, T, (int)frame_words, inter, area_t, area_p);
+  else
+    pair_iou_gather_kernel<1><<<grid, GT_THREADS, 0, stream>>>(tracks, prompts, frame_idx, N, P, T, (int)frame_words, inter, area_t, area_p);
   return check_launch("pair_iou_gather kernel");
 }
 

@@ -70,7 +70,8 @@ resize_bilinear_tiled_kernel(const uint32_t* __restrict__ in, int n_frames, int 
   const int Wp = (W + 31) >> 5, owp = (ow + 31) >> 5;
   XParam* xtab = reinterpret_cast<XParam*>(r1_smem);                         // [owp * 32]
   YParam* ytab = reinterpret_cast<YParam*>(xtab + owp * 32);                 // [R1_TR]
-  uint32_t* tile = reinterpret_cast<uint32_t*>(ytab + R1_TR);                // [2][max_in_rows * Wp]
+  int2* ctab = reinterpret_cast<int2*>(ytab + R1_TR);                        // [owp rounded up to even]: source word window per output word column
+  uint32_t* tile = reinterpret_cast<uint32_t*>(ctab + ((owp + 1) & ~1));     // [2][max_in_rows * Wp]
   const int tile_words_max = max_in_rows * Wp;
   const int tid = threadIdx.x, lane = tid & 31;
   const int oy0 = blockIdx.x * R1_TR;
@@ -88,6 +89,11 @@ resize_bilinear_tiled_kernel(const uint32_t* __restrict__ in, int n_frames, int 
   if (tid < R1_TR) {
     const Axis a = bilinear_axis(min(oy0 + tid, oh - 1), sy, H);
     ytab[tid] = YParam{a.i0 - ylo, a.i1 - ylo, a.l0, a.l1};
+  }
+  for (int c = tid; c < owp; c += R1_THREADS) {
+    const int wlo = bilinear_axis(c * 32, sx, W).i0 >> 5;
+    const int whi = bilinear_axis(min(c * 32 + 31, ow - 1), sx, W).i1 >> 5;
+    ctab[c] = make_int2(wlo, whi);
   }
   const long long FW = (long long)H * Wp, oFW = (long long)oh * owp;
   const bool vec16 = ((Wp & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);   // every row block starts 16-byte aligned
@@ -126,7 +132,8 @@ resize_bilinear_tiled_kernel(const uint32_t* __restrict__ in, int n_frames, int 
         r = i / owp; c = i - r * owp;
         const YParam yp = ytab[r];
         const int px_first = c * 32, px_last = min(c * 32 + 31, ow - 1);
-        const int wlo = xtab[px_first].x0 >> 5, whi = xtab[px_last].x1 >> 5;
+        const int2 win = ctab[c];
+        const int wlo = win.x, whi = win.y;
         const uint32_t* r0 = t + yp.y0 * Wp;
         const uint32_t* r1 = t + yp.y1 * Wp;
         uint32_t any1 = 0u, all1 = 0xffffffffu;
@@ -308,7 +315,8 @@ int sola_resize_bilinear_bin_packed(const uint32_t* in_packed, long long n_frame
   // input rows one tile of R1_TR output rows can touch (+2 for the y1 row and rounding)
   long long max_in_rows = (long long)ceil((double)R1_TR * (double)sy) + 3;
   if (max_in_rows > H) max_in_rows = H;
-  const size_t smem = (size_t)owp * 32 * sizeof(XParam) + R1_TR * sizeof(YParam) + 2 * (size_t)max_in_rows * Wp * sizeof(uint32_t);
+  const size_t smem = (size_t)owp * 32 * sizeof(XParam) + R1_TR * sizeof(YParam) + (size_t)((owp + 1) & ~1) * sizeof(int2) +
+                      2 * (size_t)max_in_rows * Wp * sizeof(uint32_t);
   if (smem <= 200 * 1024) {
     SOLA_CUDA(cudaFuncSetAttribute(resize_bilinear_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = (oh + R1_TR - 1) / R1_TR;

@@ -242,3 +242,79 @@ def dedup_matrix(tracks: P.PackedMasks, miou_thresh: float = 0.7):
         for j in hit.tolist():
             by[j] = i
     return [i for i in range(n) if alive[i]], by, iou, inter
+
+
+class VideoDedupJob:
+    """Whole-video pass with the device work and the host work decoupled, for streaming many videos:
+
+        enqueue(logits, prompt_masks)  K1 -> R1 -> R2 -> K2-gather -> K2 N x N, then async read-back of the three small
+                                       result tensors into pinned host memory; returns immediately (no synchronisation)
+        finish()                       waits for THIS job's event only, then replays the reference greedy loop, the
+                                       spatio-temporal greedy and the float64 stability scores on the host
+
+    Two jobs used alternately keep the GPU busy while the host post-processes the previous video (bench.py)."""
+
+    def __init__(self, prompt_meta: Sequence[dict], n_frames: int, *, device=None, mode: str = "grid", **rules):
+        self.prompt_meta = list(prompt_meta)
+        self.n_frames = n_frames
+        self.mode, self.rules = mode, rules
+        self.device = P._dev(device)
+        self.frame_idx = np.array([p["frame_idx"] for p in self.prompt_meta], dtype=np.int32)
+        self.frame_idx_dev = P.to_device(self.frame_idx, device=self.device)
+        self.event = torch.cuda.Event()
+        self._host = None
+        self.packed = self.counts = self.resized = None
+
+    def _pinned(self, n_tracks: int, n_prompts: int, T: int):
+        if self._host is None:
+            self._host = (torch.empty((3, n_tracks, n_prompts), dtype=torch.int32).pin_memory(),
+                          torch.empty((n_tracks, n_tracks), dtype=torch.int64).pin_memory(),
+                          torch.empty((3, n_tracks, T), dtype=torch.int32).pin_memory())
+        return self._host
+
+    def enqueue(self, logits: torch.Tensor, prompt_masks: torch.Tensor, *, mask_threshold: float = 0.0, threshold_offset: float = 1.0,
+                packed_out: Optional[P.PackedMasks] = None, counts_out: Optional[torch.Tensor] = None, target_shape=None):
+        """logits (N, T, H, W) fp32/bf16 and prompt_masks (N, H, W) uint8, both on the device, in prompt order."""
+        packed, counts = P.binarize_pack_stability(logits, mask_threshold, threshold_offset, out=packed_out, counts_out=counts_out)   # K1
+        self.enqueue_after_k1(packed, counts, prompt_masks, target_shape=target_shape)
+
+    def enqueue_after_k1(self, packed: P.PackedMasks, counts: torch.Tensor, prompt_masks: torch.Tensor, *, target_shape=None):
+        """Same, for callers that already ran K1 (e.g. chunk by chunk behind H2D copies)."""
+        N, T = int(packed.words.shape[0]), int(packed.words.shape[1])
+        self.packed = packed
+        self.resized = P.resize_bilinear_bin(self.packed, target_shape)                                                # R1
+        planes = P.resize_nearest(prompt_masks, self.resized.H, self.resized.W)                                        # R2
+        g = P.gathered_inter(self.resized, planes, self.frame_idx_dev)                                                 # K2 gather
+        inter = P.pairwise_inter_matrix(self.packed)                                                                   # K2 N x N
+        hg, hi, hc = self._pinned(N, int(planes.words.shape[0]), T)
+        hg.copy_(g, non_blocking=True)
+        hi.copy_(inter, non_blocking=True)
+        hc.copy_(counts.reshape(3, N, T), non_blocking=True)
+        self.event.record(torch.cuda.current_stream(self.device))
+        self.counts = counts
+
+    def finish(self, miou_thresh_st: Optional[float] = None) -> dict:
+        self.event.synchronize()
+        hg, hi, hc = (t.numpy() for t in self._host)
+        state = GreedyState(self.prompt_meta, self.n_frames, mode=self.mode, **self.rules)
+        M = iou_from_counts(hg[0], hg[1], hg[2])
+        while (batch := state.next_batch()) is not None:
+            state.apply_iou_rows(batch, M[batch])
+        res = state.result()
+        thr = state.miou_thresh if miou_thresh_st is None else miou_thresh_st
+        iou = P.iou_matrix_from_inter(hi)
+        n = iou.shape[0]
+        alive = np.ones(n, dtype=bool)
+        by = {}
+        for i in range(n):
+            if not alive[i]:
+                continue
+            hit = np.nonzero(alive[i + 1:] & (iou[i, i + 1:] > thr))[0] + i + 1
+            alive[hit] = False
+            for j in hit.tolist():
+                by[j] = i
+        with np.errstate(divide="ignore", invalid="ignore"):
+            stability = hc[0] / hc[2]
+        res.update({"kept_spatiotemporal": np.nonzero(alive)[0].tolist(), "suppressed_by_spatiotemporal": by,
+                    "inter": hi.copy(), "stability": stability, "iou_gather": M})
+        return res

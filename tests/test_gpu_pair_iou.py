@@ -109,7 +109,7 @@ def test_track_dedup_matches_golden(golden, case):
 def test_track_dedup_from_logits_roundtrip():
     from sola_b200 import dedup, synth
     import sola_b200 as S
-    logits, prompts = synth.dedup_candidates(12, 8, 72, 128, seed=5, device="cpu")
+    logits, prompts = synth.dedup_candidates(12, 8, 72, 128, seed=5, device="cpu", n_clusters=2, jitter=1)
     dd = dedup.TrackDedup(prompts, 8, mode="grid", n_max_tracks=64, batch_size=4)
     masklets_f32 = (logits > 0).float()
     track_fn = lambda frame, batch: {p["prompt_id"]: masklets_f32[p["prompt_id"]] for p in batch}
@@ -120,3 +120,34 @@ def test_track_dedup_from_logits_roundtrip():
     ref = GO.grid_greedy([dict(p) for p in prompts], 8, track_fn, bin_size=4, n_max_tracks=64, batch_size=4)
     assert res["batches"] == ref["batches"] and res["tracked"] == ref["tracked"] and res["filtered"] == ref["filtered"]
     assert len(res["filtered"]) > 0
+
+
+def test_video_dedup_job_matches_session_and_oracle():
+    """The pipelined whole-video job (enqueue / finish) gives the same kept sets as the batch-by-batch session, the
+    oracle loops, and the N x N greedy; two jobs in flight do not disturb each other."""
+    import sola_b200 as S
+    from sola_b200 import dedup, synth
+    logits, prompts = synth.dedup_candidates(16, 8, 72, 128, seed=6, device="cpu", n_clusters=3, jitter=1)
+    meta = [{"prompt_id": p["prompt_id"], "frame_idx": p["frame_idx"]} for p in prompts]
+    pm = torch.from_numpy(np.stack([p["segmentation"] for p in prompts])).cuda()
+    lg = logits.cuda()
+    jobs = [dedup.VideoDedupJob(meta, 8, mode="grid", n_max_tracks=64, batch_size=4, miou_thresh=0.7) for _ in range(2)]
+    jobs[0].enqueue(lg, pm)
+    jobs[1].enqueue(lg.flip(0).contiguous(), pm)            # a different video in flight at the same time
+    r0 = jobs[0].finish()
+    jobs[1].finish()
+    masks = (logits > 0).float()
+    ref = GO.grid_greedy([dict(p) for p in prompts], 8, lambda f, b: {p["prompt_id"]: masks[p["prompt_id"]] for p in b},
+                         bin_size=4, n_max_tracks=64, batch_size=4)
+    assert r0["batches"] == ref["batches"] and r0["tracked"] == ref["tracked"] and r0["filtered"] == ref["filtered"]
+    assert r0["filtered_by"] == ref["filtered_by"] and len(r0["filtered"]) > 0
+    dd = dedup.TrackDedup(prompts, 8, mode="grid", n_max_tracks=64, batch_size=4)
+    packed = S.pack_masks(masks.numpy())
+    assert dd.run_offline(S.resize_bilinear_bin(packed)) ["tracked"] == r0["tracked"]
+    kept, by, iou, inter = dedup.dedup_matrix(packed, 0.7)
+    assert kept == r0["kept_spatiotemporal"] and by == r0["suppressed_by_spatiotemporal"]
+    np.testing.assert_array_equal(inter, r0["inter"])
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        np.testing.assert_array_equal(r0["stability"], O.get_stability_score(logits.numpy()))

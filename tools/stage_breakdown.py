@@ -7,6 +7,7 @@ from sola_b200 import dedup
 import bench
 
 w = bench.Workload(torch.device("cuda", 0), seed=1236, n_tracks=64, n_frames=80)
+w.make_jobs()
 for _ in range(3):
     w.step()
 torch.cuda.synchronize()
@@ -32,7 +33,9 @@ _, out["G1_per_batch_sessions"] = timed(per_batch)
 _, out["K2_pair_iou_st_kernel_only"] = timed(lambda: S.pairwise_inter_matrix(packed))
 _, out["K2_dedup_matrix_total"] = timed(lambda: dedup.dedup_matrix(packed, 0.7))
 _, out["stability_d2h"] = timed(lambda: S.packed.stability_from_counts(counts))
-_, out["full_step"] = timed(lambda: w.step())
+_, out["full_step_sync"] = timed(lambda: w.step())
+_, t10 = timed(lambda: w.run_steps(10), reps=3)
+out["pipelined_step"] = t10 / 10
 pred = S.unpack_masks(packed[0], torch.float32); gt = S.unpack_masks(packed[1], torch.float32)
 _, out["K3_frame_counts_f32_80x720p"] = timed(lambda: S.frame_counts(pred, gt))
 out["K3_GBps"] = 2 * pred.numel() * 4 / (out["K3_frame_counts_f32_80x720p"] * 1e-3) / 1e9
