@@ -7,7 +7,7 @@ One step = one video's pass over the path, inputs already in HBM:
     R1  bilinear resize to 540 x 960 + > 0.5 of all 5120 packed planes             (seg_utils.reshape_masklet)
     R2  nearest resize + pack of the 64 prompt masks
     G1  reference-order greedy filter: K2-gather IoU per tracked batch + host suppression
-    K2  64 x 64 spatio-temporal intersection matrix at native resolution + index-order greedy (compute_masklet_iou semantics)
+    K2  64 x 64 spatio-temporal intersection matrix of the resized masklets + index-order greedy (compute_masklet_iou semantics)
     one D2H of the stability counts -> float64 scores
 `value` = masklet-frames processed by all ranks / max-over-ranks device time (weak scaling: one video per GPU per step, no
 data-path collective).  `e2e` = the same step with the logits and prompt masks starting in pinned HOST memory (H2D inside the
@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--streams", type=int, default=1, choices=[1, 2], help="videos in flight on separate CUDA streams")
     return ap.parse_args()
 
 
@@ -101,8 +102,9 @@ class ClockSampler:
 # the step (product path)
 # ---------------------------------------------------------------------------------------------------------------
 class Workload:
-    def __init__(self, device, seed, n_tracks, n_frames):
+    def __init__(self, device, seed, n_tracks, n_frames, n_streams=1):
         import sola_b200 as S
+        self.n_streams = n_streams
         from sola_b200 import synth
         self.S, self.device = S, device
         self.N, self.T, self.H, self.W = n_tracks, n_frames, CFG["H"], CFG["W"]
@@ -120,22 +122,34 @@ class Workload:
         mk = lambda: dedup.VideoDedupJob(self.prompt_meta, self.T, device=self.device, mode="grid", bin_size=CFG["bin_size"],
                                          n_max_tracks=CFG["n_max_tracks"], batch_size=CFG["batch_size"], miou_thresh=CFG["miou_thresh"])
         self.jobs = [mk(), mk()]
+        # one stream per in-flight video: the HBM-bound K1 of video k+1 overlaps the ALU/XU-bound R1 + K2 of video k
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.jobs] if self.n_streams > 1 else [None, None]
+        self.packed_slots = [self.packed, self.S.PackedMasks.empty((self.N, self.T), self.H, self.W, self.device)] if self.n_streams > 1 else [self.packed, self.packed]
+        self.counts_slots = [self.counts, torch.empty_like(self.counts)] if self.n_streams > 1 else [self.counts, self.counts]
 
     def enqueue(self, slot, logits=None, prompt_masks=None, record_k1=False):
         """Device half of one step (no synchronisation): K1, R1, R2, K2-gather, K2 N x N, async read-back."""
         job = self.jobs[slot]
         logits = self.logits if logits is None else logits
         prompt_masks = self.prompt_masks_dev if prompt_masks is None else prompt_masks
+        if self.streams[slot] is not None:
+            with torch.cuda.stream(self.streams[slot]):
+                self._enqueue(job, slot, logits, prompt_masks, record_k1)
+        else:
+            self._enqueue(job, slot, logits, prompt_masks, record_k1)
+
+    def _enqueue(self, job, slot, logits, prompt_masks, record_k1):
+        packed_out, counts_out = self.packed_slots[slot], self.counts_slots[slot]
         if record_k1:
             # K1 is the first launch of the step: bracket it with events on the launching stream
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            packed, counts = self.S.binarize_pack_stability(logits, 0.0, 1.0, out=self.packed, counts_out=self.counts)
+            packed, counts = self.S.binarize_pack_stability(logits, 0.0, 1.0, out=packed_out, counts_out=counts_out)
             e1.record()
             self.k1_events.append((e0, e1))
             job.enqueue_after_k1(packed, counts, prompt_masks)
         else:
-            job.enqueue(logits, prompt_masks, packed_out=self.packed, counts_out=self.counts)
+            job.enqueue(logits, prompt_masks, packed_out=packed_out, counts_out=counts_out)
 
     def finish(self, slot):
         """Host half: wait for that step's read-back, replay both greedy filters, stability scores."""
@@ -168,7 +182,9 @@ def checks(w: Workload, out) -> dict:
     assert np.array_equal(inter, inter.T), "intersection matrix not symmetric"
     area = np.diag(inter)
     c = w.counts.view(3, w.N, w.T).cpu().numpy()
-    assert np.array_equal(c[1].sum(1, dtype=np.int64), area), "diag(inter) != sum of K1 areas (checksum of checksums)"
+    _, r_area = w.S.resize_bilinear_bin(w.packed, want_area=True)                      # untimed: R1's own per-frame areas
+    r_area = r_area.view(w.N, w.T).cpu().numpy().sum(1, dtype=np.int64)
+    assert np.array_equal(r_area, area), "diag(inter) != sum of R1 areas (checksum of checksums)"
     assert (c[0] <= c[1]).all() and (c[1] <= c[2]).all(), "stability counts not nested"
     assert (inter <= np.minimum(area[:, None], area[None, :])).all()
     # sub-sample vs the oracle: 2 tracks x 3 frames of planes + their pair intersection
@@ -211,7 +227,7 @@ def cpu_reference_step(logits_cpu: torch.Tensor, prompts, n_pairs_st: int):
         for j in range(i + 1, S_):
             if n_st >= n_pairs_st:
                 break
-            O.compute_masklet_iou(masklets[i], masklets[j])                                                  # seg_utils.py:110
+            O.compute_masklet_iou(resized[i], resized[j])          # seg_utils.py:110 on the resized masklets (all that exist after grid :248-250)
             n_st += 1
     t_st = (time.perf_counter() - t0) / max(n_st, 1)
     return t_lin, t_g, t_st
@@ -274,7 +290,7 @@ def main():
     import sola_b200 as S
     S.load_library()
 
-    w = Workload(device, seed=1234 + 2 + 1000 * rank, n_tracks=n_tracks, n_frames=n_frames)
+    w = Workload(device, seed=1234 + 2 + 1000 * rank, n_tracks=n_tracks, n_frames=n_frames, n_streams=args.streams)
     w.make_jobs()
     torch.cuda.synchronize()
 

@@ -70,8 +70,8 @@ resize_bilinear_tiled_kernel(const uint32_t* __restrict__ in, int n_frames, int 
   const int Wp = (W + 31) >> 5, owp = (ow + 31) >> 5;
   XParam* xtab = reinterpret_cast<XParam*>(r1_smem);                         // [owp * 32]
   YParam* ytab = reinterpret_cast<YParam*>(xtab + owp * 32);                 // [R1_TR]
-  int2* ctab = reinterpret_cast<int2*>(ytab + R1_TR);                        // [owp rounded up to even]: source word window per output word column
-  uint32_t* tile = reinterpret_cast<uint32_t*>(ctab + ((owp + 1) & ~1));     // [2][max_in_rows * Wp]
+  int4* ctab = reinterpret_cast<int4*>(ytab + R1_TR);                        // [owp]: source window per output word column: first / last word, care masks
+  uint32_t* tile = reinterpret_cast<uint32_t*>(ctab + owp);                  // [2][max_in_rows * Wp]
   const int tile_words_max = max_in_rows * Wp;
   const int tid = threadIdx.x, lane = tid & 31;
   const int oy0 = blockIdx.x * R1_TR;
@@ -91,9 +91,9 @@ resize_bilinear_tiled_kernel(const uint32_t* __restrict__ in, int n_frames, int 
     ytab[tid] = YParam{a.i0 - ylo, a.i1 - ylo, a.l0, a.l1};
   }
   for (int c = tid; c < owp; c += R1_THREADS) {
-    const int wlo = bilinear_axis(c * 32, sx, W).i0 >> 5;
-    const int whi = bilinear_axis(min(c * 32 + 31, ow - 1), sx, W).i1 >> 5;
-    ctab[c] = make_int2(wlo, whi);
+    const int xa = bilinear_axis(c * 32, sx, W).i0;                       // first source pixel any lane of this word reads
+    const int xb = bilinear_axis(min(c * 32 + 31, ow - 1), sx, W).i1;     // last one
+    ctab[c] = make_int4(xa >> 5, xb >> 5, (int)(0xffffffffu << (xa & 31)), (int)(0xffffffffu >> (31 - (xb & 31))));
   }
   const long long FW = (long long)H * Wp, oFW = (long long)oh * owp;
   const bool vec16 = ((Wp & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);   // every row block starts 16-byte aligned
@@ -132,15 +132,19 @@ resize_bilinear_tiled_kernel(const uint32_t* __restrict__ in, int n_frames, int 
         r = i / owp; c = i - r * owp;
         const YParam yp = ytab[r];
         const int px_first = c * 32, px_last = min(c * 32 + 31, ow - 1);
-        const int2 win = ctab[c];
+        const int4 win = ctab[c];
         const int wlo = win.x, whi = win.y;
         const uint32_t* r0 = t + yp.y0 * Wp;
         const uint32_t* r1 = t + yp.y1 * Wp;
         uint32_t any1 = 0u, all1 = 0xffffffffu;
         for (int w = wlo; w <= whi; ++w) {
+          // only the source pixels [xa, xb] matter: bits outside are forced to "don't care" for both tests
+          uint32_t care = 0xffffffffu;
+          if (w == wlo) care &= (uint32_t)win.z;
+          if (w == whi) care &= (uint32_t)win.w;
           const uint32_t v0 = r0[w], v1 = r1[w];
-          any1 |= v0 | v1;
-          all1 &= v0 & v1;
+          any1 |= (v0 | v1) & care;
+          all1 &= (v0 & v1) | ~care;
         }
         if (any1 == 0u) word = 0u;
         else if (all1 == 0xffffffffu) word = (px_last - px_first == 31) ? 0xffffffffu : ((1u << (px_last - px_first + 1)) - 1u);
@@ -293,7 +297,7 @@ static inline float host_scale(int in_size, int out_size) { return (float)in_siz
 
 static int grid_for_warps(long long warps) {
   long long blocks = (warps + 7) / 8;
-  const long long cap = (long long)num_sms() * 32;
+  const long long cap = 1ll << 20;                   // one warp per output word up to ~8M words, grid-stride beyond
   if (blocks > cap) blocks = cap;
   return (int)(blocks < 1 ? 1 : blocks);
 }
@@ -315,7 +319,7 @@ int sola_resize_bilinear_bin_packed(const uint32_t* in_packed, long long n_frame
   // input rows one tile of R1_TR output rows can touch (+2 for the y1 row and rounding)
   long long max_in_rows = (long long)ceil((double)R1_TR * (double)sy) + 3;
   if (max_in_rows > H) max_in_rows = H;
-  const size_t smem = (size_t)owp * 32 * sizeof(XParam) + R1_TR * sizeof(YParam) + (size_t)((owp + 1) & ~1) * sizeof(int2) +
+  const size_t smem = (size_t)owp * 32 * sizeof(XParam) + R1_TR * sizeof(YParam) + (size_t)owp * sizeof(int4) +
                       2 * (size_t)max_in_rows * Wp * sizeof(uint32_t);
   if (smem <= 200 * 1024) {
     SOLA_CUDA(cudaFuncSetAttribute(resize_bilinear_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -254,7 +254,9 @@ class VideoDedupJob:
 
     Two jobs used alternately keep the GPU busy while the host post-processes the previous video (bench.py)."""
 
-    def __init__(self, prompt_meta: Sequence[dict], n_frames: int, *, device=None, mode: str = "grid", **rules):
+    def __init__(self, prompt_meta: Sequence[dict], n_frames: int, *, device=None, mode: str = "grid",
+                 st_on_resized: bool = True, **rules):
+        self.st_on_resized = st_on_resized
         self.prompt_meta = list(prompt_meta)
         self.n_frames = n_frames
         self.mode, self.rules = mode, rules
@@ -285,7 +287,9 @@ class VideoDedupJob:
         self.resized = P.resize_bilinear_bin(self.packed, target_shape)                                                # R1
         planes = P.resize_nearest(prompt_masks, self.resized.H, self.resized.W)                                        # R2
         g = P.gathered_inter(self.resized, planes, self.frame_idx_dev)                                                 # K2 gather
-        inter = P.pairwise_inter_matrix(self.packed)                                                                   # K2 N x N
+        # K2 N x N on the resized planes: after generate_tokens_grid.py:248-250 only the 540x960 masklets exist, so a
+        # masklet-vs-masklet IoU (seg_utils.compute_masklet_iou) in that flow compares those
+        inter = P.pairwise_inter_matrix(self.resized if self.st_on_resized else self.packed)                           # K2 N x N
         hg, hi, hc = self._pinned(N, int(planes.words.shape[0]), T)
         hg.copy_(g, non_blocking=True)
         hi.copy_(inter, non_blocking=True)

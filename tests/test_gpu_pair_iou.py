@@ -144,7 +144,7 @@ def test_video_dedup_job_matches_session_and_oracle():
     dd = dedup.TrackDedup(prompts, 8, mode="grid", n_max_tracks=64, batch_size=4)
     packed = S.pack_masks(masks.numpy())
     assert dd.run_offline(S.resize_bilinear_bin(packed)) ["tracked"] == r0["tracked"]
-    kept, by, iou, inter = dedup.dedup_matrix(packed, 0.7)
+    kept, by, iou, inter = dedup.dedup_matrix(S.resize_bilinear_bin(packed), 0.7)        # the job compares the resized masklets
     assert kept == r0["kept_spatiotemporal"] and by == r0["suppressed_by_spatiotemporal"]
     np.testing.assert_array_equal(inter, r0["inter"])
     import warnings
