@@ -164,3 +164,22 @@ def dedup_matrix_greedy(iou: np.ndarray, miou_thresh: float = 0.7):
                 alive[j] = False
                 by[j] = i
     return [i for i in range(n) if alive[i]], by
+
+
+def part_suppression(masks: torch.Tensor, part_thresh: float = 0.7, compute_P=O.compute_P, autocast_bf16: bool = False):
+    """generate_prompts_grid.py:105-116 (script loop, parity unpinned): masks (N,H,W) fp32 sorted by area descending.
+    `autocast_bf16` emulates the bf16 rounding of the GEMV output that the reference's CUDA autocast context applies."""
+    n = masks.shape[0]
+    is_part = torch.tensor([False] * n)
+    for k in range(n - 1):
+        if is_part[k]:
+            continue
+        if autocast_bf16:
+            flat = masks.reshape(n, -1)
+            inter = (flat @ masks[k].reshape(-1, 1)).to(torch.bfloat16).float()
+            Pk = (inter / flat.sum(dim=1, keepdim=True)).squeeze(1)
+        else:
+            Pk = compute_P(masks, masks[k])
+        is_part[Pk > part_thresh] = True
+        is_part[k] = False
+    return is_part
