@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--streams", type=int, default=1, choices=[1, 2], help="videos in flight on separate CUDA streams")
+    ap.add_argument("--no-fuse", action="store_true", help="run K1 and R1 as two kernels instead of the fused one")
     return ap.parse_args()
 
 
@@ -102,9 +103,10 @@ class ClockSampler:
 # the step (product path)
 # ---------------------------------------------------------------------------------------------------------------
 class Workload:
-    def __init__(self, device, seed, n_tracks, n_frames, n_streams=1):
+    def __init__(self, device, seed, n_tracks, n_frames, n_streams=1, fused=True):
         import sola_b200 as S
         self.n_streams = n_streams
+        self.fused = fused
         from sola_b200 import synth
         self.S, self.device = S, device
         self.N, self.T, self.H, self.W = n_tracks, n_frames, CFG["H"], CFG["W"]
@@ -115,7 +117,10 @@ class Workload:
         self.packed = S.PackedMasks.empty((self.N, self.T), self.H, self.W, device)                   # reused outputs
         self.counts = torch.empty((3, self.N * self.T), dtype=torch.int32, device=device)
         self.k1_events = []
-        self.k1_bytes = self.N * self.T * (self.H * self.W * 4 + self.H * ((self.W + 31) // 32) * 4 + 12)
+        oh, ow = S.packed.default_target_shape(self.H, self.W)
+        self.k1_bytes = self.N * self.T * (self.H * self.W * 4 + self.H * ((self.W + 31) // 32) * 4 + 12)          # logits in, planes + 3 counts out
+        if fused:
+            self.k1_bytes += self.N * self.T * oh * ((ow + 31) // 32) * 4                                           # + resized planes out
 
     def make_jobs(self):
         from sola_b200 import dedup
@@ -140,16 +145,21 @@ class Workload:
 
     def _enqueue(self, job, slot, logits, prompt_masks, record_k1):
         packed_out, counts_out = self.packed_slots[slot], self.counts_slots[slot]
+        S = self.S
+        # the dominant kernel is the first launch of the step: bracket it with events on the launching stream
         if record_k1:
-            # K1 is the first launch of the step: bracket it with events on the launching stream
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            packed, counts = self.S.binarize_pack_stability(logits, 0.0, 1.0, out=packed_out, counts_out=counts_out)
+        if self.fused:
+            packed, counts, resized = S.binarize_pack_resize(logits, 0.0, 1.0, out=packed_out, counts_out=counts_out)      # K1 + R1
+        else:
+            packed, counts = S.binarize_pack_stability(logits, 0.0, 1.0, out=packed_out, counts_out=counts_out)            # K1
+        if record_k1:
             e1.record()
             self.k1_events.append((e0, e1))
-            job.enqueue_after_k1(packed, counts, prompt_masks)
-        else:
-            job.enqueue(logits, prompt_masks, packed_out=packed_out, counts_out=counts_out)
+        if not self.fused:
+            resized = S.resize_bilinear_bin(packed)                                                                        # R1
+        job._enqueue_tail(packed, resized, counts, prompt_masks)                                                           # R2, K2 gather, K2 N x N, read-backs
 
     def finish(self, slot):
         """Host half: wait for that step's read-back, replay both greedy filters, stability scores."""
@@ -290,7 +300,7 @@ def main():
     import sola_b200 as S
     S.load_library()
 
-    w = Workload(device, seed=1234 + 2 + 1000 * rank, n_tracks=n_tracks, n_frames=n_frames, n_streams=args.streams)
+    w = Workload(device, seed=1234 + 2 + 1000 * rank, n_tracks=n_tracks, n_frames=n_frames, n_streams=args.streams, fused=not args.no_fuse)
     w.make_jobs()
     torch.cuda.synchronize()
 
@@ -396,7 +406,8 @@ def main():
         "clocks": clk.summary(),
         "gpu_launches": int(launches),
         "e2e": e2e,
-        "roofline": {"bound": "hbm", "kernel": "pack_flat_kernel<float, THRESH3> (K1 binarise+pack+stability)",
+        "roofline": {"bound": "hbm", "kernel": ("fused_pack_resize_kernel<float> (K1+R1: binarise+pack+stability+resize)" if w.fused
+                                                else "pack_flat_kernel<float, THRESH3> (K1 binarise+pack+stability)"),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                      "bytes_per_launch": w.k1_bytes, "ms_per_launch": k1_ms, "share_of_step": k1_ms / (max_ms / args.steps),
                      "traffic": None},

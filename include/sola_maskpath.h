@@ -106,6 +106,17 @@ int sola_resize_nearest_u8(const uint8_t* in, long long n_frames, int H, int W, 
 int sola_resize_nearest_packed(const uint32_t* in_packed, long long n_frames, int H, int W, int oh, int ow,
                                uint32_t* out_packed, int* area, sola_stream_t stream);
 
+/* K1 + R1 fused: one pass over the logits yields the full-resolution packed planes, the stability counts AND the
+ * bilinear-resized packed planes (replaces generate_tokens_grid.py:215-224 + prompt_generator.py:169-186 + seg_utils.py:145-160).
+ * resized_out (n_frames, oh, owp) is required; packed_out / counts / area_resized may be NULL.  Falls back internally to the
+ * two separate kernels (same results) when W % 32 != 0 or the base pointer is not 16-byte aligned. */
+int sola_binarize_pack_resize_f32(const float* logits, long long n_frames, int H, int W, int oh, int ow, double thr, double off,
+                                  uint32_t* packed_out, uint32_t* resized_out, int* cnt_hi, int* cnt_mid, int* cnt_lo,
+                                  int* area_resized, sola_stream_t stream);
+int sola_binarize_pack_resize_bf16(const void* logits_bf16, long long n_frames, int H, int W, int oh, int ow, double thr, double off,
+                                   uint32_t* packed_out, uint32_t* resized_out, int* cnt_hi, int* cnt_mid, int* cnt_lo,
+                                   int* area_resized, sola_stream_t stream);
+
 /* ---- boundary F (extension; no reference implementation — DAVIS definition, see oracle/boundary_oracle.py) --
  * pred, gt packed (n_frames, H, Wp); radius = bound_pix; counts int32 [n_frames] each:
  * n_fg = |bmap(pred)|, n_gt = |bmap(gt)|, fg_match = |bmap(pred) & dilate(bmap(gt))|, gt_match = |bmap(gt) & dilate(bmap(pred))|. */

@@ -14,7 +14,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsola_maskpath.so")
 STAMP = os.path.join(LIB_DIR, "libsola_maskpath.stamp")
 
-SOURCES = ["abi.cu", "binarize_pack.cu", "counts.cu", "pair_iou.cu", "resize.cu", "boundary.cu", "rle.cu"]
+SOURCES = ["abi.cu", "binarize_pack.cu", "counts.cu", "pair_iou.cu", "resize.cu", "fused_pack_resize.cu", "boundary.cu", "rle.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

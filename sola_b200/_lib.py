@@ -35,6 +35,8 @@ SIGNATURES = {
     "sola_resize_bilinear_bin_f32": [_P, _LL, _I, _I, _I, _I, _P, _P, _P, _P],
     "sola_resize_nearest_u8": [_P, _LL, _I, _I, _I, _I, _P, _P, _P],
     "sola_resize_nearest_packed": [_P, _LL, _I, _I, _I, _I, _P, _P, _P],
+    "sola_binarize_pack_resize_f32": [_P, _LL, _I, _I, _I, _I, _D, _D, _P, _P, _P, _P, _P, _P, _P],
+    "sola_binarize_pack_resize_bf16": [_P, _LL, _I, _I, _I, _I, _D, _D, _P, _P, _P, _P, _P, _P, _P],
     "sola_boundary_counts": [_P, _P, _LL, _I, _I, _I, _P, _P, _P, _P, _P],
 }
 _RESTYPES = {

@@ -17,144 +17,9 @@
 //   * for the stored plane the L x L slot matrix held by each group of L lanes is transposed with log2(L)
 //     shuffle+select steps, after which every lane owns one finished word, and the warp stores 128 contiguous bytes.
 // HBM traffic is exactly the algorithmic minimum: each logit is read once, each packed word written once.
-#include "common.cuh"
-#include <type_traits>
+#include "pack_core.cuh"
 
 namespace sola {
-
-enum PackMode { MODE_THRESH3 = 0, MODE_THRESH1 = 1, MODE_NONZERO = 2 };
-
-struct Thresholds {
-  float mid, hi, lo;
-};
-
-template <typename T> struct ElemTraits;
-template <> struct ElemTraits<float> { static constexpr int E = 4; };
-template <> struct ElemTraits<__nv_bfloat16> { static constexpr int E = 8; };
-template <> struct ElemTraits<uint8_t> { static constexpr int E = 16; };
-
-__device__ __forceinline__ uint32_t gt_bit(float x, float t) { return x > t ? 1u : 0u; }   // NaN -> 0
-
-// ---- per-128-bit-load predicate extraction -------------------------------------------------------------------
-// Threshold modes use the sign of (t - x): with IEEE subtraction (denormals kept, canonical positive NaN on sm_100)
-// sign(t - x) == 1  <=>  x > t, for every input including +-0, +-inf, denormals and NaN (-> 0, as `NaN > t` is False).
-// That is one FADD on the fma pipe plus one funnel shift on the alu pipe per (element, threshold) — the shift pushes the
-// sign bit into an accumulator — instead of FSETP + SEL + shift/or, which kept the alu pipe ~70 % busy at HBM speed.
-// Elements are pushed last-to-first so that element 0 of the first vector ends up in bit 0.
-__device__ __forceinline__ uint32_t push_gt(uint32_t acc, float x, float t) {
-  return __funnelshift_l(__float_as_uint(__fsub_rn(t, x)), acc, 1);
-}
-
-
-// Returns E bits (element c of the vector -> bit c) for mid, and (MODE_THRESH3 only) hi / lo.   [MODE_NONZERO path]
-template <int MODE>
-__device__ __forceinline__ void vec_bits(const uint4& raw, const Thresholds& th, float, uint32_t& mid, uint32_t& hi, uint32_t& lo) {
-  const float v[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
-  mid = hi = lo = 0;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (MODE == MODE_NONZERO) {
-      mid |= (v[c] != 0.0f ? 1u : 0u) << c;
-    } else {
-      mid |= gt_bit(v[c], th.mid) << c;
-      if (MODE == MODE_THRESH3) {
-        hi |= gt_bit(v[c], th.hi) << c;
-        lo |= gt_bit(v[c], th.lo) << c;
-      }
-    }
-  }
-}
-
-// push the E elements of one vector (last element first) into the three accumulators
-template <int MODE>
-__device__ __forceinline__ void vec_push(const uint4& raw, const Thresholds& th, float, uint32_t& mid, uint32_t& hi, uint32_t& lo) {
-  const float v[4] = {__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w)};
-#pragma unroll
-  for (int c = 3; c >= 0; --c) {
-    mid = push_gt(mid, v[c], th.mid);
-    if (MODE == MODE_THRESH3) { hi = push_gt(hi, v[c], th.hi); lo = push_gt(lo, v[c], th.lo); }
-  }
-}
-
-template <int MODE>
-__device__ __forceinline__ void vec_push(const uint4& raw, const Thresholds& th, __nv_bfloat16, uint32_t& mid, uint32_t& hi, uint32_t& lo) {
-  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-  for (int c = 7; c >= 0; --c) {
-    const float x = __uint_as_float((c & 1) ? (w[c >> 1] & 0xffff0000u) : (w[c >> 1] << 16));   // bf16 -> fp32 is exact
-    mid = push_gt(mid, x, th.mid);
-    if (MODE == MODE_THRESH3) { hi = push_gt(hi, x, th.hi); lo = push_gt(lo, x, th.lo); }
-  }
-}
-
-template <int MODE>
-__device__ __forceinline__ void vec_push(const uint4&, const Thresholds&, uint8_t, uint32_t&, uint32_t&, uint32_t&) {}
-
-template <int MODE>
-__device__ __forceinline__ void vec_bits(const uint4& raw, const Thresholds& th, __nv_bfloat16, uint32_t& mid, uint32_t& hi, uint32_t& lo) {
-  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-  mid = hi = lo = 0;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    // bf16 -> fp32 is exact: the 16 bits are the high half of the fp32 pattern
-    const float x = __uint_as_float((c & 1) ? (w[c >> 1] & 0xffff0000u) : (w[c >> 1] << 16));
-    if (MODE == MODE_NONZERO) {
-      mid |= (x != 0.0f ? 1u : 0u) << c;
-    } else {
-      mid |= gt_bit(x, th.mid) << c;
-      if (MODE == MODE_THRESH3) {
-        hi |= gt_bit(x, th.hi) << c;
-        lo |= gt_bit(x, th.lo) << c;
-      }
-    }
-  }
-}
-
-// 4 bytes -> 4 bits "byte != 0" (byte k -> bit k).
-__device__ __forceinline__ uint32_t nonzero_bytes4(uint32_t w) {
-  const uint32_t m = __vcmpne4(w, 0u) & 0x01010101u;
-  return (m * 0x01020408u) >> 24;
-}
-__device__ __forceinline__ uint32_t gt_bytes4(uint32_t w, uint32_t thr_rep) {
-  const uint32_t m = __vcmpgtu4(w, thr_rep) & 0x01010101u;
-  return (m * 0x01020408u) >> 24;
-}
-
-template <int MODE>
-__device__ __forceinline__ void vec_bits(const uint4& raw, const Thresholds& th, uint8_t, uint32_t& mid, uint32_t& hi, uint32_t& lo) {
-  hi = lo = 0;
-  if (MODE == MODE_NONZERO) {
-    mid = nonzero_bytes4(raw.x) | (nonzero_bytes4(raw.y) << 4) | (nonzero_bytes4(raw.z) << 8) | (nonzero_bytes4(raw.w) << 12);
-  } else {
-    // u8 "logits": integer compare against floor(threshold), clamped to [0,255]; x > t  <=>  x > floor(t) for integers x
-    const int ti = th.mid < 0.f ? -1 : (th.mid >= 255.f ? 255 : (int)floorf(th.mid));
-    if (ti < 0) { mid = 0xffffu; return; }
-    const uint32_t rep = 0x01010101u * (uint32_t)ti;
-    mid = gt_bytes4(raw.x, rep) | (gt_bytes4(raw.y, rep) << 4) | (gt_bytes4(raw.z, rep) << 8) | (gt_bytes4(raw.w, rep) << 12);
-  }
-}
-
-// ---- L x L slot transpose inside groups of L lanes -----------------------------------------------------------
-template <int E>
-__host__ __device__ constexpr uint32_t keep_mask(int d) {
-  uint32_t m = 0;
-  const uint32_t slot = (E >= 32) ? 0xffffffffu : ((1u << E) - 1u);
-  for (int j = 0; j < 32 / E; ++j)
-    if (!(j & d)) m |= slot << (E * j);
-  return m;
-}
-
-template <int E>
-__device__ __forceinline__ uint32_t transpose_slots(uint32_t x, int lane) {
-  constexpr int L = 32 / E;
-#pragma unroll
-  for (int d = L / 2; d >= 1; d >>= 1) {
-    const uint32_t lo = keep_mask<E>(d);
-    const uint32_t v = __shfl_xor_sync(FULL, x, d);
-    x = (lane & d) ? ((x & ~lo) | ((v >> (E * d)) & lo)) : ((x & lo) | ((v << (E * d)) & ~lo));
-  }
-  return x;
-}
 
 // ---- flat kernel ---------------------------------------------------------------------------------------------
 constexpr int K1_THREADS = 256;

@@ -13,31 +13,10 @@
 //     the contract: kept-track sets flip otherwise.  tests/test_gpu_resize.py checks bit-equality with torch-CUDA.
 // R2  F.interpolate(prompt[None,None], (h, w), mode='nearest') (generate_tokens_grid.py:271-272):
 //       src = min((int)floorf(dst * scale), in - 1), scale = (float)in / out.
-#include "common.cuh"
+#include "resize_core.cuh"
 #include <math.h>
 
 namespace sola {
-
-struct Axis { int i0, i1; float l0, l1; };
-
-__device__ __forceinline__ Axis bilinear_axis(int dst, float scale, int in_size) {
-  float src = __fmaf_rn((float)dst + 0.5f, scale, -0.5f);
-  src = (src >= 0.f) ? src : 0.f;
-  Axis a;
-  a.i0 = (int)src;
-  a.i1 = a.i0 + (a.i0 < in_size - 1 ? 1 : 0);
-  a.l1 = __fsub_rn(src, (float)a.i0);
-  a.l0 = __fsub_rn(1.f, a.l1);
-  return a;
-}
-
-__device__ __forceinline__ float bilinear_val(const Axis& ax, const Axis& ay, float v00, float v01, float v10, float v11) {
-  const float top = __fmaf_rn(ax.l0, v00, __fmul_rn(ax.l1, v01));
-  const float bot = __fmaf_rn(ax.l0, v10, __fmul_rn(ax.l1, v11));
-  return __fmaf_rn(ay.l0, top, __fmul_rn(ay.l1, bot));
-}
-
-__device__ __forceinline__ uint32_t get_bit(const uint32_t* __restrict__ row, int x) { return (__ldg(row + (x >> 5)) >> (x & 31)) & 1u; }
 
 // ---- R1 from packed planes -----------------------------------------------------------------------------------
 // CTA = one tile of R1_TR output rows x the full output width, walked over a slice of the frames.
@@ -48,12 +27,6 @@ __device__ __forceinline__ uint32_t get_bit(const uint32_t* __restrict__ row, in
 //     resolves the whole word (background / interior) with ~1 instruction per output pixel-row of the warp;
 //   * phase B, one WARP per remaining (edge) word, lane = output pixel: ATen's exact fma sequence on the 4 bits.
 // Output words are written by consecutive threads -> coalesced.
-constexpr int R1_TR = 32;
-constexpr int R1_THREADS = 256;
-
-struct __align__(16) XParam { int x0, x1; float w0, w1; };
-struct __align__(16) YParam { int y0, y1; float h0, h1; };     // rows relative to the tile's first input row
-
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem));
@@ -68,10 +41,9 @@ resize_bilinear_tiled_kernel(const uint32_t* __restrict__ in, int n_frames, int 
                              float sy, float sx, int max_in_rows, uint32_t* __restrict__ out, int* __restrict__ area) {
   extern __shared__ __align__(16) unsigned char r1_smem[];
   const int Wp = (W + 31) >> 5, owp = (ow + 31) >> 5;
-  XParam* xtab = reinterpret_cast<XParam*>(r1_smem);                         // [owp * 32]
-  YParam* ytab = reinterpret_cast<YParam*>(xtab + owp * 32);                 // [R1_TR]
-  int4* ctab = reinterpret_cast<int4*>(ytab + R1_TR);                        // [owp]: source window per output word column: first / last word, care masks
-  uint32_t* tile = reinterpret_cast<uint32_t*>(ctab + owp);                  // [2][max_in_rows * Wp]
+  R1Tables tb;
+  tb.carve(r1_smem, owp);
+  uint32_t* tile = reinterpret_cast<uint32_t*>(r1_smem + R1Tables::bytes(owp));   // [2][max_in_rows * Wp]
   const int tile_words_max = max_in_rows * Wp;
   const int tid = threadIdx.x, lane = tid & 31;
   const int oy0 = blockIdx.x * R1_TR;
@@ -82,19 +54,7 @@ resize_bilinear_tiled_kernel(const uint32_t* __restrict__ in, int n_frames, int 
   const int ylo = bilinear_axis(oy0, sy, H).i0;
   const int yhi = bilinear_axis(oy0 + nrows - 1, sy, H).i1;
   const int n_in_words = (yhi - ylo + 1) * Wp;
-  for (int i = tid; i < owp * 32; i += R1_THREADS) {
-    const Axis a = bilinear_axis(min(i, ow - 1), sx, W);
-    xtab[i] = XParam{a.i0, a.i1, a.l0, a.l1};
-  }
-  if (tid < R1_TR) {
-    const Axis a = bilinear_axis(min(oy0 + tid, oh - 1), sy, H);
-    ytab[tid] = YParam{a.i0 - ylo, a.i1 - ylo, a.l0, a.l1};
-  }
-  for (int c = tid; c < owp; c += R1_THREADS) {
-    const int xa = bilinear_axis(c * 32, sx, W).i0;                       // first source pixel any lane of this word reads
-    const int xb = bilinear_axis(min(c * 32 + 31, ow - 1), sx, W).i1;     // last one
-    ctab[c] = make_int4(xa >> 5, xb >> 5, (int)(0xffffffffu << (xa & 31)), (int)(0xffffffffu >> (31 - (xb & 31))));
-  }
+  tb.build(oy0, ylo, H, W, oh, ow, sy, sx);
   const long long FW = (long long)H * Wp, oFW = (long long)oh * owp;
   const bool vec16 = ((Wp & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);   // every row block starts 16-byte aligned
 
@@ -109,7 +69,6 @@ resize_bilinear_tiled_kernel(const uint32_t* __restrict__ in, int n_frames, int 
     asm volatile("cp.async.commit_group;");
   };
 
-  int area_acc = 0;
   if (f_begin < f_end) prefetch(f_begin, 0);
   for (int f = f_begin; f < f_end; ++f) {
     const int buf = (f - f_begin) & 1;
@@ -120,64 +79,8 @@ resize_bilinear_tiled_kernel(const uint32_t* __restrict__ in, int n_frames, int 
       asm volatile("cp.async.wait_group 0;");
     }
     __syncthreads();                                   // tile of frame f (and, first time round, the tables) visible
-    const uint32_t* t = tile + buf * tile_words_max;
-    const int n_words = nrows * owp;
-    for (int base = 0; base < n_words; base += R1_THREADS) {
-      const int i = base + tid;
-      const bool have = i < n_words;
-      uint32_t word = 0;
-      bool edge = false;
-      int r = 0, c = 0;
-      if (have) {
-        r = i / owp; c = i - r * owp;
-        const YParam yp = ytab[r];
-        const int px_first = c * 32, px_last = min(c * 32 + 31, ow - 1);
-        const int4 win = ctab[c];
-        const int wlo = win.x, whi = win.y;
-        const uint32_t* r0 = t + yp.y0 * Wp;
-        const uint32_t* r1 = t + yp.y1 * Wp;
-        uint32_t any1 = 0u, all1 = 0xffffffffu;
-        for (int w = wlo; w <= whi; ++w) {
-          // only the source pixels [xa, xb] matter: bits outside are forced to "don't care" for both tests
-          uint32_t care = 0xffffffffu;
-          if (w == wlo) care &= (uint32_t)win.z;
-          if (w == whi) care &= (uint32_t)win.w;
-          const uint32_t v0 = r0[w], v1 = r1[w];
-          any1 |= (v0 | v1) & care;
-          all1 &= (v0 & v1) | ~care;
-        }
-        if (any1 == 0u) word = 0u;
-        else if (all1 == 0xffffffffu) word = (px_last - px_first == 31) ? 0xffffffffu : ((1u << (px_last - px_first + 1)) - 1u);
-        else edge = true;
-      }
-      // phase B: the warp resolves its edge words one at a time, lane = output pixel
-      unsigned pending = __ballot_sync(FULL, edge);
-      while (pending) {
-        const int src = __ffs(pending) - 1;
-        pending &= pending - 1;
-        const int rr = __shfl_sync(FULL, r, src), cc = __shfl_sync(FULL, c, src);
-        const int ox = cc * 32 + lane;
-        const XParam xp = xtab[ox];
-        const YParam yp = ytab[rr];
-        const uint32_t* r0 = t + yp.y0 * Wp;
-        const uint32_t* r1 = t + yp.y1 * Wp;
-        // v in {0,1}: w*v is w or +0 exactly, and fma(w0, v00, t) is fl(w0*v00 + t) = fl((w0 & m00) + t)
-        const uint32_t m00 = 0u - ((r0[xp.x0 >> 5] >> (xp.x0 & 31)) & 1u), m01 = 0u - ((r0[xp.x1 >> 5] >> (xp.x1 & 31)) & 1u);
-        const uint32_t m10 = 0u - ((r1[xp.x0 >> 5] >> (xp.x0 & 31)) & 1u), m11 = 0u - ((r1[xp.x1 >> 5] >> (xp.x1 & 31)) & 1u);
-        const uint32_t w0b = __float_as_uint(xp.w0), w1b = __float_as_uint(xp.w1);
-        const float top = __fadd_rn(__uint_as_float(w0b & m00), __uint_as_float(w1b & m01));
-        const float bot = __fadd_rn(__uint_as_float(w0b & m10), __uint_as_float(w1b & m11));
-        const float val = __fmaf_rn(yp.h0, top, __fmul_rn(yp.h1, bot));
-        const uint32_t wv = __ballot_sync(FULL, ox < ow && val > 0.5f);
-        if (lane == src) word = wv;
-      }
-      if (have) {
-        out[f * oFW + (long long)(oy0 + r) * owp + c] = word;
-        area_acc += __popc(word);
-      }
-    }
+    const int area_acc = resize_tile_from_smem(tile + buf * tile_words_max, Wp, tb, nrows, ow, out + f * oFW + (long long)oy0 * owp);
     if (area) {
-      // per-frame area: block reduction, one atomic per CTA per frame
       __shared__ int red[R1_THREADS / 32];
       const int s = warp_sum(area_acc);
       if (lane == 0) red[tid >> 5] = s;
@@ -187,7 +90,6 @@ resize_bilinear_tiled_kernel(const uint32_t* __restrict__ in, int n_frames, int 
         for (int w = 0; w < R1_THREADS / 32; ++w) tot += red[w];
         if (tot) atomicAdd(area + f, tot);
       }
-      area_acc = 0;
     }
     __syncthreads();                                   // everyone done with `buf` before frame f+2 overwrites it
   }
@@ -320,7 +222,7 @@ int sola_resize_bilinear_bin_packed(const uint32_t* in_packed, long long n_frame
   long long max_in_rows = (long long)ceil((double)R1_TR * (double)sy) + 3;
   if (max_in_rows > H) max_in_rows = H;
   const size_t smem = (size_t)owp * 32 * sizeof(XParam) + R1_TR * sizeof(YParam) + (size_t)owp * sizeof(int4) +
-                      2 * (size_t)max_in_rows * Wp * sizeof(uint32_t);
+                      2 * (size_t)max_in_rows * Wp * sizeof(uint32_t);   // == R1Tables::bytes(owp) + double-buffered tile
   if (smem <= 200 * 1024) {
     SOLA_CUDA(cudaFuncSetAttribute(resize_bilinear_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = (oh + R1_TR - 1) / R1_TR;

@@ -255,8 +255,9 @@ class VideoDedupJob:
     Two jobs used alternately keep the GPU busy while the host post-processes the previous video (bench.py)."""
 
     def __init__(self, prompt_meta: Sequence[dict], n_frames: int, *, device=None, mode: str = "grid",
-                 st_on_resized: bool = True, **rules):
+                 st_on_resized: bool = True, fused: bool = True, **rules):
         self.st_on_resized = st_on_resized
+        self.fused = fused
         self.prompt_meta = list(prompt_meta)
         self.n_frames = n_frames
         self.mode, self.rules = mode, rules
@@ -277,14 +278,22 @@ class VideoDedupJob:
     def enqueue(self, logits: torch.Tensor, prompt_masks: torch.Tensor, *, mask_threshold: float = 0.0, threshold_offset: float = 1.0,
                 packed_out: Optional[P.PackedMasks] = None, counts_out: Optional[torch.Tensor] = None, target_shape=None):
         """logits (N, T, H, W) fp32/bf16 and prompt_masks (N, H, W) uint8, both on the device, in prompt order."""
-        packed, counts = P.binarize_pack_stability(logits, mask_threshold, threshold_offset, out=packed_out, counts_out=counts_out)   # K1
-        self.enqueue_after_k1(packed, counts, prompt_masks, target_shape=target_shape)
+        if self.fused:
+            # K1 + R1 in one pass: the resize work hides under the HBM time of reading the logits
+            packed, counts, resized = P.binarize_pack_resize(logits, mask_threshold, threshold_offset, target_shape,
+                                                             out=packed_out, counts_out=counts_out)
+            self._enqueue_tail(packed, resized, counts, prompt_masks)
+        else:
+            packed, counts = P.binarize_pack_stability(logits, mask_threshold, threshold_offset, out=packed_out, counts_out=counts_out)   # K1
+            self.enqueue_after_k1(packed, counts, prompt_masks, target_shape=target_shape)
 
     def enqueue_after_k1(self, packed: P.PackedMasks, counts: torch.Tensor, prompt_masks: torch.Tensor, *, target_shape=None):
         """Same, for callers that already ran K1 (e.g. chunk by chunk behind H2D copies)."""
-        N, T = int(packed.words.shape[0]), int(packed.words.shape[1])
-        self.packed = packed
-        self.resized = P.resize_bilinear_bin(self.packed, target_shape)                                                # R1
+        self._enqueue_tail(packed, P.resize_bilinear_bin(packed, target_shape), counts, prompt_masks)                # R1
+
+    def _enqueue_tail(self, packed: P.PackedMasks, resized: P.PackedMasks, counts: torch.Tensor, prompt_masks: torch.Tensor):
+        N, T = int(resized.words.shape[0]), int(resized.words.shape[1])
+        self.packed, self.resized = packed, resized
         planes = P.resize_nearest(prompt_masks, self.resized.H, self.resized.W)                                        # R2
         g = P.gathered_inter(self.resized, planes, self.frame_idx_dev)                                                 # K2 gather
         # K2 N x N on the resized planes: after generate_tokens_grid.py:248-250 only the 540x960 masklets exist, so a

@@ -140,6 +140,41 @@ def binarize_pack_stability(logits, mask_threshold: float = 0.0, threshold_offse
     return packed, counts
 
 
+def binarize_pack_resize(logits, mask_threshold: float = 0.0, threshold_offset: float = 1.0, target_shape=None, *,
+                         want_packed: bool = True, want_area: bool = False,
+                         out: Optional[PackedMasks] = None, counts_out: Optional[torch.Tensor] = None,
+                         resized_out: Optional[PackedMasks] = None):
+    """K1 + R1 in one pass over the logits: (full-resolution packed planes | None, counts (3, ...), resized packed planes
+    [, per-frame areas of the resized planes]).  Bit-identical to binarize_pack_stability followed by resize_bilinear_bin;
+    the resize work hides under the HBM time of reading the logits."""
+    x = to_device(logits)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    H, W = int(x.shape[-2]), int(x.shape[-1])
+    oh, ow = default_target_shape(H, W) if target_shape is None else (int(target_shape[0]), int(target_shape[1]))
+    lead = tuple(x.shape[:-2])
+    n = int(np.prod(lead, dtype=np.int64)) if lead else 1
+    fusable = (W % 32 == 0) and (x.data_ptr() % 16 == 0)
+    packed = None
+    if want_packed or not fusable:
+        packed = out if out is not None else PackedMasks.empty(lead, H, W, x.device)
+        assert packed.words.is_contiguous() and packed.n_frames == n
+    resized = resized_out if resized_out is not None else PackedMasks.empty(lead, oh, ow, x.device)
+    assert resized.words.is_contiguous() and resized.n_frames == n and (resized.H, resized.W) == (oh, ow)
+    counts = counts_out if counts_out is not None else torch.empty((3, n), dtype=torch.int32, device=x.device)
+    assert counts.is_contiguous() and counts.shape == (3, n) and counts.dtype == torch.int32
+    area = torch.empty((n,), dtype=torch.int32, device=x.device) if want_area else None
+    fn = "sola_binarize_pack_resize_f32" if x.dtype == torch.float32 else "sola_binarize_pack_resize_bf16"
+    with torch.cuda.device(x.device):
+        _lib.call(fn, x.data_ptr(), n, H, W, oh, ow, float(mask_threshold), float(threshold_offset),
+                  _ptr(packed.words) if packed is not None else None, resized.words.data_ptr(),
+                  counts[0].data_ptr(), counts[1].data_ptr(), counts[2].data_ptr(), _ptr(area), _stream(x))
+    counts = counts.view(3, *lead)
+    if want_area:
+        return packed, counts, resized, area.view(*lead) if lead else area
+    return packed, counts, resized
+
+
 def stability_from_counts(counts) -> np.ndarray:
     """float64 hi/lo with numpy's 0/0 -> nan (prompt_generator.py:186)."""
     c = counts.cpu().numpy() if isinstance(counts, torch.Tensor) else np.asarray(counts)

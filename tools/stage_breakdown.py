@@ -20,6 +20,7 @@ def timed(fn, reps=5):
 
 out = {}
 (packed, counts), out["K1_binarize_pack_stability"] = timed(lambda: S.binarize_pack_stability(w.logits, 0.0, 1.0, out=w.packed, counts_out=w.counts))
+_, out["K1R1_fused"] = timed(lambda: S.binarize_pack_resize(w.logits, 0.0, 1.0, out=w.packed, counts_out=w.counts))
 resized, out["R1_resize_bilinear_packed"] = timed(lambda: S.resize_bilinear_bin(packed))
 mk = lambda: dedup.TrackDedup(w.prompt_meta, w.T, mode="grid", prompt_masks=w.prompt_masks_dev, bin_size=4, n_max_tracks=64, batch_size=4, miou_thresh=0.7)
 dd, out["R2_trackdedup_init_nearest"] = timed(mk)
