@@ -117,6 +117,18 @@ int sola_binarize_pack_resize_bf16(const void* logits_bf16, long long n_frames, 
                                    uint32_t* packed_out, uint32_t* resized_out, int* cnt_hi, int* cnt_mid, int* cnt_lo,
                                    int* area_resized, sola_stream_t stream);
 
+/* ---- COCO RLE <-> packed planes (replaces the pycocotools hops: dataloader.py:353-369, seg_utils.py:70-75,93-106) --------
+ * sola_bit_transpose: planes (n, A, Bw) of A x B bits -> (n, B, Aw) (row-major <-> column-major bit planes).
+ * sola_rle_decode_runs: ones-runs [run_start, run_end) in flat column-major pixel index, run_plane = plane of each run
+ *   (device int32 arrays) -> packed_out (n, H, Wp); scratch_colmajor (n, W, Hp) words.
+ * sola_rle_encode_transitions: packed (n, H, Wp) -> per plane the ordered column-major positions where the bit value changes
+ *   (out_pos (n, cap) int32, out_n (n) = number found, may exceed cap); the host turns them into counts + the varint string. */
+int sola_bit_transpose(const uint32_t* in, long long n_planes, int A, int B, uint32_t* out, sola_stream_t stream);
+int sola_rle_decode_runs(const int* run_plane, const int* run_start, const int* run_end, long long n_runs,
+                         long long n_planes, int H, int W, uint32_t* scratch_colmajor, uint32_t* packed_out, sola_stream_t stream);
+int sola_rle_encode_transitions(const uint32_t* packed, long long n_planes, int H, int W, uint32_t* scratch_colmajor,
+                                int cap, int* out_pos, int* out_n, sola_stream_t stream);
+
 /* ---- boundary F (extension; no reference implementation — DAVIS definition, see oracle/boundary_oracle.py) --
  * pred, gt packed (n_frames, H, Wp); radius = bound_pix; counts int32 [n_frames] each:
  * n_fg = |bmap(pred)|, n_gt = |bmap(gt)|, fg_match = |bmap(pred) & dilate(bmap(gt))|, gt_match = |bmap(gt) & dilate(bmap(pred))|. */

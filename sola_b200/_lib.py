@@ -37,6 +37,9 @@ SIGNATURES = {
     "sola_resize_nearest_packed": [_P, _LL, _I, _I, _I, _I, _P, _P, _P],
     "sola_binarize_pack_resize_f32": [_P, _LL, _I, _I, _I, _I, _D, _D, _P, _P, _P, _P, _P, _P, _P],
     "sola_binarize_pack_resize_bf16": [_P, _LL, _I, _I, _I, _I, _D, _D, _P, _P, _P, _P, _P, _P, _P],
+    "sola_bit_transpose": [_P, _LL, _I, _I, _P, _P],
+    "sola_rle_decode_runs": [_P, _P, _P, _LL, _LL, _I, _I, _P, _P, _P],
+    "sola_rle_encode_transitions": [_P, _LL, _I, _I, _P, _I, _P, _P, _P],
     "sola_boundary_counts": [_P, _P, _LL, _I, _I, _I, _P, _P, _P, _P, _P],
 }
 _RESTYPES = {

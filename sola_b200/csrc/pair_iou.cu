@@ -36,6 +36,29 @@ __device__ __forceinline__ int popc4_and(const uint4& a, const uint4& b) {
   return __popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w);
 }
 
+// Carry-save accumulation (Harley-Seal): POPC issues at 16 lanes/clk/SM on sm_100 (measured, profiles/r1_microbench_int_b200.jsonl)
+// against 64 for LOP3, so the plain AND+POPC+IADD loop is POPC-bound.  Per pair we keep bit-sliced counters `ones`, `twos`
+// and feed the four AND-ed words of a k-quad through three 3:2 compressors; only the weight-4 carry word is popcounted:
+//   4 AND + 6 LOP3 + 1 POPC per 4 words  (2.5 alu ops and 0.25 POPC per word instead of 1 and 1).
+// total = 4 * acc4 + 2 * popc(twos) + popc(ones) at the end — exactly the same integer.
+struct Csa { uint32_t ones, twos; int acc4; };
+
+__device__ __forceinline__ void csa32(uint32_t& carry, uint32_t& sum, uint32_t a, uint32_t b, uint32_t c) {
+  const uint32_t u = a ^ b;
+  carry = (a & b) | (u & c);
+  sum = u ^ c;
+}
+
+__device__ __forceinline__ void csa_quad(Csa& st, const uint4& a, const uint4& b) {
+  uint32_t t1, t2, f;
+  csa32(t1, st.ones, st.ones, a.x & b.x, a.y & b.y);
+  csa32(t2, st.ones, st.ones, a.z & b.z, a.w & b.w);
+  csa32(f, st.twos, st.twos, t1, t2);
+  st.acc4 += __popc(f);
+}
+
+__device__ __forceinline__ int csa_total(const Csa& st) { return 4 * st.acc4 + 2 * __popc(st.twos) + __popc(st.ones); }
+
 // tile list: (ti, tj) with ti <= tj, enumerated row-major over the upper triangle
 __device__ __forceinline__ void tile_from_index(int idx, int nt, int& ti, int& tj) {
   int i = 0;
@@ -49,11 +72,11 @@ __device__ __forceinline__ void st_tile_body(const uint32_t* __restrict__ packed
                                              unsigned long long* __restrict__ inter) {
   constexpr int ROWS = DIAG ? PT : 2 * PT;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  int acc[4][4];
+  Csa acc[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0;
+    for (int b = 0; b < 4; ++b) acc[a][b] = Csa{0u, 0u, 0};
 
   // stage loader: ROWS*KQ 16-byte copies, thread t copies (row = c / KQ, q = c % KQ) for c = t, t+256, ...
   auto issue = [&](long long stage, int buf) {
@@ -96,7 +119,7 @@ __device__ __forceinline__ void st_tile_body(const uint32_t* __restrict__ packed
 #pragma unroll
         for (int rj = 0; rj < 4; ++rj) {
           if (DIAG && rj < ri) continue;               // mirror entry is produced by another (ri, rj)
-          acc[ri][rj] += popc4_and(a[ri], b[rj]);
+          csa_quad(acc[ri][rj], a[ri], b[rj]);
         }
     }
   }
@@ -110,7 +133,7 @@ __device__ __forceinline__ void st_tile_body(const uint32_t* __restrict__ packed
       const int i = ti * PT + ty + 16 * ri, j = tj * PT + tx + 16 * rj;
       if (i >= N || j >= N) continue;
       if (DIAG && ri == rj && tx < ty) continue;       // lower half of the 16x16 diagonal blocks
-      const unsigned long long v = (unsigned long long)acc[ri][rj];
+      const unsigned long long v = (unsigned long long)csa_total(acc[ri][rj]);
       if (v == 0) continue;
       atomicAdd(inter + (long long)i * N + j, v);
       if (i != j) atomicAdd(inter + (long long)j * N + i, v);
@@ -240,7 +263,7 @@ int sola_pair_iou_st(const uint32_t* packed, int N, long long words_per_track, l
     const long long stages = (words_per_track + STAGE_WORDS - 1) / STAGE_WORDS;
     long long splits = ((long long)num_sms() * 4 + n_tiles - 1) / n_tiles;
     if (splits > stages) splits = stages;
-    const long long min_splits = (stages + (1 << 20) - 1) >> 20;     // keep int32 partial sums below 2^31
+    const long long min_splits = (stages + (1 << 20) - 1) >> 20;     // keep int32 partial sums (4 * acc4 + ...) below 2^31
     if (splits < min_splits) splits = min_splits;
     if (splits < 1) splits = 1;
     const size_t smem = (size_t)NSTAGE * (2 * PT) * KQ * sizeof(uint4);
