@@ -39,7 +39,7 @@ CFG = dict(n_tracks=64, n_frames=80, H=720, W=1280, miou_thresh=0.7, n_max_track
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sola_b200", choices=["sola_b200", "reference"])
     ap.add_argument("--tracks", type=int, default=CFG["n_tracks"], help="override for quick local checks only")
@@ -64,39 +64,54 @@ def peaks():
 # clocks
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """`nvidia-smi -lms 50` running beside the bench; samples are time-stamped on arrival so that the summary can be
+    restricted to the timed region (the recipe's clocks line, /opt/skills/guides/B200_PROFILING.md)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
-        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.samples, self._proc, self._t = index, [], None, None
 
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+    def _reader(self):
+        try:
+            for line in self._proc.stdout:
+                f = [x.strip() for x in line.split(",")]
+                if len(f) >= 6:
+                    self.samples.append((time.perf_counter(), f))
+        except Exception:
+            pass
 
-    def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+    def start(self):
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
+            self._t = threading.Thread(target=self._reader, daemon=True)
+            self._t.start()
+        except Exception:
+            self._proc = None
         return self
 
-    def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+    def stop(self):
+        if self._proc is not None:
+            try:
+                self._proc.terminate()
+                self._proc.wait(timeout=3)
+            except Exception:
+                pass
 
-    def summary(self):
-        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples if len(s) >= 6 for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+    def summary(self, t0: float, t1: float):
+        inside = [f for (t, f) in self.samples if t0 <= t <= t1]
+        scope = "timed region"
+        if not inside:                      # region shorter than the sampling period: take the samples closest to it
+            near = sorted(self.samples, key=lambda tf: min(abs(tf[0] - t0), abs(tf[0] - t1)))[:3]
+            inside, scope = [f for (_, f) in near], "nearest samples (timed region shorter than the 50 ms sampling period)"
+        num = lambda x: float(x) if x.replace(".", "", 1).isdigit() else None
+        sm = [v for v in (num(f[0]) for f in inside) if v is not None]
+        mx = [v for v in (num(f[1]) for f in inside) if v is not None]
+        reasons = sorted({n for f in inside for n, v in zip(self.NAMES, f[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "scope": scope}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -309,18 +324,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clk = ClockSampler(local_rank).start()
     out = w.run_steps(max(args.warmup, 3))
     info = checks(w, out)
     barrier()
     launches0 = S.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        torch.cuda.nvtx.range_push("timed")
-        ev0.record()
-        out = w.run_steps(args.steps, record_k1=True)
-        ev1.record()
-        barrier()
-        torch.cuda.nvtx.range_pop()
+    torch.cuda.nvtx.range_push("timed")
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    out = w.run_steps(args.steps, record_k1=True)
+    ev1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    torch.cuda.nvtx.range_pop()
+    time.sleep(0.12)                         # let the last in-flight sample arrive
+    clk.stop()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = S.launch_count() - launches0
     k1_ms = float(np.mean([a.elapsed_time(b) for a, b in w.k1_events]))
@@ -403,7 +422,7 @@ def main():
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload, "l2_policy": "inputs larger than L2 (18.9 GB fp32 logits per step vs 126 MB L2)",
                    "kept_sets": info, "parallelism": f"video-sharded x{world}, no data-path collective"},
-        "clocks": clk.summary(),
+        "clocks": clk.summary(t_wall0, t_wall1),
         "gpu_launches": int(launches),
         "e2e": e2e,
         "roofline": {"bound": "hbm", "kernel": ("fused_pack_resize_kernel<float> (K1+R1: binarise+pack+stability+resize)" if w.fused
@@ -415,10 +434,11 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         v, full, sample = cpu_arm(n_tracks, n_frames, 1, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
-    traffic_path = os.path.join(ROOT, "profiles", "k1_traffic.json")
-    if os.path.isfile(traffic_path):
+    traffic_path = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")       # from the committed `ncu --set full` capture
+    if os.path.isfile(traffic_path) and (n_tracks, n_frames) == (CFG["n_tracks"], CFG["n_frames"]):
         with open(traffic_path) as f:
-            line["roofline"]["traffic"] = json.load(f).get("dram_bytes_per_launch")
+            key = "fused_pack_resize_kernel<float>" if w.fused else "pack_flat_kernel<float, THRESH3>"
+            line["roofline"]["traffic"] = json.load(f).get(key, {}).get("dram_bytes_per_launch")
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

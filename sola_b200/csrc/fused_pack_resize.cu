@@ -17,6 +17,7 @@
 #include "pack_core.cuh"
 #include "resize_core.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace sola {
 
@@ -158,7 +159,11 @@ static FusedPlan plan_fused(const void* base, long long n_frames, int H, int W, 
   if (elem_size == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_pack_resize_kernel<float>, FU_THREADS, p.smem);
   else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_pack_resize_kernel<__nv_bfloat16>, FU_THREADS, p.smem);
   if (occ < 1) occ = 1;
-  const int target_ctas = num_sms() * occ * 2;                       // two full waves of resident CTAs
+  // several waves of resident CTAs: finer slices cost a table rebuild per CTA (~5 % of one frame's work) but shrink the
+  // tail where the last CTAs run alone; SOLA_FUSED_WAVES overrides for experiments
+  int waves = 16;
+  if (const char* e = getenv("SOLA_FUSED_WAVES")) { const int v = atoi(e); if (v > 0) waves = v; }
+  const int target_ctas = num_sms() * occ * waves;
   int slices = target_ctas / p.n_bands;
   if (slices < 1) slices = 1;
   if (slices > n_frames) slices = (int)n_frames;

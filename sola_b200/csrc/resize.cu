@@ -168,31 +168,44 @@ __device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
 
 template <bool PACKED_IN>
 __global__ void __launch_bounds__(256)
-resize_nearest_kernel(const void* __restrict__ in_, long long n_frames, int H, int W, int oh, int ow, float sy, float sx,
+resize_nearest_kernel(const void* __restrict__ in_, int H, int W, int oh, int ow, float sy, float sx,
                       uint32_t* __restrict__ out_packed, int* __restrict__ area) {
+  // grid: x = 8-word groups of one output plane, y = plane; one warp per output word, 32-bit index math only
   const int lane = threadIdx.x & 31;
   const int owp = (ow + 31) >> 5, Wp = (W + 31) >> 5;
-  const long long words_per_frame = (long long)oh * owp;
-  const long long total = n_frames * words_per_frame;
-  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long wi = warp0; wi < total; wi += n_warps) {
-    const long long f = wi / words_per_frame;
-    const int rem = (int)(wi - f * words_per_frame);
-    const int oy = rem / owp, owx = rem - oy * owp;
-    const int ox = owx * 32 + lane;
-    bool bit = false;
-    if (ox < ow) {
-      const int y = nearest_src(oy, sy, H), x = nearest_src(ox, sx, W);
-      if (PACKED_IN) bit = get_bit(reinterpret_cast<const uint32_t*>(in_) + (f * H + y) * (long long)Wp, x) != 0u;
-      else bit = __ldg(reinterpret_cast<const uint8_t*>(in_) + (f * H + y) * (long long)W + x) != 0;
-    }
-    const uint32_t word = __ballot_sync(FULL, bit);
-    if (lane == 0) {
-      out_packed[wi] = word;
-      if (area && word) atomicAdd(area + f, __popc(word));
-    }
+  const int words_per_frame = oh * owp;
+  const int wi = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (wi >= words_per_frame) return;
+  const long long f = blockIdx.y;
+  const int oy = wi / owp, owx = wi - oy * owp;
+  const int ox = owx * 32 + lane;
+  bool bit = false;
+  if (ox < ow) {
+    const int y = nearest_src(oy, sy, H), x = nearest_src(ox, sx, W);
+    if (PACKED_IN) bit = get_bit(reinterpret_cast<const uint32_t*>(in_) + (f * H + y) * Wp, x) != 0u;
+    else bit = __ldg(reinterpret_cast<const uint8_t*>(in_) + (f * H + y) * W + x) != 0;
   }
+  const uint32_t word = __ballot_sync(FULL, bit);
+  if (lane == 0) {
+    out_packed[f * words_per_frame + wi] = word;
+    if (area && word) atomicAdd(area + f, __popc(word));
+  }
+}
+
+template <bool PACKED_IN>
+static int launch_nearest(const void* in, long long n_frames, int H, int W, int oh, int ow, uint32_t* out_packed, int* area, cudaStream_t stream) {
+  const int owp = (ow + 31) >> 5;
+  const float sy = (float)H / (float)oh, sx = (float)W / (float)ow;
+  const unsigned gx = (unsigned)((oh * owp + 7) / 8);
+  for (long long f0 = 0; f0 < n_frames; f0 += 65535) {
+    const long long nf = n_frames - f0 < 65535 ? n_frames - f0 : 65535;
+    const char* src = reinterpret_cast<const char*>(in) + (PACKED_IN ? f0 * H * ((W + 31) >> 5) * 4 : f0 * H * (long long)W);
+    resize_nearest_kernel<PACKED_IN><<<dim3(gx, (unsigned)nf), 256, 0, stream>>>(src, H, W, oh, ow, sy, sx, out_packed + f0 * oh * owp,
+                                                                                area ? area + f0 : nullptr);
+    int rc = check_launch("resize_nearest kernel");
+    if (rc != SOLA_OK) return rc;
+  }
+  return SOLA_OK;
 }
 
 static inline float host_scale(int in_size, int out_size) { return (float)in_size / (float)out_size; }
@@ -268,10 +281,7 @@ int sola_resize_nearest_u8(const uint8_t* in, long long n_frames, int H, int W, 
   SOLA_REQUIRE(n_frames >= 0 && H > 0 && W > 0 && oh > 0 && ow > 0, "resize_nearest_u8: bad shape");
   if (n_frames == 0) return SOLA_OK;
   if (area) SOLA_CUDA(cudaMemsetAsync(area, 0, sizeof(int) * n_frames, stream));
-  const long long warps = n_frames * oh * ((ow + 31) >> 5);
-  resize_nearest_kernel<false><<<grid_for_warps(warps), 256, 0, stream>>>(in, n_frames, H, W, oh, ow, host_scale(H, oh), host_scale(W, ow),
-                                                                          out_packed, area);
-  return check_launch("resize_nearest_u8 kernel");
+  return launch_nearest<false>(in, n_frames, H, W, oh, ow, out_packed, area, stream);
 }
 
 int sola_resize_nearest_packed(const uint32_t* in_packed, long long n_frames, int H, int W, int oh, int ow,
@@ -280,10 +290,7 @@ int sola_resize_nearest_packed(const uint32_t* in_packed, long long n_frames, in
   SOLA_REQUIRE(n_frames >= 0 && H > 0 && W > 0 && oh > 0 && ow > 0, "resize_nearest_packed: bad shape");
   if (n_frames == 0) return SOLA_OK;
   if (area) SOLA_CUDA(cudaMemsetAsync(area, 0, sizeof(int) * n_frames, stream));
-  const long long warps = n_frames * oh * ((ow + 31) >> 5);
-  resize_nearest_kernel<true><<<grid_for_warps(warps), 256, 0, stream>>>(in_packed, n_frames, H, W, oh, ow, host_scale(H, oh), host_scale(W, ow),
-                                                                         out_packed, area);
-  return check_launch("resize_nearest_packed kernel");
+  return launch_nearest<true>(in_packed, n_frames, H, W, oh, ow, out_packed, area, stream);
 }
 
 }  // extern "C"
