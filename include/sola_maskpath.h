@@ -85,6 +85,11 @@ int sola_or_merge(const uint32_t* tracks, const uint8_t* select, int K, long lon
  * area_out int64 [N] (may be NULL).  Semantics of seg_utils.compute_masklet_iou (seg_utils.py:110-125) per pair. */
 int sola_pair_iou_st(const uint32_t* packed, int N, long long words_per_track, long long* inter_out, long long* area_out,
                      sola_stream_t stream);
+/* one rank's share of the same matrix (BASELINE config 5: tracks all-gathered, pair tiles split over the ranks): computes the
+ * 64 x 64 tiles part, part + n_parts, ... of the upper triangle (mirrors written too), zeros elsewhere; the sum over parts
+ * (one all-reduce) is the full matrix. */
+int sola_pair_iou_st_part(const uint32_t* packed, int N, long long words_per_track, int part, int n_parts, long long* inter_out,
+                          sola_stream_t stream);
 /* gathered single-frame: tracks (N, T, frame_words), prompts (P, frame_words), frame_idx int32 [P] ->
  * inter (N, P) = |track_i[frame_idx[j]] ∩ prompt_j|, area_t (N, P) = |track_i[frame_idx[j]]|, area_p [P].
  * This is the matrix walked by generate_tokens_grid.py:266-278 / generate_tokens_gdino.py:288-300. */

@@ -142,9 +142,10 @@ __device__ __forceinline__ void st_tile_body(const uint32_t* __restrict__ packed
 
 __global__ void __launch_bounds__(ST_THREADS)
 pair_iou_st_kernel(const uint32_t* __restrict__ packed, int N, long long words, int nt, int n_tiles, int splits,
-                   unsigned long long* __restrict__ inter) {
+                   int tile_first, int tile_step, unsigned long long* __restrict__ inter) {
   extern __shared__ uint4 smem_st[];
-  const int tile = blockIdx.x % n_tiles, split = blockIdx.x / n_tiles;
+  // n_tiles = tiles this launch computes: global tile ids tile_first, tile_first + tile_step, ... (a rank's share)
+  const int tile = tile_first + (blockIdx.x % n_tiles) * tile_step, split = blockIdx.x / n_tiles;
   int ti, tj;
   tile_from_index(tile, nt, ti, tj);
   const long long stages = (words + STAGE_WORDS - 1) / STAGE_WORDS;
@@ -250,32 +251,33 @@ using namespace sola;
 
 extern "C" {
 
-int sola_pair_iou_st(const uint32_t* packed, int N, long long words_per_track, long long* inter_out, long long* area_out,
-                     cudaStream_t stream) {
-  SOLA_REQUIRE(packed && inter_out, "pair_iou_st: null pointer");
+static int launch_pair_iou_st(const uint32_t* packed, int N, long long words_per_track, long long* inter_out, long long* area_out,
+                              int part, int n_parts, cudaStream_t stream) {
   SOLA_REQUIRE(N >= 0 && words_per_track > 0, "pair_iou_st: bad shape N=%d words=%lld", N, words_per_track);
+  SOLA_REQUIRE(n_parts >= 1 && part >= 0 && part < n_parts, "pair_iou_st: bad partition %d / %d", part, n_parts);
   if (N == 0) return SOLA_OK;
+  SOLA_REQUIRE(packed && inter_out, "pair_iou_st: null pointer");
   SOLA_CUDA(cudaMemsetAsync(inter_out, 0, sizeof(long long) * (size_t)N * N, stream));
   const bool fast = (words_per_track % 4 == 0) && aligned16(packed);
   if (fast) {
     const int nt = (N + PT - 1) / PT;
-    const int n_tiles = nt * (nt + 1) / 2;
-    const long long stages = (words_per_track + STAGE_WORDS - 1) / STAGE_WORDS;
-    long long splits = ((long long)num_sms() * 4 + n_tiles - 1) / n_tiles;
-    if (splits > stages) splits = stages;
-    const long long min_splits = (stages + (1 << 20) - 1) >> 20;     // keep int32 partial sums (4 * acc4 + ...) below 2^31
-    if (splits < min_splits) splits = min_splits;
-    if (splits < 1) splits = 1;
-    const size_t smem = (size_t)NSTAGE * (2 * PT) * KQ * sizeof(uint4);
-    static bool attr_set = false;
-    if (!attr_set) {
+    const int all_tiles = nt * (nt + 1) / 2;
+    const int n_tiles = (all_tiles - part + n_parts - 1) / n_parts;          // tiles part, part + n_parts, ...
+    if (n_tiles > 0) {
+      const long long stages = (words_per_track + STAGE_WORDS - 1) / STAGE_WORDS;
+      long long splits = ((long long)num_sms() * 4 + n_tiles - 1) / n_tiles;
+      if (splits > stages) splits = stages;
+      const long long min_splits = (stages + (1 << 20) - 1) >> 20;     // keep int32 partial sums (4 * acc4 + ...) below 2^31
+      if (splits < min_splits) splits = min_splits;
+      if (splits < 1) splits = 1;
+      const size_t smem = (size_t)NSTAGE * (2 * PT) * KQ * sizeof(uint4);
       SOLA_CUDA(cudaFuncSetAttribute(pair_iou_st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
+      SOLA_REQUIRE(splits * n_tiles < (1ll << 31), "pair_iou_st: grid too large");
+      pair_iou_st_kernel<<<(unsigned)(splits * n_tiles), ST_THREADS, smem, stream>>>(
+          packed, N, words_per_track, nt, n_tiles, (int)splits, part, n_parts, reinterpret_cast<unsigned long long*>(inter_out));
     }
-    SOLA_REQUIRE(splits * n_tiles < (1ll << 31), "pair_iou_st: grid too large");
-    pair_iou_st_kernel<<<(unsigned)(splits * n_tiles), ST_THREADS, smem, stream>>>(
-        packed, N, words_per_track, nt, n_tiles, (int)splits, reinterpret_cast<unsigned long long*>(inter_out));
   } else {
+    SOLA_REQUIRE(n_parts == 1, "pair_iou_st: the unaligned fallback does not support partitioning");
     SOLA_REQUIRE(N <= 65535, "pair_iou_st: unaligned fallback supports N <= 65535");
     dim3 grid(N, N);
     pair_iou_st_simple_kernel<<<grid, 256, 0, stream>>>(packed, N, words_per_track, reinterpret_cast<unsigned long long*>(inter_out));
@@ -286,6 +288,18 @@ int sola_pair_iou_st(const uint32_t* packed, int N, long long words_per_track, l
     SOLA_CUDA(cudaMemcpy2DAsync(area_out, sizeof(long long), inter_out, sizeof(long long) * ((size_t)N + 1), sizeof(long long), N,
                                 cudaMemcpyDeviceToDevice, stream));
   return SOLA_OK;
+}
+
+int sola_pair_iou_st(const uint32_t* packed, int N, long long words_per_track, long long* inter_out, long long* area_out,
+                     cudaStream_t stream) {
+  return launch_pair_iou_st(packed, N, words_per_track, inter_out, area_out, 0, 1, stream);
+}
+
+// One rank's share of the N x N matrix: 64 x 64 tiles part, part + n_parts, ... of the upper triangle (both mirror halves are
+// written); every other entry of inter_out is left 0, so summing the outputs of all parts (an all-reduce) gives the full matrix.
+int sola_pair_iou_st_part(const uint32_t* packed, int N, long long words_per_track, int part, int n_parts, long long* inter_out,
+                          cudaStream_t stream) {
+  return launch_pair_iou_st(packed, N, words_per_track, inter_out, nullptr, part, n_parts, stream);
 }
 
 int sola_pair_iou_gather(const uint32_t* tracks, const uint32_t* prompts, const int* frame_idx, int N, int P, int T,

@@ -305,6 +305,17 @@ def pairwise_inter_matrix(tracks: PackedMasks) -> torch.Tensor:
     return inter
 
 
+def pairwise_inter_matrix_part(tracks: PackedMasks, part: int, n_parts: int) -> torch.Tensor:
+    """This part's share of the N x N intersection matrix (pair tiles part, part + n_parts, ...; zeros elsewhere)."""
+    w = tracks.words.contiguous()
+    N = int(w.shape[0])
+    words = int(w[0].numel()) if N else 1
+    inter = torch.empty((N, N), dtype=torch.int64, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.call("sola_pair_iou_st_part", w.data_ptr(), N, words, int(part), int(n_parts), inter.data_ptr(), _stream(w))
+    return inter
+
+
 def iou_matrix_from_inter(inter) -> np.ndarray:
     """float64 IoU matrix from the integer intersection matrix: union = a_i + a_j - inter; empty union -> 1.0."""
     m = inter.cpu().numpy().astype(np.int64) if isinstance(inter, torch.Tensor) else np.asarray(inter, dtype=np.int64)

@@ -67,3 +67,33 @@ def allreduce_jf(sum_J: float, sum_F: float, sum_JF: float, n_units: int, int_to
     means = (f / max(n, 1)).tolist()
     return {"mean_J": means[0], "mean_F": means[1], "mean_JF": means[2], "n_units": n,
             "int_totals": i[1:].numpy().copy()}
+
+
+def pairwise_inter_matrix_sharded(local_tracks, group=None) -> torch.Tensor:
+    """BASELINE config 5 (one video with more candidate tracks than one GPU should binarise): every rank holds the packed
+    planes of ITS tracks (n_local, T, H, Wp) — equal n_local on every rank.  The path has a real exchange step here:
+      1. NCCL all-gather of the packed tracks (1/32 of the mask bytes; 13.3 GB in total for 256 x 200 x 1080p),
+      2. each rank computes its share of the 64 x 64 pair tiles of the upper triangle (sola_pair_iou_st_part),
+      3. one all-reduce(SUM) of the int64 N x N matrix (512 KB at N = 256).
+    Returns the full symmetric matrix on every rank; integer sums, so the result is identical for any world size."""
+    from . import packed as P
+    w = local_tracks.words.contiguous()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return P.pairwise_inter_matrix(local_tracks)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    full = torch.empty((world * w.shape[0], *w.shape[1:]), dtype=w.dtype, device=w.device)
+    dist.all_gather_into_tensor(full, w, group=group)
+    inter = P.pairwise_inter_matrix_part(P.PackedMasks(full, local_tracks.H, local_tracks.W), rank, world)
+    dist.all_reduce(inter, op=dist.ReduceOp.SUM, group=group)
+    return inter
+
+
+def pair_tile_owner(n_tracks: int, world: int, tile: int = 64):
+    """Host mirror of the kernel's tile assignment: list of (ti, tj, owner rank) over the upper triangle."""
+    nt = (n_tracks + tile - 1) // tile
+    out, idx = [], 0
+    for ti in range(nt):
+        for tj in range(ti, nt):
+            out.append((ti, tj, idx % world))
+            idx += 1
+    return out

@@ -151,3 +151,18 @@ def test_video_dedup_job_matches_session_and_oracle():
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         np.testing.assert_array_equal(r0["stability"], O.get_stability_score(logits.numpy()))
+
+
+@pytest.mark.parametrize("N,parts", [(200, 3), (64, 2), (130, 8), (300, 5)])
+def test_pairwise_matrix_parts_sum_to_full(N, parts):
+    """Config-5 style tile partition: the shares of all parts sum to the full matrix and never overlap."""
+    import sola_b200 as S
+    rng = np.random.default_rng(N)
+    m = rng.random((N, 2, 16, 64)) > 0.5
+    packed = S.pack_masks(m)
+    full = S.pairwise_inter_matrix(packed).cpu().numpy()
+    shares = [S.packed.pairwise_inter_matrix_part(packed, p, parts).cpu().numpy() for p in range(parts)]
+    np.testing.assert_array_equal(sum(shares), full)
+    nz = sum((s != 0).astype(int) for s in shares)
+    assert nz.max() <= 1                                           # every entry is produced by exactly one part
+    np.testing.assert_array_equal(full, _np_inter(m))

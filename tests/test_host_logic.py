@@ -117,3 +117,13 @@ def test_shard_partitions():
     assert sorted(sum(parts, [])) == list(range(len(costs)))
     loads = [sum(costs[i] for i in p) for p in parts]
     assert max(loads) - min(loads) <= max(costs)
+
+
+def test_pair_tile_partition_covers_upper_triangle_once():
+    for n, world in ((256, 8), (64, 2), (130, 3), (1, 4)):
+        tiles = sharding.pair_tile_owner(n, world)
+        nt = (n + 63) // 64
+        assert len(tiles) == nt * (nt + 1) // 2 and len({(a, b) for a, b, _ in tiles}) == len(tiles)
+        assert all(a <= b for a, b, _ in tiles) and all(0 <= r < world for _, _, r in tiles)
+        counts = np.bincount([r for _, _, r in tiles], minlength=world)
+        assert counts.max() - counts.min() <= 1                                   # round-robin: balanced to within one tile

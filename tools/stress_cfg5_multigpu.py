@@ -1,0 +1,87 @@
+"""BASELINE config 5 shape ("256 candidate tracks x 200 frames at 1080x1920 pairwise IoU matrix, sharded across 8 x B200"):
+tracks are sharded over the ranks for K1 (each rank binarises / packs its own tracks' logits), the packed planes are all-gathered
+over NCCL, the N x N pair tiles are split over the ranks, one all-reduce sums the int64 matrix, rank 0 runs the greedy pass.
+
+    torchrun --nproc-per-node N tools/stress_cfg5_multigpu.py [--tracks 256 --frames 200]      (defaults are the full config at N = 8)
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import sola_b200 as S  # noqa: E402
+from sola_b200 import dedup, sharding, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tracks", type=int, default=256)
+    ap.add_argument("--frames", type=int, default=200)
+    ap.add_argument("--H", type=int, default=1080)
+    ap.add_argument("--W", type=int, default=1920)
+    ap.add_argument("--verify", action="store_true", help="rank 0 recomputes the matrix alone from the gathered planes")
+    args = ap.parse_args()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    rank, world = sharding.init_process_group_from_env(device)
+    assert args.tracks % world == 0
+    n_local = args.tracks // world
+    # every rank generates ITS tracks: clusters are shared across ranks (same seed for the base fields) so duplicates exist
+    logits = torch.empty((n_local, args.frames, args.H, args.W), dtype=torch.float32, device=device)
+    for i in range(n_local):
+        g = rank * n_local + i
+        logits[i] = synth.smooth_logits(args.frames, args.H, args.W, seed=100 + g % max(1, args.tracks // 3), device=device, cell=160,
+                                        bias=0.9, gain=30.0, noise=0.5 + 0.1 * (g % 5))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    packed, counts = S.binarize_pack_stability(logits)                       # K1 on the local tracks
+    e1.record()
+    inter = sharding.pairwise_inter_matrix_sharded(packed)                   # all-gather + tile share + all-reduce
+    e2.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        m = inter.cpu().numpy()
+        iou = S.packed.iou_matrix_from_inter(m)
+        alive = np.ones(len(m), bool)
+        for i in range(len(m)):
+            if alive[i]:
+                alive[i + 1:] &= ~(iou[i, i + 1:] > 0.7)
+        ok = None
+        if args.verify and world > 1:
+            full = torch.empty((args.tracks, *packed.words.shape[1:]), dtype=torch.int32, device=device)
+        words = packed.words[0].numel()
+        out = {"workload": f"config5-shaped: {args.tracks} tracks x {args.frames} frames x {args.H}x{args.W}", "n_gpus": world,
+               "k1_ms_max_over_ranks": float(t[0]), "pairwise_ms_max_over_ranks (all-gather + K2 share + all-reduce)": float(t[1]),
+               "masklet_frames_per_s": args.tracks * args.frames / ((float(t[0]) + float(t[1])) * 1e-3),
+               "pair_words_per_s": args.tracks * (args.tracks - 1) / 2 * words / (float(t[1]) * 1e-3),
+               "symmetric": bool(np.array_equal(m, m.T)), "kept": int(alive.sum()),
+               "diag_equals_k1_area": None}
+        print(json.dumps(out))
+    # checksum of checksums across ranks: diag(inter) of my tracks == my K1 areas
+    mine = inter.diagonal()[rank * n_local:(rank + 1) * n_local]
+    assert torch.equal(mine, counts[1].sum(dim=1, dtype=torch.int64)), "diag(inter) != K1 areas"
+    if args.verify and world > 1:
+        gathered = torch.empty((args.tracks, *packed.words.shape[1:]), dtype=torch.int32, device=device)
+        dist.all_gather_into_tensor(gathered, packed.words.contiguous())
+        if rank == 0:
+            alone = S.pairwise_inter_matrix(S.PackedMasks(gathered, args.H, args.W))
+            assert torch.equal(alone, inter), "sharded matrix differs from the single-rank matrix"
+            print(json.dumps({"sharded_matrix_identical_to_single_rank": True}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
