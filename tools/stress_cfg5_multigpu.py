@@ -58,16 +58,12 @@ def main():
         for i in range(len(m)):
             if alive[i]:
                 alive[i + 1:] &= ~(iou[i, i + 1:] > 0.7)
-        ok = None
-        if args.verify and world > 1:
-            full = torch.empty((args.tracks, *packed.words.shape[1:]), dtype=torch.int32, device=device)
         words = packed.words[0].numel()
         out = {"workload": f"config5-shaped: {args.tracks} tracks x {args.frames} frames x {args.H}x{args.W}", "n_gpus": world,
                "k1_ms_max_over_ranks": float(t[0]), "pairwise_ms_max_over_ranks (all-gather + K2 share + all-reduce)": float(t[1]),
                "masklet_frames_per_s": args.tracks * args.frames / ((float(t[0]) + float(t[1])) * 1e-3),
                "pair_words_per_s": args.tracks * (args.tracks - 1) / 2 * words / (float(t[1]) * 1e-3),
-               "symmetric": bool(np.array_equal(m, m.T)), "kept": int(alive.sum()),
-               "diag_equals_k1_area": None}
+               "symmetric": bool(np.array_equal(m, m.T)), "kept": int(alive.sum())}
         print(json.dumps(out))
     # checksum of checksums across ranks: diag(inter) of my tracks == my K1 areas
     mine = inter.diagonal()[rank * n_local:(rank + 1) * n_local]
