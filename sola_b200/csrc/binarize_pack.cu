@@ -158,6 +158,13 @@ pack_rows_kernel(const T* __restrict__ in, int H, int W, int row_blocks, Thresho
   }
 }
 
+// only float / bf16 logits have the any-width band kernel
+template <typename T>
+static int band_pack_dispatch(const T* in, long long n, int H, int W, Thresholds th, uint32_t* p, int* a, int* b, int* c, cudaStream_t s) {
+  return launch_band_pack<T>(in, n, H, W, th, p, a, b, c, s);
+}
+static int band_pack_dispatch(const uint8_t*, long long, int, int, Thresholds, uint32_t*, int*, int*, int*, cudaStream_t) { return SOLA_ERR_UNSUPPORTED; }
+
 template <typename T, int MODE>
 static int launch_pack(const T* in, long long n_frames, int H, int W, Thresholds th, uint32_t* packed,
                        int* cnt_hi, int* cnt_mid, int* cnt_lo, cudaStream_t stream) {
@@ -172,6 +179,11 @@ static int launch_pack(const T* in, long long n_frames, int H, int W, Thresholds
   }
   const int frame_px = H * W;
   const bool flat = (W % 32 == 0) && aligned16(in);
+  if (!flat && MODE == MODE_THRESH3 && sizeof(T) > 1 && aligned16(in) && (n_frames * frame_px) % ElemTraits<T>::E == 0 && n_frames < (1ll << 31)) {
+    // W % 32 != 0 (e.g. 480 x 854): flat 16-byte-aligned run per band + re-cut into row-padded words (fused_pack_resize.cu)
+    const int rc = band_pack_dispatch(in, n_frames, H, W, th, packed, cnt_hi, cnt_mid, cnt_lo, stream);
+    if (rc != SOLA_ERR_UNSUPPORTED) return rc;
+  }
   if (flat) {
     const int n_chunks = (frame_px + K1_CHUNK_PX - 1) / K1_CHUNK_PX;
     const int ctas_per_frame = (n_chunks + K1_CHUNKS_PER_CTA - 1) / K1_CHUNKS_PER_CTA;
@@ -230,15 +242,6 @@ static int launch_unpack(const uint32_t* packed, long long n_frames, int H, int 
 }  // namespace sola
 
 using namespace sola;
-
-static Thresholds make_thresholds(double thr, double off) {
-  // numpy compares float32 arrays against the Python scalar cast to float32 (prompt_generator.py:177,182)
-  Thresholds t;
-  t.mid = (float)thr;
-  t.hi = (float)(thr + off);
-  t.lo = (float)(thr - off);
-  return t;
-}
 
 extern "C" {
 

@@ -122,18 +122,151 @@ fused_pack_resize_kernel(const T* __restrict__ logits, int n_frames, int frames_
   }
 }
 
+// ---- any-width variant ---------------------------------------------------------------------------------------------
+// When W % 32 != 0 (480x854 DAVIS / MeViS frames) a row of the packed plane is not a whole number of 1024-pixel chunks and
+// rows do not start on 16-byte boundaries, so the loads cannot be row-aligned.  Instead the band's pixels are streamed as ONE
+// flat, 16-byte-aligned run (starting up to E-1 elements before the band, ending up to E-1 after it) into flat 32-pixel words
+// in shared memory, and a second, cheap pass re-cuts the flat bit string into row-padded words with one funnel shift each.
+// Counts are taken on the flat words with range masks on the first / last / ownership-boundary chunks.
+// RESIZE = false gives the stand-alone K1 for these shapes (bands of 32 input rows, everything owned).
+constexpr int BAND_ROWS = 32;
+
+template <typename T, bool RESIZE>
+__global__ void __launch_bounds__(FU_THREADS)
+band_pack_generic_kernel(const T* __restrict__ logits, int n_frames, int frames_per_slice, int H, int W, int oh, int ow,
+                         float sy, float sx, int max_tile_rows, int max_flat_words, Thresholds th,
+                         uint32_t* __restrict__ packed, uint32_t* __restrict__ resized,
+                         int* __restrict__ cnt_hi, int* __restrict__ cnt_mid, int* __restrict__ cnt_lo, int* __restrict__ area_resized) {
+  constexpr int E = ElemTraits<T>::E;
+  constexpr int L = 32 / E;
+  extern __shared__ __align__(16) unsigned char gb_smem[];
+  const int Wp = (W + 31) >> 5, owp = RESIZE ? (ow + 31) >> 5 : 0;
+  R1Tables tb;
+  unsigned char* cursor = gb_smem;
+  if (RESIZE) {
+    tb.carve(cursor, owp);
+    cursor += (size_t)owp * 32 * sizeof(XParam) + R1_TR * sizeof(YParam) + (size_t)owp * sizeof(int4);
+  }
+  uint32_t* flat = reinterpret_cast<uint32_t*>(cursor);                       // [max_flat_words]
+  uint32_t* tile = flat + max_flat_words;                                     // [max_tile_rows * Wp] (RESIZE only)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int band = blockIdx.x;
+  const int f_begin = blockIdx.y * frames_per_slice;
+  const int f_end = min(n_frames, f_begin + frames_per_slice);
+
+  int tlo, yend, own_end, oy0 = 0, nrows = 0;
+  if (RESIZE) {
+    const int n_bands = (oh + R1_TR - 1) / R1_TR;
+    oy0 = band * R1_TR;
+    nrows = min(R1_TR, oh - oy0);
+    const int ylo = bilinear_axis(oy0, sy, H).i0;
+    const int yhi = bilinear_axis(oy0 + nrows - 1, sy, H).i1;
+    tlo = band == 0 ? 0 : ylo;
+    own_end = band == n_bands - 1 ? H : bilinear_axis(oy0 + R1_TR, sy, H).i0;
+    yend = max(yhi, own_end - 1);
+    tb.build(oy0, tlo, H, W, oh, ow, sy, sx);
+  } else {
+    tlo = band * BAND_ROWS;
+    own_end = min(H, tlo + BAND_ROWS);
+    yend = own_end - 1;
+  }
+  const int n_tile_rows = yend - tlo + 1;
+  const int owned_rows = own_end - tlo;
+  const long long FW = (long long)H * Wp, oFW = RESIZE ? (long long)oh * owp : 0;
+  const int out_word_in_chunk = E * (lane % L) + lane / L;
+  __shared__ int red[4][FU_WARPS];
+
+  for (int f = f_begin; f < f_end; ++f) {
+    const long long g0 = ((long long)f * H + tlo) * W;                        // first pixel of the tile (global element index)
+    const long long g1 = g0 + (long long)n_tile_rows * W;
+    const long long s0 = g0 - (g0 % E);                                       // 16-byte aligned start of the flat run
+    const int off0 = (int)(g0 - s0);                                          // tile starts at this bit of the flat string
+    const int n_flat_px = (int)(((g1 + E - 1) / E) * E - s0);                 // multiple of E; in-bounds (total elements % E == 0)
+    const int n_flat_words = (n_flat_px + 31) >> 5;
+    const int n_chunks = (n_flat_px + FU_CHUNK_PX - 1) / FU_CHUNK_PX;
+    const int cnt_lo_px = off0, cnt_hi_px = off0 + owned_rows * W;             // pixels whose counts belong to this band
+    const T* src = logits + s0;
+    int n_mid = 0, n_hi = 0, n_lo = 0;
+    for (int c = warp; c < n_chunks; c += FU_WARPS) {
+      const int px0 = c * FU_CHUNK_PX;
+      uint4 raw[L];
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        const int px = px0 + E * (j * 32 + lane);
+        if (px < n_flat_px) {
+          raw[j] = ld_stream_u4(src + px);
+        } else {
+          const uint32_t ninf = sizeof(T) == 4 ? 0xff800000u : 0xff80ff80u;
+          raw[j] = make_uint4(ninf, ninf, ninf, ninf);
+        }
+      }
+      uint32_t xm = 0, xh = 0, xl = 0;
+#pragma unroll
+      for (int j = L - 1; j >= 0; --j) vec_push<MODE_THRESH3>(raw[j], th, T(), xm, xh, xl);
+      if (px0 >= cnt_lo_px && px0 + FU_CHUNK_PX <= cnt_hi_px) {
+        n_mid += __popc(xm); n_hi += __popc(xh); n_lo += __popc(xl);
+      } else if (px0 < cnt_hi_px && px0 + FU_CHUNK_PX > cnt_lo_px) {
+        uint32_t own = 0;
+#pragma unroll
+        for (int j = 0; j < L; ++j) {
+          const int p = px0 + E * (j * 32 + lane);                            // first pixel of this vector
+          const int a = min(max(cnt_lo_px - p, 0), E), b = min(max(cnt_hi_px - p, 0), E);
+          if (b > a) own |= ((b - a >= 32 ? 0xffffffffu : ((1u << (b - a)) - 1u)) << a) << (E * j);
+        }
+        n_mid += __popc(xm & own); n_hi += __popc(xh & own); n_lo += __popc(xl & own);
+      }
+      const uint32_t word = transpose_slots<E>(xm, lane);
+      const int k = (px0 >> 5) + out_word_in_chunk;
+      if (k < n_flat_words) flat[k] = word;
+    }
+    if (tid < 2) flat[n_flat_words + tid] = 0u;                               // the re-cut may read up to two words past the end (pad bits only)
+    __syncthreads();
+
+    // re-cut the flat bit string into row-padded words
+    uint32_t* dst = packed ? packed + f * FW + (long long)tlo * Wp : nullptr;
+    for (int i = tid; i < n_tile_rows * Wp; i += FU_THREADS) {
+      const int r = i / Wp, w = i - r * Wp;
+      const int o = off0 + r * W + 32 * w;
+      uint32_t v = __funnelshift_r(flat[o >> 5], flat[(o >> 5) + 1], o & 31);
+      const int nvalid = W - 32 * w;
+      if (nvalid < 32) v &= (1u << nvalid) - 1u;
+      if (RESIZE) tile[i] = v;
+      if (dst && r < owned_rows) dst[i] = v;
+    }
+    int n_area = 0;
+    if (RESIZE) {
+      __syncthreads();
+      n_area = resize_tile_from_smem(tile, Wp, tb, nrows, ow, resized + f * oFW + (long long)oy0 * owp);
+    }
+    n_mid = warp_sum(n_mid); n_hi = warp_sum(n_hi); n_lo = warp_sum(n_lo);
+    const int s_area = RESIZE ? warp_sum(n_area) : 0;
+    if (lane == 0) { red[0][warp] = n_mid; red[1][warp] = n_hi; red[2][warp] = n_lo; red[3][warp] = s_area; }
+    __syncthreads();                                                           // also: flat / tile free for the next frame
+    if (tid < 4) {
+      int s = 0;
+#pragma unroll
+      for (int w = 0; w < FU_WARPS; ++w) s += red[tid][w];
+      int* out = tid == 0 ? cnt_mid : (tid == 1 ? cnt_hi : (tid == 2 ? cnt_lo : area_resized));
+      if (out && s) atomicAdd(out + f, s);
+    }
+  }
+}
+
 struct FusedPlan {
-  bool ok;
-  int max_tile_rows, n_bands, slices, frames_per_slice;
+  bool ok, generic;
+  int max_tile_rows, max_flat_words, n_bands, slices, frames_per_slice;
   size_t smem;
 };
 
 static FusedPlan plan_fused(const void* base, long long n_frames, int H, int W, int oh, int ow, int elem_size) {
   FusedPlan p{};
   p.ok = false;
-  if (W % 32 != 0 || !aligned16(base) || n_frames <= 0 || n_frames >= (1ll << 31)) return p;
+  const int E = 16 / elem_size;
+  if (!aligned16(base) || n_frames <= 0 || n_frames >= (1ll << 31)) return p;
+  p.generic = (W % 32 != 0);
+  if (p.generic && (n_frames * H * W) % E != 0) return p;               // the flat run must end on a vector boundary inside the buffer
   const float sy = (float)H / (float)oh;
-  const int Wp = W >> 5, owp = (ow + 31) >> 5;
+  const int Wp = (W + 31) >> 5, owp = (ow + 31) >> 5;
   p.n_bands = (oh + R1_TR - 1) / R1_TR;
   // rows of the largest band tile, from the same fp32 index arithmetic the kernel uses (fmaf is the correctly rounded fma)
   auto i0 = [&](int dst) {
@@ -153,10 +286,15 @@ static FusedPlan plan_fused(const void* base, long long n_frames, int H, int W, 
     if (yend - tlo + 1 > rows) rows = yend - tlo + 1;
   }
   p.max_tile_rows = (int)rows;
+  p.max_flat_words = (int)((rows * W + 2 * E + 31) / 32) + 2;
   p.smem = (size_t)owp * 32 * sizeof(XParam) + R1_TR * sizeof(YParam) + (size_t)owp * sizeof(int4) + (size_t)rows * Wp * sizeof(uint32_t);
+  if (p.generic) p.smem += (size_t)p.max_flat_words * sizeof(uint32_t);
   if (p.smem > 160 * 1024) return p;
   int occ = 4;
-  if (elem_size == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_pack_resize_kernel<float>, FU_THREADS, p.smem);
+  if (p.generic) {
+    if (elem_size == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, band_pack_generic_kernel<float, true>, FU_THREADS, p.smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, band_pack_generic_kernel<__nv_bfloat16, true>, FU_THREADS, p.smem);
+  } else if (elem_size == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_pack_resize_kernel<float>, FU_THREADS, p.smem);
   else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_pack_resize_kernel<__nv_bfloat16>, FU_THREADS, p.smem);
   if (occ < 1) occ = 1;
   // several waves of resident CTAs: finer slices cost a table rebuild per CTA (~5 % of one frame's work) but shrink the
@@ -203,15 +341,51 @@ static int launch_fused(const T* logits, long long n_frames, int H, int W, int o
   }
   for (int* c : {cnt_hi, cnt_mid, cnt_lo, area_resized})
     if (c) SOLA_CUDA(cudaMemsetAsync(c, 0, sizeof(int) * n_frames, stream));
-  Thresholds th;
-  th.mid = (float)thr; th.hi = (float)(thr + off); th.lo = (float)(thr - off);
-  SOLA_CUDA(cudaFuncSetAttribute(fused_pack_resize_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  const Thresholds th = make_thresholds(thr, off);
   dim3 grid(p.n_bands, p.slices);
+  if (p.generic) {
+    SOLA_CUDA(cudaFuncSetAttribute(band_pack_generic_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    band_pack_generic_kernel<T, true><<<grid, FU_THREADS, p.smem, stream>>>(logits, (int)n_frames, p.frames_per_slice, H, W, oh, ow,
+                                                                            (float)H / (float)oh, (float)W / (float)ow, p.max_tile_rows,
+                                                                            p.max_flat_words, th, packed_out, resized_out, cnt_hi, cnt_mid,
+                                                                            cnt_lo, area_resized);
+    return check_launch("band_pack_generic<resize> kernel");
+  }
+  SOLA_CUDA(cudaFuncSetAttribute(fused_pack_resize_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   fused_pack_resize_kernel<T><<<grid, FU_THREADS, p.smem, stream>>>(logits, (int)n_frames, p.frames_per_slice, H, W, oh, ow,
                                                                     (float)H / (float)oh, (float)W / (float)ow, p.max_tile_rows, th,
                                                                     packed_out, resized_out, cnt_hi, cnt_mid, cnt_lo, area_resized);
   return check_launch("fused_pack_resize kernel");
 }
+
+namespace sola {
+// Stand-alone K1 for W % 32 != 0 (called from binarize_pack.cu): bands of 32 input rows, flat run + re-cut, no resize.
+template <typename T>
+int launch_band_pack(const T* in, long long n_frames, int H, int W, Thresholds th, uint32_t* packed, int* cnt_hi, int* cnt_mid, int* cnt_lo,
+                     cudaStream_t stream) {
+  constexpr int E = ElemTraits<T>::E;
+  const int n_bands = (H + BAND_ROWS - 1) / BAND_ROWS;
+  const int max_flat_words = (BAND_ROWS * W + 2 * E + 31) / 32 + 2;
+  const size_t smem = (size_t)max_flat_words * sizeof(uint32_t);
+  if (smem > 160 * 1024) return SOLA_ERR_UNSUPPORTED;
+  SOLA_CUDA(cudaFuncSetAttribute(band_pack_generic_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 4;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, band_pack_generic_kernel<T, false>, FU_THREADS, smem);
+  if (occ < 1) occ = 1;
+  int slices = num_sms() * occ * 16 / n_bands;
+  if (slices < 1) slices = 1;
+  if (slices > n_frames) slices = (int)n_frames;
+  if (slices > 65535) slices = 65535;
+  const int frames_per_slice = (int)((n_frames + slices - 1) / slices);
+  slices = (int)((n_frames + frames_per_slice - 1) / frames_per_slice);
+  dim3 grid(n_bands, slices);
+  band_pack_generic_kernel<T, false><<<grid, FU_THREADS, smem, stream>>>(in, (int)n_frames, frames_per_slice, H, W, 0, 0, 1.f, 1.f, BAND_ROWS,
+                                                                         max_flat_words, th, packed, nullptr, cnt_hi, cnt_mid, cnt_lo, nullptr);
+  return check_launch("band_pack_generic kernel");
+}
+template int launch_band_pack<float>(const float*, long long, int, int, Thresholds, uint32_t*, int*, int*, int*, cudaStream_t);
+template int launch_band_pack<__nv_bfloat16>(const __nv_bfloat16*, long long, int, int, Thresholds, uint32_t*, int*, int*, int*, cudaStream_t);
+}  // namespace sola
 
 extern "C" {
 

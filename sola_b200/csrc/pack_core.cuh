@@ -12,6 +12,17 @@ struct Thresholds {
   float mid, hi, lo;
 };
 
+// numpy / torch compare float32 data against the Python scalar cast to float32 (prompt_generator.py:177,182).  A threshold of
+// -0.0 is normalised to +0.0: `x > -0.0` and `x > +0.0` are the same predicate, but the sign-of-(t - x) extraction below would
+// see (-0.0) - (+0.0) = -0.0 as "greater".
+inline Thresholds make_thresholds(double thr, double off) {
+  Thresholds t;
+  t.mid = (float)thr + 0.0f;
+  t.hi = (float)(thr + off) + 0.0f;
+  t.lo = (float)(thr - off) + 0.0f;
+  return t;
+}
+
 template <typename T> struct ElemTraits;
 template <> struct ElemTraits<float> { static constexpr int E = 4; };
 template <> struct ElemTraits<__nv_bfloat16> { static constexpr int E = 8; };
@@ -139,5 +150,10 @@ __device__ __forceinline__ uint32_t transpose_slots(uint32_t x, int lane) {
   }
   return x;
 }
+
+// any-width stand-alone K1 (flat run + re-cut), defined in fused_pack_resize.cu
+template <typename T>
+int launch_band_pack(const T* in, long long n_frames, int H, int W, Thresholds th, uint32_t* packed, int* cnt_hi, int* cnt_mid, int* cnt_lo,
+                     cudaStream_t stream);
 
 }  // namespace sola

@@ -43,7 +43,7 @@ def test_golden_stability_and_planes(golden, tag):
 
 
 @pytest.mark.parametrize("shape", [(3, 64, 96), (2, 5, 720, 1280), (1, 540, 960), (4, 33, 32), (2, 480, 854),
-                                   (3, 37, 70), (1, 1, 1), (2, 7, 1000), (1, 1080, 1920), (5, 3, 17, 31)])
+                                   (3, 37, 70), (1, 1, 1), (2, 7, 1000), (1, 1080, 1920), (5, 3, 17, 31), (4, 37, 70), (8, 5, 33), (2, 481, 854), (4, 64, 2000)])
 def test_random_shapes_fp32(shape):
     g = torch.Generator().manual_seed(sum(shape))
     x = torch.randn(shape, generator=g) * 2.0
@@ -66,7 +66,7 @@ def test_unaligned_base_pointer_takes_row_path():
     np.testing.assert_array_equal(counts.cpu().numpy()[2], (ref > -1).sum((-2, -1)))
 
 
-@pytest.mark.parametrize("shape", [(3, 64, 96), (2, 720, 1280), (2, 37, 70)])
+@pytest.mark.parametrize("shape", [(3, 64, 96), (2, 720, 1280), (2, 37, 70), (8, 37, 70), (4, 480, 854)])
 def test_bf16_logits(shape):
     import sola_b200 as S
     g = torch.Generator().manual_seed(17)
@@ -116,3 +116,15 @@ def test_empty_batch_and_errors():
     assert p.words.shape == (0, 8, 1) and c.shape == (3, 0)
     with pytest.raises(_lib.SolaError):
         _lib.call("sola_binarize_pack_f32", None, 1, 8, 8, 0.0, 1.0, None, None, None, None, None)
+
+
+def test_negative_zero_threshold():
+    """thr - off can round to -0.0 (found by the hypothesis sweep): `x > -0.0` must behave like `x > 0.0`."""
+    import sola_b200 as S
+    x = torch.tensor([[0.0, -0.0, 1e-45, -1e-45, 1.0, -1.0, float("nan"), 0.0]]).repeat(4, 4)[None]
+    for thr, off in ((0.0, 1.2e-211), (-0.0, 0.0), (0.0, 0.0)):
+        packed, counts = S.binarize_pack_stability(x.cuda(), thr, off)
+        ref = x.numpy()
+        for k, t in enumerate((np.float32(thr + off), np.float32(thr), np.float32(thr - off))):
+            np.testing.assert_array_equal(counts.cpu().numpy()[k], (ref > t).sum((1, 2)))
+        np.testing.assert_array_equal(packed.numpy_u32(), O.pack_bits(ref > np.float32(thr)))

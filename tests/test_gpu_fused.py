@@ -10,7 +10,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("shape,target", [((3, 5, 720, 1280), None), ((2, 4, 1080, 1920), None), ((7, 480, 864), None), ((2, 3, 1280, 736), None),
                                           ((2, 3, 96, 160), (54, 96)), ((5, 64, 64), None), ((3, 200, 320), (37, 50)), ((2, 40, 64), (300, 500)),
-                                          ((1, 720, 1280), (100, 100)), ((2, 480, 854), None), ((70, 96, 160), (54, 96))])
+                                          ((1, 720, 1280), (100, 100)), ((2, 480, 854), None), ((70, 96, 160), (54, 96)),
+                                          ((4, 37, 70), None), ((2, 3, 481, 854), None), ((8, 50, 33), (40, 70)), ((3, 50, 33), None), ((16, 21, 1000), (33, 500))])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_fused_equals_two_kernels(shape, target, dtype):
     import sola_b200 as S
