@@ -4,9 +4,10 @@ Host side in Python (as the reference is Python): thin mirrors of the reference'
 C-ABI CUDA library (`include/sola_maskpath.h`, `sola_b200/csrc/`).  No CPU fallback: importing is cheap, but any
 computation without the built library / a CUDA device raises `SolaError`."""
 from ._lib import SolaError, load as load_library, launch_count  # noqa: F401
-from . import packed, seg_utils, utils, prompt_generator, evaluator, dedup, dataloader_ops, metric, sharding, rle  # noqa: F401
+from . import packed, seg_utils, utils, prompt_generator, evaluator, dedup, dataloader_ops, metric, sharding, rle, api  # noqa: F401
 from .packed import (PackedMasks, binarize_pack_stability, binarize_pack_resize, pack_masks, unpack_masks, frame_counts,  # noqa: F401
                      frame_counts_packed, pairwise_inter_matrix, gathered_inter, resize_bilinear_bin,
                      resize_nearest, or_merge, boundary_counts)
 
 __version__ = "0.1.0"
+from .api import pairwise_iou_matrix, gathered_iou, greedy_filter, jf_batch  # noqa: F401,E402

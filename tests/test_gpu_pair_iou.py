@@ -166,3 +166,30 @@ def test_pairwise_matrix_parts_sum_to_full(N, parts):
     nz = sum((s != 0).astype(int) for s in shares)
     assert nz.max() <= 1                                           # every entry is produced by exactly one part
     np.testing.assert_array_equal(full, _np_inter(m))
+
+
+def test_survey_named_entry_points(golden):
+    """pairwise_iou_matrix / gathered_iou / greedy_filter / jf_batch compose to the same results."""
+    import sola_b200 as S
+    masklets, frame_idx, _ = greedy_table(golden)
+    prompts = greedy_prompts(golden)
+    packed = S.pack_masks(masklets)
+    resized = S.resize_bilinear_bin(packed)
+    planes = S.resize_nearest(np.stack([p["segmentation"] for p in prompts]), resized.H, resized.W)
+    M = S.gathered_iou(resized, frame_idx, planes)
+    res = S.greedy_filter(M, prompts, 8, mode="grid", bin_size=4, n_max_tracks=64, batch_size=4)
+    exp = golden.greedy["grid_default"]
+    assert res["tracked"] == exp["tracked"] and res["filtered"] == exp["filtered"] and res["batches"] == exp["batches"]
+    iou, inter, area = S.pairwise_iou_matrix(packed)
+    np.testing.assert_array_equal(inter, _np_inter(masklets.astype(bool)))
+    assert iou.shape == inter.shape and np.array_equal(area, np.diag(inter))
+    # ragged J&F over two units
+    a, b = masklets[0], masklets[1]
+    pa, pb = O.pack_bits(a), O.pack_bits(b)
+    fw = pa.shape[1] * pa.shape[2]
+    offs = torch.arange(0, (2 * a.shape[0] + 1) * fw, fw, dtype=torch.int64).cuda()
+    wa = torch.from_numpy(np.concatenate([pa.reshape(-1), pb.reshape(-1)]).view(np.int32)).cuda()
+    wb = torch.from_numpy(np.concatenate([pb.reshape(-1), pb.reshape(-1)]).view(np.int32)).cuda()
+    counts, jf = S.jf_batch(wa, wb, offs, [(0, a.shape[0]), (a.shape[0], 2 * a.shape[0])])
+    at, bt = torch.from_numpy(a).float(), torch.from_numpy(b).float()
+    assert jf[0][0] == O.compute_J(at, bt) and abs(jf[0][1] - O.compute_F(at, bt)) < 1e-6 and jf[1] == (1.0, 1.0)
