@@ -16,6 +16,8 @@
 //     registers; diagonal tiles stage their 64 rows once and skip the strictly-lower micro-tile entries;
 //   * partial sums leave the CTA as 64-bit atomics on the N x N output (a few hundred adds per address).
 #include "common.cuh"
+#include <cuda.h>
+#include <stdlib.h>          // CUtensorMap + enums only; the encoder is fetched at run time through cudaGetDriverEntryPoint
 
 namespace sola {
 
@@ -154,6 +156,144 @@ pair_iou_st_kernel(const uint32_t* __restrict__ packed, int N, long long words, 
   else st_tile_body<false>(packed, N, words, ti, tj, s_begin, s_end, smem_st, inter);
 }
 
+// ---- TMA-staged variant (default) --------------------------------------------------------------------------------------
+// The (rows x 32 words) stage tiles are regular, so they are fetched by the TMA unit instead of 4 cp.async per thread:
+// a rank-2 tensor map over packed[N][words] (uint32), box = 32 words x 64 rows = 8 KB, SWIZZLE_128B.  One elected thread
+// arms the stage's mbarrier with the byte count and issues one (diagonal tile) or two `cp.async.bulk.tensor.2d` per stage;
+// out-of-range rows (>= N) and the K tail are zero-filled by the hardware.  With the 128-byte swizzle the 16-byte chunk q of
+// row r lives at chunk q ^ (r & 7), so 8 lanes reading 8 consecutive rows at the same q touch 8 different bank groups.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  for (long long spin = 0; !done; ++spin) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (spin > (1ll << 26)) __trap();                    // never hang the GPU on a lost transaction
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+                   "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"(c0), "r"(c1),
+               "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+constexpr int TMA_BOX_BYTES = PT * STAGE_WORDS * 4;      // 64 rows x 128 B
+
+template <bool DIAG>
+__device__ __forceinline__ void st_tile_body_tma(const CUtensorMap* __restrict__ map, int N, int ti, int tj, long long s_begin,
+                                                 long long s_end, unsigned char* smem, uint64_t* full,
+                                                 unsigned long long* __restrict__ inter) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  Csa acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = Csa{0u, 0u, 0};
+  auto issue = [&](long long stage, int buf) {         // one thread
+    unsigned char* dst = smem + (size_t)buf * 2 * TMA_BOX_BYTES;
+    mbar_expect_tx(full + buf, DIAG ? TMA_BOX_BYTES : 2 * TMA_BOX_BYTES);
+    tma_load_2d(dst, map, (int)(stage * STAGE_WORDS), ti * PT, full + buf);
+    if (!DIAG) tma_load_2d(dst + TMA_BOX_BYTES, map, (int)(stage * STAGE_WORDS), tj * PT, full + buf);
+  };
+  const long long n_st = s_end - s_begin;
+  if (tid == 0)
+    for (int p = 0; p < NSTAGE - 1; ++p)
+      if (p < n_st) issue(s_begin + p, p);
+  for (long long s = 0; s < n_st; ++s) {
+    const int bufi = (int)(s % NSTAGE);
+    __syncthreads();                                    // everyone has finished reading the buffer that is refilled next
+    if (tid == 0 && s + NSTAGE - 1 < n_st) issue(s_begin + s + NSTAGE - 1, (int)((s + NSTAGE - 1) % NSTAGE));
+    mbar_wait(full + bufi, (unsigned)((s / NSTAGE) & 1));
+    const uint4* A = reinterpret_cast<const uint4*>(smem + (size_t)bufi * 2 * TMA_BOX_BYTES);
+    const uint4* B = DIAG ? A : A + TMA_BOX_BYTES / 16;
+#pragma unroll
+    for (int q = 0; q < KQ; ++q) {
+      uint4 a[4], b[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int ra = ty + 16 * r, rb = tx + 16 * r;
+        a[r] = A[ra * KQ + (q ^ (ra & 7))];
+        b[r] = B[rb * KQ + (q ^ (rb & 7))];
+      }
+#pragma unroll
+      for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+        for (int rj = 0; rj < 4; ++rj) {
+          if (DIAG && rj < ri) continue;
+          csa_quad(acc[ri][rj], a[ri], b[rj]);
+        }
+    }
+  }
+#pragma unroll
+  for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+    for (int rj = 0; rj < 4; ++rj) {
+      if (DIAG && rj < ri) continue;
+      const int i = ti * PT + ty + 16 * ri, j = tj * PT + tx + 16 * rj;
+      if (i >= N || j >= N) continue;
+      if (DIAG && ri == rj && tx < ty) continue;
+      const unsigned long long v = (unsigned long long)csa_total(acc[ri][rj]);
+      if (v == 0) continue;
+      atomicAdd(inter + (long long)i * N + j, v);
+      if (i != j) atomicAdd(inter + (long long)j * N + i, v);
+    }
+}
+
+__global__ void __launch_bounds__(ST_THREADS)
+pair_iou_st_tma_kernel(const __grid_constant__ CUtensorMap map, int N, long long words, int nt, int n_tiles, int splits,
+                       int tile_first, int tile_step, unsigned long long* __restrict__ inter) {
+  extern __shared__ __align__(1024) unsigned char smem_tma[];          // SWIZZLE_128B needs 1024-byte aligned boxes
+  __shared__ uint64_t full[NSTAGE];
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < NSTAGE; ++b) mbar_init(full + b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int tile = tile_first + (blockIdx.x % n_tiles) * tile_step, split = blockIdx.x / n_tiles;
+  int ti, tj;
+  tile_from_index(tile, nt, ti, tj);
+  const long long stages = (words + STAGE_WORDS - 1) / STAGE_WORDS;
+  const long long s_begin = stages * split / splits, s_end = stages * (split + 1) / splits;
+  unsigned char* boxes = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_tma) + 1023) & ~(uintptr_t)1023);
+  if (ti == tj) st_tile_body_tma<true>(&map, N, ti, tj, s_begin, s_end, boxes, full, inter);
+  else st_tile_body_tma<false>(&map, N, ti, tj, s_begin, s_end, boxes, full, inter);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    if (getenv("SOLA_NO_TMA")) fn = nullptr;
+  }
+  return fn;
+}
+
+// rank-2 map over packed[N][words] (uint32): box = STAGE_WORDS x PT, 128-byte swizzle, zero fill out of range
+static bool make_track_map(const uint32_t* packed, int N, long long words, CUtensorMap* map) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc || words >= (1ll << 31)) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)words, (cuuint64_t)N};
+  const cuuint64_t strides[1] = {(cuuint64_t)words * 4};
+  const cuuint32_t box[2] = {STAGE_WORDS, PT};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t*>(packed), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Fallback for track rows that are not 16-byte aligned (words % 4 != 0 or odd base): one CTA per pair.
 __global__ void __launch_bounds__(256)
 pair_iou_st_simple_kernel(const uint32_t* __restrict__ packed, int N, long long words, unsigned long long* __restrict__ inter) {
@@ -271,10 +411,18 @@ static int launch_pair_iou_st(const uint32_t* packed, int N, long long words_per
       if (splits < min_splits) splits = min_splits;
       if (splits < 1) splits = 1;
       const size_t smem = (size_t)NSTAGE * (2 * PT) * KQ * sizeof(uint4);
-      SOLA_CUDA(cudaFuncSetAttribute(pair_iou_st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       SOLA_REQUIRE(splits * n_tiles < (1ll << 31), "pair_iou_st: grid too large");
-      pair_iou_st_kernel<<<(unsigned)(splits * n_tiles), ST_THREADS, smem, stream>>>(
-          packed, N, words_per_track, nt, n_tiles, (int)splits, part, n_parts, reinterpret_cast<unsigned long long*>(inter_out));
+      CUtensorMap map;
+      if (make_track_map(packed, N, words_per_track, &map)) {
+        // TMA-staged tiles (UTMALDG): one elected thread per stage instead of 4 cp.async per thread
+        SOLA_CUDA(cudaFuncSetAttribute(pair_iou_st_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
+        pair_iou_st_tma_kernel<<<(unsigned)(splits * n_tiles), ST_THREADS, smem + 1024, stream>>>(
+            map, N, words_per_track, nt, n_tiles, (int)splits, part, n_parts, reinterpret_cast<unsigned long long*>(inter_out));
+      } else {
+        SOLA_CUDA(cudaFuncSetAttribute(pair_iou_st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pair_iou_st_kernel<<<(unsigned)(splits * n_tiles), ST_THREADS, smem, stream>>>(
+            packed, N, words_per_track, nt, n_tiles, (int)splits, part, n_parts, reinterpret_cast<unsigned long long*>(inter_out));
+      }
     }
   } else {
     SOLA_REQUIRE(n_parts == 1, "pair_iou_st: the unaligned fallback does not support partitioning");

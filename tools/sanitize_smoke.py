@@ -1,0 +1,43 @@
+"""Every kernel of libsola_maskpath.so once, on small awkward shapes — run under compute-sanitizer (memcheck / racecheck)."""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import sola_b200 as S
+from sola_b200 import dedup, evaluator, rle, synth, utils
+
+g = torch.Generator().manual_seed(0)
+for shape in [(3, 40, 64), (2, 37, 70), (4, 21, 100), (2, 5, 33), (2, 96, 160)]:
+    x = (torch.randn(shape, generator=g) * 2).cuda()
+    for dt in (torch.float32, torch.bfloat16):
+        xx = x.to(dt)
+        p, c = S.binarize_pack_stability(xx)
+        S.binarize_pack_resize(xx, target_shape=(27, 48), want_area=True)
+        S.binarize_pack_resize(xx, target_shape=(60, 50))
+    m = (x > 0)
+    pk, area = S.pack_masks(m.float(), want_area=True)
+    S.pack_masks(m.to(torch.uint8))
+    S.unpack_masks(pk, torch.float32); S.unpack_masks(pk, torch.uint8)
+    S.frame_counts(m.float(), (x > 0.5).float()); S.frame_counts(m.to(torch.uint8), (x > 0.5).to(torch.uint8))
+    r = S.resize_bilinear_bin(pk, (30, 45), want_area=True)
+    S.packed.resize_bilinear_bin_f32(x, (30, 45), want_f32=True)
+    S.resize_nearest(m.to(torch.uint8), 30, 45); S.resize_nearest(pk, 30, 45)
+    S.boundary_counts(pk, S.pack_masks((x > 0.3).float()))
+    S.or_merge(pk, select=[1] + [0] * (shape[0] - 1))
+    enc = rle.encode_rle_masklet_torch(pk)
+    assert np.array_equal(rle.decode_rle_masklet(enc), m.cpu().numpy().astype(np.uint8))
+tracks = S.pack_masks((torch.randn((70, 3, 16, 64), generator=g) > 0).cuda().float())
+S.pairwise_inter_matrix(tracks)
+S.packed.pairwise_inter_matrix_part(tracks, 1, 3)
+odd = S.pack_masks((torch.randn((5, 1, 5, 70), generator=g) > 0).cuda().float())
+S.pairwise_inter_matrix(odd)
+prompts = S.pack_masks((torch.randn((9, 16, 64), generator=g) > 0).cuda().float())
+S.gathered_inter(tracks[:6], prompts, np.arange(9) % 3)
+S.frame_counts_packed(tracks[:5], tracks[5:11])
+utils.suppress_part_masks((torch.randn((6, 20, 30), generator=g) > 0).float().cuda())
+logits, pr = synth.dedup_candidates(8, 8, 72, 128, seed=5, device="cpu", n_clusters=2, jitter=1)
+job = dedup.VideoDedupJob([{"prompt_id": p["prompt_id"], "frame_idx": p["frame_idx"]} for p in pr], 8, mode="grid")
+job.enqueue(logits.cuda(), torch.from_numpy(np.stack([p["segmentation"] for p in pr])).cuda())
+job.finish()
+evaluator.compute_JF(*synth.jf_pair(4, 50, 77, 1, device="cuda"))
+torch.cuda.synchronize()
+print("sanitize smoke ok")
