@@ -191,8 +191,8 @@ class TrackDedup:
     def submit_logits(self, batch, logits, mask_threshold: float = 0.0, threshold_offset: float = 1.0):
         """logits (B, T, H, W) fp32/bf16 of the batch members, in batch order.  Returns (native-resolution packed
         masklets, stability counts) so the caller can RLE-encode / store them."""
-        packed, counts = P.binarize_pack_stability(logits, mask_threshold, threshold_offset)
-        self.submit_packed(batch, packed)
+        packed, counts, resized = P.binarize_pack_resize(logits, mask_threshold, threshold_offset, self.target_shape)   # K1 + R1, one pass
+        self.submit_resized(batch, resized)
         return packed, counts
 
     def submit_masks(self, batch, masklets):
@@ -269,7 +269,8 @@ class VideoDedupJob:
         self.packed = self.counts = self.resized = None
 
     def _pinned(self, n_tracks: int, n_prompts: int, T: int):
-        if self._host is None:
+        shapes = ((3, n_tracks, n_prompts), (n_tracks, n_tracks), (3, n_tracks, T))
+        if self._host is None or tuple(tuple(t.shape) for t in self._host) != shapes:
             self._host = (torch.empty((3, n_tracks, n_prompts), dtype=torch.int32).pin_memory(),
                           torch.empty((n_tracks, n_tracks), dtype=torch.int64).pin_memory(),
                           torch.empty((3, n_tracks, T), dtype=torch.int32).pin_memory())

@@ -34,9 +34,10 @@ def _dev(device=None) -> torch.device:
 def to_device(x, device=None, dtype=None) -> torch.Tensor:
     """numpy / CPU tensor / CUDA tensor -> contiguous CUDA tensor (H2D copy when needed)."""
     if isinstance(x, np.ndarray):
+        x = np.ascontiguousarray(x)
         if x.dtype == np.bool_:
             x = x.view(np.uint8)
-        x = torch.from_numpy(np.ascontiguousarray(x))
+        x = torch.from_numpy(x)
     if x.dtype == torch.bool:
         x = x.view(torch.uint8) if x.is_contiguous() else x.contiguous().view(torch.uint8)
     if not x.is_cuda:
