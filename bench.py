@@ -354,6 +354,14 @@ def main():
     e2e = None
     if not args.no_e2e:
         try:
+            need = w.logits.numel() * 4 * world
+            try:
+                import psutil
+                avail = psutil.virtual_memory().available
+            except Exception:
+                avail = None
+            if avail is not None and need > 0.7 * avail:
+                raise MemoryError(f"pinned staging for {world} ranks needs {need / 1e9:.0f} GB, host has {avail / 1e9:.0f} GB available")
             chunk = 4
             host_chunks = []
             for s in range(0, n_tracks, chunk):
