@@ -166,37 +166,52 @@ __device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
   return min((int)floorf(__fmul_rn((float)dst, scale)), in_size - 1);
 }
 
+constexpr int NN_ROWS = 4;   // output rows per warp: 4 independent loads in flight per lane
+
 template <bool PACKED_IN>
 __global__ void __launch_bounds__(256)
 resize_nearest_kernel(const void* __restrict__ in_, int H, int W, int oh, int ow, float sy, float sx,
                       uint32_t* __restrict__ out_packed, int* __restrict__ area) {
-  // grid: x = 8-word groups of one output plane, y = plane; one warp per output word, 32-bit index math only
+  // grid: x = groups of 8 warps over (row groups x word columns) of one output plane, y = plane; 32-bit index math only
   const int lane = threadIdx.x & 31;
   const int owp = (ow + 31) >> 5, Wp = (W + 31) >> 5;
-  const int words_per_frame = oh * owp;
-  const int wi = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (wi >= words_per_frame) return;
+  const int row_groups = (oh + NN_ROWS - 1) / NN_ROWS;
+  const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (item >= row_groups * owp) return;
   const long long f = blockIdx.y;
-  const int oy = wi / owp, owx = wi - oy * owp;
+  const int rg = item / owp, owx = item - rg * owp;
   const int ox = owx * 32 + lane;
-  bool bit = false;
-  if (ox < ow) {
-    const int y = nearest_src(oy, sy, H), x = nearest_src(ox, sx, W);
-    if (PACKED_IN) bit = get_bit(reinterpret_cast<const uint32_t*>(in_) + (f * H + y) * Wp, x) != 0u;
-    else bit = __ldg(reinterpret_cast<const uint8_t*>(in_) + (f * H + y) * W + x) != 0;
+  const bool live = ox < ow;
+  const int x = nearest_src(live ? ox : 0, sx, W);
+  bool bit[NN_ROWS];
+#pragma unroll
+  for (int k = 0; k < NN_ROWS; ++k) {
+    const int oy = rg * NN_ROWS + k;
+    bit[k] = false;
+    if (live && oy < oh) {
+      const int y = nearest_src(oy, sy, H);
+      if (PACKED_IN) bit[k] = get_bit(reinterpret_cast<const uint32_t*>(in_) + (f * H + y) * Wp, x) != 0u;
+      else bit[k] = __ldg(reinterpret_cast<const uint8_t*>(in_) + (f * H + y) * W + x) != 0;
+    }
   }
-  const uint32_t word = __ballot_sync(FULL, bit);
-  if (lane == 0) {
-    out_packed[f * words_per_frame + wi] = word;
-    if (area && word) atomicAdd(area + f, __popc(word));
+  int pop = 0;
+#pragma unroll
+  for (int k = 0; k < NN_ROWS; ++k) {
+    const int oy = rg * NN_ROWS + k;
+    const uint32_t word = __ballot_sync(FULL, bit[k]);
+    if (lane == 0 && oy < oh) {
+      out_packed[f * (long long)(oh * owp) + oy * owp + owx] = word;
+      pop += __popc(word);
+    }
   }
+  if (lane == 0 && area && pop) atomicAdd(area + f, pop);
 }
 
 template <bool PACKED_IN>
 static int launch_nearest(const void* in, long long n_frames, int H, int W, int oh, int ow, uint32_t* out_packed, int* area, cudaStream_t stream) {
   const int owp = (ow + 31) >> 5;
   const float sy = (float)H / (float)oh, sx = (float)W / (float)ow;
-  const unsigned gx = (unsigned)((oh * owp + 7) / 8);
+  const unsigned gx = (unsigned)((((oh + NN_ROWS - 1) / NN_ROWS) * owp + 7) / 8);
   for (long long f0 = 0; f0 < n_frames; f0 += 65535) {
     const long long nf = n_frames - f0 < 65535 ? n_frames - f0 : 65535;
     const char* src = reinterpret_cast<const char*>(in) + (PACKED_IN ? f0 * H * ((W + 31) >> 5) * 4 : f0 * H * (long long)W);
