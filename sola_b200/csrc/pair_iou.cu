@@ -117,12 +117,16 @@ __device__ __forceinline__ void st_tile_body(const uint32_t* __restrict__ packed
         b[r] = buf[q * ROWS + (DIAG ? 0 : PT) + tx + 16 * r];
       }
 #pragma unroll
-      for (int ri = 0; ri < 4; ++ri)
+      for (int ri = 0; ri < 4; ++ri) {
+        // masklets are mostly background: an all-zero quad of row i contributes nothing to any of its pairs (the carry-save
+        // state is unchanged by zero inputs), so skip its 4 compressor chains.  The 16 lanes that share `ty` agree on this.
+        if ((a[ri].x | a[ri].y | a[ri].z | a[ri].w) == 0u) continue;
 #pragma unroll
         for (int rj = 0; rj < 4; ++rj) {
           if (DIAG && rj < ri) continue;               // mirror entry is produced by another (ri, rj)
           csa_quad(acc[ri][rj], a[ri], b[rj]);
         }
+      }
     }
   }
   cp_async_wait<0>();
@@ -221,12 +225,16 @@ __device__ __forceinline__ void st_tile_body_tma(const CUtensorMap* __restrict__
         b[r] = B[rb * KQ + (q ^ (rb & 7))];
       }
 #pragma unroll
-      for (int ri = 0; ri < 4; ++ri)
+      for (int ri = 0; ri < 4; ++ri) {
+        // masklets are mostly background: an all-zero quad of row i contributes nothing to any of its pairs (the carry-save
+        // state is unchanged by zero inputs), so skip its 4 compressor chains.  The 16 lanes that share `ty` agree on this.
+        if ((a[ri].x | a[ri].y | a[ri].z | a[ri].w) == 0u) continue;
 #pragma unroll
         for (int rj = 0; rj < 4; ++rj) {
           if (DIAG && rj < ri) continue;
           csa_quad(acc[ri][rj], a[ri], b[rj]);
         }
+      }
     }
   }
 #pragma unroll
@@ -259,7 +267,8 @@ pair_iou_st_tma_kernel(const __grid_constant__ CUtensorMap map, int N, long long
   tile_from_index(tile, nt, ti, tj);
   const long long stages = (words + STAGE_WORDS - 1) / STAGE_WORDS;
   const long long s_begin = stages * split / splits, s_end = stages * (split + 1) / splits;
-  unsigned char* boxes = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_tma) + 1023) & ~(uintptr_t)1023);
+  // round the dynamic-smem base up to 1024 B by OFFSET (a pointer cast would demote the tile reads to generic loads)
+  unsigned char* boxes = smem_tma + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_tma) & 1023u)) & 1023u);
   if (ti == tj) st_tile_body_tma<true>(&map, N, ti, tj, s_begin, s_end, boxes, full, inter);
   else st_tile_body_tma<false>(&map, N, ti, tj, s_begin, s_end, boxes, full, inter);
 }
