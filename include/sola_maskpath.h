@@ -57,6 +57,8 @@ int sola_pack_mask_u8(const uint8_t* mask, long long n_frames, int H, int W, uin
 /* packed -> {0,1} planes, for drop-in return types (reshape_masklet returns fp32; get_sam2_masklet returns uint8) */
 int sola_unpack_f32(const uint32_t* packed, long long n_frames, int H, int W, float* out, sola_stream_t stream);
 int sola_unpack_u8(const uint32_t* packed, long long n_frames, int H, int W, uint8_t* out, sola_stream_t stream);
+/* same with foreground = one_value (255 -> the PNG planes written by inference.py:89-91) */
+int sola_unpack_u8_value(const uint32_t* packed, long long n_frames, int H, int W, int one_value, uint8_t* out, sola_stream_t stream);
 
 /* ---- K3: per-frame |A∩B|, |A|, |B| ------------------------------------------------------------------------
  * replaces the mul/add/sum/.item() chains of

@@ -24,6 +24,7 @@ SIGNATURES = {
     "sola_pack_mask_u8": [_P, _LL, _I, _I, _P, _P, _P],
     "sola_unpack_f32": [_P, _LL, _I, _I, _P, _P],
     "sola_unpack_u8": [_P, _LL, _I, _I, _P, _P],
+    "sola_unpack_u8_value": [_P, _LL, _I, _I, _I, _P, _P],
     "sola_frame_counts_f32": [_P, _P, _LL, _LL, _P, _P, _P, _P],
     "sola_frame_counts_u8": [_P, _P, _LL, _LL, _P, _P, _P, _P],
     "sola_frame_counts_packed": [_P, _P, _I, _I, _I, _LL, _P, _P, _P, _P],

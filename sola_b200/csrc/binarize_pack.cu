@@ -203,7 +203,7 @@ static int launch_pack(const T* in, long long n_frames, int H, int W, Thresholds
 // warp-cooperative variant: each warp takes one word at a time, lane b writes pixel b (coalesced 128 B fp32 stores)
 template <typename T>
 __global__ void __launch_bounds__(256)
-unpack_warp_kernel(const uint32_t* __restrict__ packed, long long n_rows, int W, int Wp, T* __restrict__ out) {
+unpack_warp_kernel(const uint32_t* __restrict__ packed, long long n_rows, int W, int Wp, T one, T* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const long long total_words = n_rows * Wp;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -218,13 +218,13 @@ unpack_warp_kernel(const uint32_t* __restrict__ packed, long long n_rows, int W,
       const long long row = wi / Wp;
       const int w = (int)(wi - row * Wp);
       const int x = w * 32 + lane;
-      if (x < W) out[row * W + x] = (T)((bits >> lane) & 1u);
+      if (x < W) out[row * W + x] = ((bits >> lane) & 1u) ? one : (T)0;
     }
   }
 }
 
 template <typename T>
-static int launch_unpack(const uint32_t* packed, long long n_frames, int H, int W, T* out, cudaStream_t stream) {
+static int launch_unpack(const uint32_t* packed, long long n_frames, int H, int W, T one, T* out, cudaStream_t stream) {
   SOLA_REQUIRE(packed && out, "unpack: null pointer");
   SOLA_REQUIRE(n_frames >= 0 && H > 0 && W > 0, "unpack: bad shape");
   if (n_frames == 0) return SOLA_OK;
@@ -235,7 +235,7 @@ static int launch_unpack(const uint32_t* packed, long long n_frames, int H, int 
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  unpack_warp_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(packed, n_rows, W, Wp, out);
+  unpack_warp_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(packed, n_rows, W, Wp, one, out);
   return check_launch("unpack kernel");
 }
 
@@ -270,11 +270,17 @@ int sola_pack_mask_u8(const uint8_t* mask, long long n_frames, int H, int W, uin
 }
 
 int sola_unpack_f32(const uint32_t* packed, long long n_frames, int H, int W, float* out, cudaStream_t stream) {
-  return launch_unpack<float>(packed, n_frames, H, W, out, stream);
+  return launch_unpack<float>(packed, n_frames, H, W, 1.0f, out, stream);
 }
 
 int sola_unpack_u8(const uint32_t* packed, long long n_frames, int H, int W, uint8_t* out, cudaStream_t stream) {
-  return launch_unpack<uint8_t>(packed, n_frames, H, W, out, stream);
+  return launch_unpack<uint8_t>(packed, n_frames, H, W, (uint8_t)1, out, stream);
+}
+
+// foreground written as `one_value` (255 for the PNG planes of inference.py:90)
+int sola_unpack_u8_value(const uint32_t* packed, long long n_frames, int H, int W, int one_value, uint8_t* out, cudaStream_t stream) {
+  SOLA_REQUIRE(one_value >= 0 && one_value <= 255, "unpack_u8_value: one_value out of range");
+  return launch_unpack<uint8_t>(packed, n_frames, H, W, (uint8_t)one_value, out, stream);
 }
 
 }  // extern "C"

@@ -207,14 +207,18 @@ def pack_masks(mask, *, want_area: bool = False, threshold: Optional[float] = No
     return packed
 
 
-def unpack_masks(packed: PackedMasks, dtype=torch.float32) -> torch.Tensor:
-    """PackedMasks -> (..., H, W) {0,1} tensor of fp32 or uint8 on the device."""
+def unpack_masks(packed: PackedMasks, dtype=torch.float32, one_value: int = 1) -> torch.Tensor:
+    """PackedMasks -> (..., H, W) {0,1} tensor of fp32 or uint8 on the device (uint8: foreground = `one_value`, e.g. 255
+    for the PNG planes of inference.py:89-91)."""
     assert dtype in (torch.float32, torch.uint8)
     w = packed.words.contiguous()
     out = torch.empty((*packed.lead_shape, packed.H, packed.W), dtype=dtype, device=w.device)
     with torch.cuda.device(w.device):
-        _lib.call("sola_unpack_f32" if dtype == torch.float32 else "sola_unpack_u8",
-                  w.data_ptr(), packed.n_frames, packed.H, packed.W, out.data_ptr(), _stream(w))
+        if dtype == torch.uint8 and one_value != 1:
+            _lib.call("sola_unpack_u8_value", w.data_ptr(), packed.n_frames, packed.H, packed.W, int(one_value), out.data_ptr(), _stream(w))
+        else:
+            _lib.call("sola_unpack_f32" if dtype == torch.float32 else "sola_unpack_u8",
+                      w.data_ptr(), packed.n_frames, packed.H, packed.W, out.data_ptr(), _stream(w))
     return out
 
 

@@ -97,3 +97,30 @@ def test_gpu_bit_transpose_and_encode_overflow_fallback():
     np.testing.assert_array_equal(out.cpu().numpy().view(np.uint32), pack_bits(m.transpose(0, 2, 1)))
     # noisy mask with more transitions than the cap -> host fallback gives the same string
     assert rle.encode_rle_masklet_packed(p, cap=64) == RO.encode_masklet(m)
+
+
+@pytest.mark.gpu
+def test_gpu_get_sam2_masklet_packed_and_png_and_sidecar(tmp_path):
+    """RLE lists -> selected OR-merge on the device == the reference's numpy path (oracle), PNG planes, packed sidecar round trip."""
+    import sola_b200 as S
+    from sola_b200 import dataloader_ops as D, evaluator
+    from oracle import maskpath_oracle as O
+    rng = np.random.default_rng(5)
+    tracks = [(rng.random((4, 45, 70)) > 0.8).astype(np.uint8) for _ in range(5)]
+    rles = [RO.encode_masklet(t) for t in tracks]
+    for preds in ([0, 1, 0, 1, 1], [0, 0, 0, 0, 0], [1, 0, 0, 0, 0]):
+        exp = np.asarray(O.merge_selected_tracks([RO.decode_masklet(r) for r in rles], preds)) != 0
+        got = D.get_sam2_masklet_packed(rles, preds)
+        np.testing.assert_array_equal(S.unpack_masks(got, torch.uint8).cpu().numpy(), exp.astype(np.uint8))
+    assert D.get_sam2_masklet_packed([], []) is None
+    merged = D.get_sam2_masklet_packed(rles, [0, 1, 0, 1, 1])
+    png = D.png_planes(merged)
+    ref = (tracks[1] | tracks[3] | tracks[4])
+    np.testing.assert_array_equal(png, (ref * 255).astype(np.uint8))              # inference.py:90
+    D.save_packed_masklet(str(tmp_path / "m.npz"), merged)
+    back = D.load_packed_masklet(str(tmp_path / "m.npz"))
+    np.testing.assert_array_equal(back.numpy_u32(), merged.numpy_u32())
+    # J&F straight from the packed planes
+    gt = S.pack_masks(tracks[0])
+    c = S.frame_counts_packed(merged.reshape_lead(1, 4), gt.reshape_lead(1, 4))[0].cpu().numpy()[0, 0]
+    np.testing.assert_array_equal(c, (ref & tracks[0]).sum((1, 2)))
