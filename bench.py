@@ -226,23 +226,30 @@ def checks(w: Workload, out) -> dict:
 # ---------------------------------------------------------------------------------------------------------------
 def cpu_reference_step(logits_cpu: torch.Tensor, prompts, n_pairs_st: int):
     """The reference's operations on a sample: per-track linear stages, greedy IoU pairs, spatio-temporal pairs.
-    Returns seconds (t_linear_per_track, t_gather_pair, t_st_pair)."""
+    Returns seconds (t_linear_per_track, t_gather_pair, t_st_pair).  Works on CPU tensors (the CPU arm) and on CUDA tensors
+    (the reference's own GPU path: generic ATen launches with a .item() sync per scalar)."""
     from oracle import maskpath_oracle as O
     S_, T = logits_cpu.shape[:2]
+    on_gpu = logits_cpu.is_cuda
+    sync = torch.cuda.synchronize if on_gpu else (lambda: None)
+    sync()
     t0 = time.perf_counter()
     masklets, resized = [], []
     for i in range(S_):
         frames = [O.binarize(logits_cpu[i, t][None]) for t in range(T)]                  # generate_tokens_grid.py:219 per frame
         m = torch.cat(frames, 0)                                                         # :224
         masklets.append(m)
-        _ = [O.get_stability_score(logits_cpu[i, t].numpy()) for t in range(T)]          # prompt_generator.py:169 (per plane)
+        _ = [O.get_stability_score(logits_cpu[i, t].cpu().numpy()) for t in range(T)]    # prompt_generator.py:169 (numpy, per plane)
         resized.append(O.reshape_masklet(m))                                             # seg_utils.py:145
+    sync()
     t_lin = (time.perf_counter() - t0) / S_
     t0 = time.perf_counter()
     n_g = 0
     for i in range(S_):
         for p in prompts[: 2 * S_]:
             pm = O.resize_prompt_nearest(p["segmentation"], resized[i].shape[1], resized[i].shape[2])       # :271-272
+            if on_gpu:
+                pm = pm.to(logits_cpu.device)              # the reference does this H2D inside the loop (:271)
             O.compute_mask_iou(resized[i][p["frame_idx"]], pm)                                                # :273
             n_g += 1
     t_g = (time.perf_counter() - t0) / max(n_g, 1)
@@ -258,9 +265,11 @@ def cpu_reference_step(logits_cpu: torch.Tensor, prompts, n_pairs_st: int):
     return t_lin, t_g, t_st
 
 
-def cpu_arm(n_tracks, n_frames, steps, warmup, sample_tracks=4):
+def cpu_arm(n_tracks, n_frames, steps, warmup, sample_tracks=4, device="cpu"):
     from sola_b200 import synth
     logits, prompts = synth.dedup_candidates(sample_tracks, n_frames, CFG["H"], CFG["W"], seed=1234 + 2, device="cpu", bin_size=CFG["bin_size"])
+    if device != "cpu":
+        logits = logits.to(device)
     n_pairs = sample_tracks * (sample_tracks - 1) // 2
     times = []
     for it in range(warmup + steps):
@@ -423,6 +432,7 @@ def main():
         return
 
     peak, peak_src = peaks()
+    fused_flag = w.fused
     achieved = w.k1_bytes / (k1_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -442,10 +452,19 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         v, full, sample = cpu_arm(n_tracks, n_frames, 1, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
+        # second, informative baseline: the same reference operations on CUDA tensors — generic ATen kernels plus
+        # one .item() sync per scalar, which is how the reference actually runs this path on a GPU
+        try:
+            del w                                   # release the bench buffers so ATen's temporaries do not fight the allocator
+            torch.cuda.empty_cache()
+            v2, full2, sample2 = cpu_arm(n_tracks, n_frames, 2, 2, device=device)
+            line["gpu_aten_baseline"] = {"value": v2, "unit": UNIT, "kind": "port on CUDA tensors (ATen)", "sample": sample2}
+        except Exception as ex:
+            line["gpu_aten_baseline"] = {"value": None, "error": repr(ex)[:200]}
     traffic_path = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")       # from the committed `ncu --set full` capture
     if os.path.isfile(traffic_path) and (n_tracks, n_frames) == (CFG["n_tracks"], CFG["n_frames"]):
         with open(traffic_path) as f:
-            key = "fused_pack_resize_kernel<float>" if w.fused else "pack_flat_kernel<float, THRESH3>"
+            key = "fused_pack_resize_kernel<float>" if fused_flag else "pack_flat_kernel<float, THRESH3>"
             line["roofline"]["traffic"] = json.load(f).get(key, {}).get("dram_bytes_per_launch")
     print(json.dumps(line))
     if world > 1:
