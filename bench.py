@@ -259,7 +259,7 @@ def cpu_reference_step(logits_cpu: torch.Tensor, prompts, n_pairs_st: int):
         for j in range(i + 1, S_):
             if n_st >= n_pairs_st:
                 break
-            O.compute_masklet_iou(resized[i], resized[j])          # seg_utils.py:110 on the resized masklets (all that exist after grid :248-250)
+            O.compute_masklet_iou(resized[i], resized[j], resized[i].device)   # seg_utils.py:110 on the resized masklets (all that exist after grid :248-250)
             n_st += 1
     t_st = (time.perf_counter() - t0) / max(n_st, 1)
     return t_lin, t_g, t_st
