@@ -112,9 +112,13 @@ static int launch_raw_counts(const T* a, const T* b, long long n_frames, long lo
   SOLA_REQUIRE(a && b && inter && area_a && area_b, "frame_counts: null pointer");
   SOLA_REQUIRE(n_frames >= 0 && frame_px > 0 && frame_px < (1ll << 31), "frame_counts: bad shape n_frames=%lld frame_px=%lld", n_frames, frame_px);
   if (n_frames == 0) return SOLA_OK;
-  SOLA_CUDA(cudaMemsetAsync(inter, 0, sizeof(int) * n_frames, stream));
-  SOLA_CUDA(cudaMemsetAsync(area_a, 0, sizeof(int) * n_frames, stream));
-  SOLA_CUDA(cudaMemsetAsync(area_b, 0, sizeof(int) * n_frames, stream));
+  if (area_a == inter + n_frames && area_b == area_a + n_frames) {      // the usual (3, n) tensor: one memset instead of three
+    SOLA_CUDA(cudaMemsetAsync(inter, 0, sizeof(int) * 3 * n_frames, stream));
+  } else {
+    SOLA_CUDA(cudaMemsetAsync(inter, 0, sizeof(int) * n_frames, stream));
+    SOLA_CUDA(cudaMemsetAsync(area_a, 0, sizeof(int) * n_frames, stream));
+    SOLA_CUDA(cudaMemsetAsync(area_b, 0, sizeof(int) * n_frames, stream));
+  }
   constexpr int E = RawTraits<T>::E;
   const int n_chunks = (int)((frame_px + K3_CHUNK_PX - 1) / K3_CHUNK_PX);
   const int ctas_per_frame = (n_chunks + K3_CHUNKS_PER_CTA - 1) / K3_CHUNKS_PER_CTA;

@@ -24,8 +24,8 @@ def compute_masklet_iou(maskletA, maskletB, device=None) -> float:
     """seg_utils.py:110-125 — IoU over the whole (N, H, W) volume; empty union -> 1.0.
     Counts are exact integers (the reference's fp32 sums drift above 2**24 set pixels; |delta| < 1e-6)."""
     a = P.to_device(maskletA, device=device)
-    c = P.frame_counts(a, P.to_device(maskletB, device=a.device)).sum(dim=1, dtype=torch.int64).tolist()
-    inter, na, nb = c
+    c = P.frame_counts(a, P.to_device(maskletB, device=a.device)).cpu().numpy()          # per-frame int32 counts, one read-back
+    inter, na, nb = (int(v) for v in c.sum(axis=1, dtype="int64"))
     union = na + nb - inter
     if union == 0:
         return 1.0
