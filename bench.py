@@ -342,6 +342,8 @@ def main():
     torch.cuda.nvtx.range_push("timed")
     t_wall0 = time.perf_counter()
     ev0.record()
+    for j in w.jobs:
+        j.timing_events = []
     out = w.run_steps(args.steps, record_k1=True)
     ev1.record()
     barrier()
@@ -352,6 +354,7 @@ def main():
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = S.launch_count() - launches0
     k1_ms = float(np.mean([a.elapsed_time(b) for a, b in w.k1_events]))
+    k2_ms = float(np.mean([a.elapsed_time(b) for j in w.jobs for a, b in (j.timing_events or [])]))
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -441,6 +444,8 @@ def main():
         "config": {"workload": workload, "l2_policy": "inputs larger than L2 (18.9 GB fp32 logits per step vs 126 MB L2)",
                    "kept_sets": info, "parallelism": f"video-sharded x{world}, no data-path collective"},
         "clocks": clk.summary(t_wall0, t_wall1),
+        "stage_ms": {"dominant (K1+R1 fused)" if w.fused else "dominant (K1)": k1_ms, "K2 N x N (int pipe, carry-save, TMA-staged)": k2_ms,
+                     "everything else incl. gaps": max_ms / args.steps - k1_ms - k2_ms},
         "gpu_launches": int(launches),
         "e2e": e2e,
         "roofline": {"bound": "hbm", "kernel": ("fused_pack_resize_kernel<float> (K1+R1: binarise+pack+stability+resize)" if w.fused

@@ -258,6 +258,7 @@ class VideoDedupJob:
                  st_on_resized: bool = True, fused: bool = True, **rules):
         self.st_on_resized = st_on_resized
         self.fused = fused
+        self.timing_events = None            # set to a list to collect (start, end) CUDA events around the K2 N x N launch
         self.prompt_meta = list(prompt_meta)
         self.n_frames = n_frames
         self.mode, self.rules = mode, rules
@@ -299,7 +300,13 @@ class VideoDedupJob:
         g = P.gathered_inter(self.resized, planes, self.frame_idx_dev)                                                 # K2 gather
         # K2 N x N on the resized planes: after generate_tokens_grid.py:248-250 only the 540x960 masklets exist, so a
         # masklet-vs-masklet IoU (seg_utils.compute_masklet_iou) in that flow compares those
+        if self.timing_events is not None:
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
         inter = P.pairwise_inter_matrix(self.resized if self.st_on_resized else self.packed)                           # K2 N x N
+        if self.timing_events is not None:
+            eb.record()
+            self.timing_events.append((ea, eb))
         hg, hi, hc = self._pinned(N, int(planes.words.shape[0]), T)
         hg.copy_(g, non_blocking=True)
         hi.copy_(inter, non_blocking=True)
