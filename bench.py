@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--streams", type=int, default=1, choices=[1, 2], help="videos in flight on separate CUDA streams")
     ap.add_argument("--no-fuse", action="store_true", help="run K1 and R1 as two kernels instead of the fused one")
+    ap.add_argument("--st-native", action="store_true",
+                    help="N x N spatio-temporal IoU on the native 720x1280 planes instead of the 540x960 resized masklets the "
+                         "reference's filter works on (generate_tokens_grid.py:248-250)")
     return ap.parse_args()
 
 
@@ -118,10 +121,11 @@ class ClockSampler:
 # the step (product path)
 # ---------------------------------------------------------------------------------------------------------------
 class Workload:
-    def __init__(self, device, seed, n_tracks, n_frames, n_streams=1, fused=True):
+    def __init__(self, device, seed, n_tracks, n_frames, n_streams=1, fused=True, st_native=False):
         import sola_b200 as S
         self.n_streams = n_streams
         self.fused = fused
+        self.st_native = st_native
         from sola_b200 import synth
         self.S, self.device = S, device
         self.N, self.T, self.H, self.W = n_tracks, n_frames, CFG["H"], CFG["W"]
@@ -139,7 +143,7 @@ class Workload:
 
     def make_jobs(self):
         from sola_b200 import dedup
-        mk = lambda: dedup.VideoDedupJob(self.prompt_meta, self.T, device=self.device, mode="grid", bin_size=CFG["bin_size"],
+        mk = lambda: dedup.VideoDedupJob(self.prompt_meta, self.T, device=self.device, mode="grid", st_on_resized=not self.st_native, bin_size=CFG["bin_size"],
                                          n_max_tracks=CFG["n_max_tracks"], batch_size=CFG["batch_size"], miou_thresh=CFG["miou_thresh"])
         self.jobs = [mk(), mk()]
         # one stream per in-flight video: the HBM-bound K1 of video k+1 overlaps the ALU/XU-bound R1 + K2 of video k
@@ -207,9 +211,12 @@ def checks(w: Workload, out) -> dict:
     assert np.array_equal(inter, inter.T), "intersection matrix not symmetric"
     area = np.diag(inter)
     c = w.counts.view(3, w.N, w.T).cpu().numpy()
-    _, r_area = w.S.resize_bilinear_bin(w.packed, want_area=True)                      # untimed: R1's own per-frame areas
-    r_area = r_area.view(w.N, w.T).cpu().numpy().sum(1, dtype=np.int64)
-    assert np.array_equal(r_area, area), "diag(inter) != sum of R1 areas (checksum of checksums)"
+    if w.st_native:
+        assert np.array_equal(c[1].sum(1, dtype=np.int64), area), "diag(inter) != sum of K1 areas (checksum of checksums)"
+    else:
+        _, r_area = w.S.resize_bilinear_bin(w.packed, want_area=True)                  # untimed: R1's own per-frame areas
+        r_area = r_area.view(w.N, w.T).cpu().numpy().sum(1, dtype=np.int64)
+        assert np.array_equal(r_area, area), "diag(inter) != sum of R1 areas (checksum of checksums)"
     assert (c[0] <= c[1]).all() and (c[1] <= c[2]).all(), "stability counts not nested"
     assert (inter <= np.minimum(area[:, None], area[None, :])).all()
     # sub-sample vs the oracle: 2 tracks x 3 frames of planes + their pair intersection
@@ -324,7 +331,7 @@ def main():
     import sola_b200 as S
     S.load_library()
 
-    w = Workload(device, seed=1234 + 2 + 1000 * rank, n_tracks=n_tracks, n_frames=n_frames, n_streams=args.streams, fused=not args.no_fuse)
+    w = Workload(device, seed=1234 + 2 + 1000 * rank, n_tracks=n_tracks, n_frames=n_frames, n_streams=args.streams, fused=not args.no_fuse, st_native=args.st_native)
     w.make_jobs()
     torch.cuda.synchronize()
 
@@ -442,7 +449,8 @@ def main():
         "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload, "l2_policy": "inputs larger than L2 (18.9 GB fp32 logits per step vs 126 MB L2)",
-                   "kept_sets": info, "parallelism": f"video-sharded x{world}, no data-path collective"},
+                   "kept_sets": info, "parallelism": f"video-sharded x{world}, no data-path collective",
+                   "n_x_n_planes": "native 720x1280" if args.st_native else "540x960 resized masklets (what the reference filter compares)"},
         "clocks": clk.summary(t_wall0, t_wall1),
         "stage_ms": {"dominant (K1+R1 fused)" if w.fused else "dominant (K1)": k1_ms, "K2 N x N (int pipe, carry-save, TMA-staged)": k2_ms,
                      "everything else incl. gaps": max_ms / args.steps - k1_ms - k2_ms},
