@@ -96,3 +96,22 @@ def test_hypothesis_k1_k3_shapes():
         np.testing.assert_array_equal(k[0] + u, k[1] + k[2])
 
     run()
+
+
+def test_pure_c_client(tmp_path):
+    """A plain C program (no Python, no torch) links the shared library through include/sola_maskpath.h and checks K1, K3 and the
+    fused entry point against C loops."""
+    import shutil
+    import subprocess
+    from sola_b200 import _build
+    _build.build()
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.isfile(nvcc):
+        pytest.skip("nvcc not available on this box")
+    exe = str(tmp_path / "c_abi_smoke")
+    libdir = os.path.join(ROOT, "sola_b200", "lib")
+    subprocess.run([nvcc, "-x", "c", os.path.join(ROOT, "tests", "c_abi_smoke.c"), "-I", os.path.join(ROOT, "include"), "-L", libdir,
+                    "-lsola_maskpath", "-Xlinker", f"-rpath={libdir}", "-o", exe], check=True, capture_output=True, text=True)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "c_abi_smoke ok" in res.stdout
