@@ -69,12 +69,13 @@ pack_flat_kernel(const T* __restrict__ in, int frame_px, int ctas_per_frame, Thr
         vec_bits<MODE>(raw[j], th, T(), m, h, l);
         xm |= m << (E * j);
       }
+    } else if (MODE == MODE_THRESH3) {
+      chunk_extract3<T, L, false>(raw, th, xm, xh, xl, n_hi, n_lo);      // hi / lo counted inside (bf16: packed compares)
     } else {
 #pragma unroll
       for (int j = L - 1; j >= 0; --j) vec_push<MODE>(raw[j], th, T(), xm, xh, xl);
     }
     n_mid += __popc(xm);
-    if (MODE == MODE_THRESH3) { n_hi += __popc(xh); n_lo += __popc(xl); }
     if (dst) {
       const uint32_t word = transpose_slots<E>(xm, lane);
       const int wi = (px0 >> 5) + out_word_in_chunk;

@@ -82,13 +82,17 @@ fused_pack_resize_kernel(const T* __restrict__ logits, int n_frames, int frames_
         }
       }
       uint32_t xm = 0, xh = 0, xl = 0;
-#pragma unroll
-      for (int j = L - 1; j >= 0; --j) vec_push<MODE_THRESH3>(raw[j], th, T(), xm, xh, xl);
       // stability / area counts cover owned words only (halo rows are counted by the band that owns them)
       const int w0 = c * 32;
       if (w0 + 32 <= owned_words) {
-        n_mid += __popc(xm); n_hi += __popc(xh); n_lo += __popc(xl);
-      } else if (w0 < owned_words) {
+        chunk_extract3<T, L, false>(raw, th, xm, xh, xl, n_hi, n_lo);
+        n_mid += __popc(xm);
+      } else if (w0 >= owned_words) {
+        int unused_hi = 0, unused_lo = 0;
+        chunk_extract3<T, L, false>(raw, th, xm, xh, xl, unused_hi, unused_lo);     // halo chunk: plane bits only
+      } else {
+        int unused_hi = 0, unused_lo = 0;
+        chunk_extract3<T, L, true>(raw, th, xm, xh, xl, unused_hi, unused_lo);
         uint32_t own = 0;
 #pragma unroll
         for (int j = 0; j < L; ++j)
@@ -201,11 +205,15 @@ band_pack_generic_kernel(const T* __restrict__ logits, int n_frames, int frames_
         }
       }
       uint32_t xm = 0, xh = 0, xl = 0;
-#pragma unroll
-      for (int j = L - 1; j >= 0; --j) vec_push<MODE_THRESH3>(raw[j], th, T(), xm, xh, xl);
       if (px0 >= cnt_lo_px && px0 + FU_CHUNK_PX <= cnt_hi_px) {
-        n_mid += __popc(xm); n_hi += __popc(xh); n_lo += __popc(xl);
-      } else if (px0 < cnt_hi_px && px0 + FU_CHUNK_PX > cnt_lo_px) {
+        chunk_extract3<T, L, false>(raw, th, xm, xh, xl, n_hi, n_lo);
+        n_mid += __popc(xm);
+      } else if (!(px0 < cnt_hi_px && px0 + FU_CHUNK_PX > cnt_lo_px)) {
+        int unused_hi = 0, unused_lo = 0;
+        chunk_extract3<T, L, false>(raw, th, xm, xh, xl, unused_hi, unused_lo);     // halo chunk: plane bits only
+      } else {
+        int unused_hi = 0, unused_lo = 0;
+        chunk_extract3<T, L, true>(raw, th, xm, xh, xl, unused_hi, unused_lo);
         uint32_t own = 0;
 #pragma unroll
         for (int j = 0; j < L; ++j) {

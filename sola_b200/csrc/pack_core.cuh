@@ -3,6 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include <type_traits>
+#include <string.h>
 
 namespace sola {
 
@@ -10,7 +11,17 @@ enum PackMode { MODE_THRESH3 = 0, MODE_THRESH1 = 1, MODE_NONZERO = 2 };
 
 struct Thresholds {
   float mid, hi, lo;
+  uint32_t hi_bf2, lo_bf2;      // floor-to-bf16 of hi / lo, replicated in both halves (bf16 count path, see vec_count2)
 };
+
+// largest bf16 value <= t, as its 16 bits: for a bf16 x, (x > t) == (x > bf16_floor(t)), so the packed bf16 compare is exact
+inline uint32_t bf16_floor_bits(float t) {
+  uint32_t b;
+  memcpy(&b, &t, 4);
+  uint32_t h = b >> 16;
+  if ((b & 0xffffu) && (b >> 31)) h += 1;        // negative and inexact: one step towards -inf
+  return h & 0xffffu;
+}
 
 // numpy / torch compare float32 data against the Python scalar cast to float32 (prompt_generator.py:177,182).  A threshold of
 // -0.0 is normalised to +0.0: `x > -0.0` and `x > +0.0` are the same predicate, but the sign-of-(t - x) extraction below would
@@ -20,6 +31,8 @@ inline Thresholds make_thresholds(double thr, double off) {
   t.mid = (float)thr + 0.0f;
   t.hi = (float)(thr + off) + 0.0f;
   t.lo = (float)(thr - off) + 0.0f;
+  t.hi_bf2 = bf16_floor_bits(t.hi) * 0x00010001u;
+  t.lo_bf2 = bf16_floor_bits(t.lo) * 0x00010001u;
   return t;
 }
 
@@ -149,6 +162,52 @@ __device__ __forceinline__ uint32_t transpose_slots(uint32_t x, int lane) {
     x = (lane & d) ? ((x & ~lo) | ((v >> (E * d)) & lo)) : ((x & lo) | ((v << (E * d)) & ~lo));
   }
   return x;
+}
+
+// ---- bf16 count path ---------------------------------------------------------------------------------------------------
+// For the two stability thresholds only the COUNT matters.  With bf16 logits a 32-bit word holds two elements, and the packed
+// compare `set.gt.bf16x2` + packed add run on the fma/half pipe: 2 instructions per PAIR per threshold and no alu-pipe work,
+// instead of unpack + FADD + funnel shift per ELEMENT.  Sums stay exact (<= 32 per half per chunk, bf16 is exact to 256).
+struct PairCounts {
+  __nv_bfloat162 hi, lo;
+  __device__ __forceinline__ void reset() { hi = __float2bfloat162_rn(0.f); lo = hi; }
+  __device__ __forceinline__ int total_hi() const { return (int)__low2float(hi) + (int)__high2float(hi); }
+  __device__ __forceinline__ int total_lo() const { return (int)__low2float(lo) + (int)__high2float(lo); }
+};
+
+__device__ __forceinline__ void vec_count2(const uint4& raw, const Thresholds& th, PairCounts& pc) {
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  const __nv_bfloat162 t_hi = *reinterpret_cast<const __nv_bfloat162*>(&th.hi_bf2);
+  const __nv_bfloat162 t_lo = *reinterpret_cast<const __nv_bfloat162*>(&th.lo_bf2);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&w[c]);
+    pc.hi = __hadd2(pc.hi, __hgt2(x2, t_hi));          // 1.0 / 0.0 per half; NaN -> 0.0 (ordered compare)
+    pc.lo = __hadd2(pc.lo, __hgt2(x2, t_lo));
+  }
+}
+
+// One chunk's predicate extraction.  Returns the stored plane's private word in xm; counts either as bit words (xh, xl — needed
+// when a range mask must be applied) or, for bf16 with WANT_BITS == false, directly as integers in n_hi / n_lo.
+template <typename T, int L, bool WANT_BITS>
+__device__ __forceinline__ void chunk_extract3(const uint4 (&raw)[L], const Thresholds& th, uint32_t& xm, uint32_t& xh, uint32_t& xl,
+                                               int& n_hi, int& n_lo) {
+  xm = xh = xl = 0;
+  if (sizeof(T) == 2 && !WANT_BITS) {
+    PairCounts pc;
+    pc.reset();
+#pragma unroll
+    for (int j = L - 1; j >= 0; --j) {
+      vec_push<MODE_THRESH1>(raw[j], th, T(), xm, xh, xl);
+      vec_count2(raw[j], th, pc);
+    }
+    n_hi += pc.total_hi();
+    n_lo += pc.total_lo();
+  } else {
+#pragma unroll
+    for (int j = L - 1; j >= 0; --j) vec_push<MODE_THRESH3>(raw[j], th, T(), xm, xh, xl);
+    if (!WANT_BITS) { n_hi += __popc(xh); n_lo += __popc(xl); }
+  }
 }
 
 // any-width stand-alone K1 (flat run + re-cut), defined in fused_pack_resize.cu

@@ -80,6 +80,14 @@ def test_bf16_logits(shape):
     c = counts.cpu().numpy()
     np.testing.assert_array_equal(c[0], (ref > 1).sum((-2, -1)))
     np.testing.assert_array_equal(c[2], (ref > -1).sum((-2, -1)))
+    # thresholds that are NOT bf16-representable (the packed-compare count path floors them to bf16; must stay exact), incl. negatives
+    for thr, off in ((0.3, 0.7), (-0.37, 0.11), (0.0, 1e-3), (2.0, 3.0)):
+        packed, counts = S.binarize_pack_stability(x.cuda(), thr, off)
+        c = counts.cpu().numpy()
+        np.testing.assert_array_equal(packed.numpy_u32(), O.pack_bits(ref > np.float32(thr)))
+        np.testing.assert_array_equal(c[0], (ref > np.float32(thr + off)).sum((-2, -1)))
+        np.testing.assert_array_equal(c[1], (ref > np.float32(thr)).sum((-2, -1)))
+        np.testing.assert_array_equal(c[2], (ref > np.float32(thr - off)).sum((-2, -1)))
 
 
 @pytest.mark.parametrize("shape", [(4, 64, 96), (3, 480, 854), (2, 33, 47), (1, 720, 1280)])
