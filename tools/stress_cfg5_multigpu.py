@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--H", type=int, default=1080)
     ap.add_argument("--W", type=int, default=1920)
     ap.add_argument("--verify", action="store_true", help="rank 0 recomputes the matrix alone from the gathered planes")
+    ap.add_argument("--native", action="store_true", help="pairwise matrix on the native-resolution planes (4x more all-gather bytes) "
+                                                          "instead of the 540x960 resized masklets the reference filter compares")
     args = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -43,9 +45,10 @@ def main():
         dist.barrier()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
-    packed, counts = S.binarize_pack_stability(logits)                       # K1 on the local tracks
+    packed, counts, resized, r_area = S.binarize_pack_resize(logits, want_area=True)   # fused K1 + R1 on the local tracks
+    planes = packed if args.native else resized
     e1.record()
-    inter = sharding.pairwise_inter_matrix_sharded(packed)                   # all-gather + tile share + all-reduce
+    inter = sharding.pairwise_inter_matrix_sharded(planes)                   # all-gather + tile share + all-reduce
     e2.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2)], dtype=torch.float64, device=device)
@@ -58,21 +61,22 @@ def main():
         for i in range(len(m)):
             if alive[i]:
                 alive[i + 1:] &= ~(iou[i, i + 1:] > 0.7)
-        words = packed.words[0].numel()
+        words = planes.words[0].numel()
         out = {"workload": f"config5-shaped: {args.tracks} tracks x {args.frames} frames x {args.H}x{args.W}", "n_gpus": world,
-               "k1_ms_max_over_ranks": float(t[0]), "pairwise_ms_max_over_ranks (all-gather + K2 share + all-reduce)": float(t[1]),
+               "k1r1_fused_ms_max_over_ranks": float(t[0]), "planes": "native" if args.native else "resized 540x960", "pairwise_ms_max_over_ranks (all-gather + K2 share + all-reduce)": float(t[1]),
                "masklet_frames_per_s": args.tracks * args.frames / ((float(t[0]) + float(t[1])) * 1e-3),
                "pair_words_per_s": args.tracks * (args.tracks - 1) / 2 * words / (float(t[1]) * 1e-3),
                "symmetric": bool(np.array_equal(m, m.T)), "kept": int(alive.sum())}
         print(json.dumps(out))
     # checksum of checksums across ranks: diag(inter) of my tracks == my K1 areas
     mine = inter.diagonal()[rank * n_local:(rank + 1) * n_local]
-    assert torch.equal(mine, counts[1].sum(dim=1, dtype=torch.int64)), "diag(inter) != K1 areas"
+    own_area = (counts[1] if args.native else r_area).sum(dim=1, dtype=torch.int64)
+    assert torch.equal(mine, own_area), "diag(inter) != areas of my planes"
     if args.verify and world > 1:
-        gathered = torch.empty((args.tracks, *packed.words.shape[1:]), dtype=torch.int32, device=device)
-        dist.all_gather_into_tensor(gathered, packed.words.contiguous())
+        gathered = torch.empty((args.tracks, *planes.words.shape[1:]), dtype=torch.int32, device=device)
+        dist.all_gather_into_tensor(gathered, planes.words.contiguous())
         if rank == 0:
-            alone = S.pairwise_inter_matrix(S.PackedMasks(gathered, args.H, args.W))
+            alone = S.pairwise_inter_matrix(S.PackedMasks(gathered, planes.H, planes.W))
             assert torch.equal(alone, inter), "sharded matrix differs from the single-rank matrix"
             print(json.dumps({"sharded_matrix_identical_to_single_rank": True}))
     if world > 1:
