@@ -92,6 +92,18 @@ int sola_pair_iou_st(const uint32_t* packed, int N, long long words_per_track, l
  * (one all-reduce) is the full matrix. */
 int sola_pair_iou_st_part(const uint32_t* packed, int N, long long words_per_track, int part, int n_parts, long long* inter_out,
                           sola_stream_t stream);
+/* fused exchange + K2: row_ptrs (device array of N device pointers) gives each track's packed planes, possibly in a PEER GPU's
+ * memory; the kernel reads peers directly over NVLink so the transfer overlaps the math (no NCCL all-gather in front).  Here the
+ * WORD axis is partitioned (part p covers 1/n_parts of every track), so the parts are balanced for any N and each rank pulls only
+ * 1/n_parts of its peers' planes; the sum of all parts' outputs is the full matrix. */
+int sola_pair_iou_st_rows(const uint32_t* const* row_ptrs, int N, long long words_per_track, int part, int n_parts, long long* inter_out,
+                          sola_stream_t stream);
+/* inter_inout += intersections over these words (no memset): walk the word axis in chunks (e.g. pulled from peers, see below). */
+int sola_pair_iou_st_accumulate(const uint32_t* packed, int N, long long words_per_track, long long* inter_inout, sola_stream_t stream);
+/* dst (N, n_words) <- words [word_lo, word_lo + n_words) of every row of the pointer table (rows may live in peer GPUs' memory:
+ * the loads then travel over NVLink).  With sola_pair_iou_st_accumulate on a second stream this is the pipelined exchange of
+ * BASELINE config 5: chunk c+1 is pulled while chunk c is reduced by the TMA-staged K2 kernel. */
+int sola_pull_rows(const uint32_t* const* row_ptrs, int N, long long word_lo, long long n_words, uint32_t* dst, sola_stream_t stream);
 /* gathered single-frame: tracks (N, T, frame_words), prompts (P, frame_words), frame_idx int32 [P] ->
  * inter (N, P) = |track_i[frame_idx[j]] ∩ prompt_j|, area_t (N, P) = |track_i[frame_idx[j]]|, area_p [P].
  * This is the matrix walked by generate_tokens_grid.py:266-278 / generate_tokens_gdino.py:288-300. */

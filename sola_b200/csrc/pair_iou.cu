@@ -69,8 +69,8 @@ __device__ __forceinline__ void tile_from_index(int idx, int nt, int& ti, int& t
 }
 
 template <bool DIAG>
-__device__ __forceinline__ void st_tile_body(const uint32_t* __restrict__ packed, int N, long long words, int ti, int tj,
-                                             long long s_begin, long long s_end, uint4* smem,
+__device__ __forceinline__ void st_tile_body(const uint32_t* __restrict__ packed, const uint32_t* const* __restrict__ row_ptrs, int N,
+                                             long long words, int ti, int tj, long long s_begin, long long s_end, uint4* smem,
                                              unsigned long long* __restrict__ inter) {
   constexpr int ROWS = DIAG ? PT : 2 * PT;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -91,7 +91,9 @@ __device__ __forceinline__ void st_tile_body(const uint32_t* __restrict__ packed
       const long long w = w0 + q * 4;
       long long remain = (words - w) * 4;               // bytes left in this track row
       int nbytes = (track < N && remain > 0) ? (int)(remain < 16 ? remain : 16) : 0;
-      const uint32_t* src = packed + (long long)(track < N ? track : 0) * words + (nbytes ? w : 0);
+      // row base: one contiguous (N, words) buffer, or a table of per-track pointers (tracks living on peer GPUs, read over NVLink)
+      const uint32_t* base = row_ptrs ? row_ptrs[track < N ? track : 0] : packed + (long long)(track < N ? track : 0) * words;
+      const uint32_t* src = base + (nbytes ? w : 0);
       cp_async16(dst + q * ROWS + row, src, nbytes);
     }
   };
@@ -147,17 +149,19 @@ __device__ __forceinline__ void st_tile_body(const uint32_t* __restrict__ packed
 }
 
 __global__ void __launch_bounds__(ST_THREADS)
-pair_iou_st_kernel(const uint32_t* __restrict__ packed, int N, long long words, int nt, int n_tiles, int splits,
-                   int tile_first, int tile_step, unsigned long long* __restrict__ inter) {
+pair_iou_st_kernel(const uint32_t* __restrict__ packed, const uint32_t* const* __restrict__ row_ptrs, int N, long long words, int nt,
+                   int n_tiles, int splits, int tile_first, int tile_step, long long stage_lo, long long stage_hi,
+                   unsigned long long* __restrict__ inter) {
   extern __shared__ uint4 smem_st[];
-  // n_tiles = tiles this launch computes: global tile ids tile_first, tile_first + tile_step, ... (a rank's share)
+  // n_tiles = tiles this launch computes: global tile ids tile_first, tile_first + tile_step, ... (a rank's share);
+  // [stage_lo, stage_hi) = the slice of the word axis this launch covers (a rank's share when the K axis is partitioned)
   const int tile = tile_first + (blockIdx.x % n_tiles) * tile_step, split = blockIdx.x / n_tiles;
   int ti, tj;
   tile_from_index(tile, nt, ti, tj);
-  const long long stages = (words + STAGE_WORDS - 1) / STAGE_WORDS;
-  const long long s_begin = stages * split / splits, s_end = stages * (split + 1) / splits;
-  if (ti == tj) st_tile_body<true>(packed, N, words, ti, tj, s_begin, s_end, smem_st, inter);
-  else st_tile_body<false>(packed, N, words, ti, tj, s_begin, s_end, smem_st, inter);
+  const long long stages = stage_hi - stage_lo;
+  const long long s_begin = stage_lo + stages * split / splits, s_end = stage_lo + stages * (split + 1) / splits;
+  if (ti == tj) st_tile_body<true>(packed, row_ptrs, N, words, ti, tj, s_begin, s_end, smem_st, inter);
+  else st_tile_body<false>(packed, row_ptrs, N, words, ti, tj, s_begin, s_end, smem_st, inter);
 }
 
 // ---- TMA-staged variant (default) --------------------------------------------------------------------------------------
@@ -401,12 +405,12 @@ using namespace sola;
 extern "C" {
 
 static int launch_pair_iou_st(const uint32_t* packed, int N, long long words_per_track, long long* inter_out, long long* area_out,
-                              int part, int n_parts, cudaStream_t stream) {
+                              int part, int n_parts, cudaStream_t stream, bool accumulate = false) {
   SOLA_REQUIRE(N >= 0 && words_per_track > 0, "pair_iou_st: bad shape N=%d words=%lld", N, words_per_track);
   SOLA_REQUIRE(n_parts >= 1 && part >= 0 && part < n_parts, "pair_iou_st: bad partition %d / %d", part, n_parts);
   if (N == 0) return SOLA_OK;
   SOLA_REQUIRE(packed && inter_out, "pair_iou_st: null pointer");
-  SOLA_CUDA(cudaMemsetAsync(inter_out, 0, sizeof(long long) * (size_t)N * N, stream));
+  if (!accumulate) SOLA_CUDA(cudaMemsetAsync(inter_out, 0, sizeof(long long) * (size_t)N * N, stream));
   const bool fast = (words_per_track % 4 == 0) && aligned16(packed);
   if (fast) {
     const int nt = (N + PT - 1) / PT;
@@ -430,11 +434,11 @@ static int launch_pair_iou_st(const uint32_t* packed, int N, long long words_per
       } else {
         SOLA_CUDA(cudaFuncSetAttribute(pair_iou_st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         pair_iou_st_kernel<<<(unsigned)(splits * n_tiles), ST_THREADS, smem, stream>>>(
-            packed, N, words_per_track, nt, n_tiles, (int)splits, part, n_parts, reinterpret_cast<unsigned long long*>(inter_out));
+            packed, nullptr, N, words_per_track, nt, n_tiles, (int)splits, part, n_parts, 0, stages, reinterpret_cast<unsigned long long*>(inter_out));
       }
     }
   } else {
-    SOLA_REQUIRE(n_parts == 1, "pair_iou_st: the unaligned fallback does not support partitioning");
+    SOLA_REQUIRE(n_parts == 1 && !accumulate, "pair_iou_st: the unaligned fallback does not support partitioning / accumulation");
     SOLA_REQUIRE(N <= 65535, "pair_iou_st: unaligned fallback supports N <= 65535");
     dim3 grid(N, N);
     pair_iou_st_simple_kernel<<<grid, 256, 0, stream>>>(packed, N, words_per_track, reinterpret_cast<unsigned long long*>(inter_out));
@@ -457,6 +461,77 @@ int sola_pair_iou_st(const uint32_t* packed, int N, long long words_per_track, l
 int sola_pair_iou_st_part(const uint32_t* packed, int N, long long words_per_track, int part, int n_parts, long long* inter_out,
                           cudaStream_t stream) {
   return launch_pair_iou_st(packed, N, words_per_track, inter_out, nullptr, part, n_parts, stream);
+}
+
+// Fused exchange + K2 for tracks spread over the GPUs of one box: row_ptrs[i] (device array of N device pointers) is the base of
+// track i's packed planes, which may live in a PEER GPU's memory (mapped through NVLink / NVSwitch).  The kernel's cp.async stage
+// loads read the peers directly, so the transfer overlaps the AND-popcount math stage by stage instead of preceding it as an NCCL
+// all-gather.  The WORD axis is partitioned: part p computes every pair tile over words [stages*p/n, stages*(p+1)/n) * 32 — perfectly
+// balanced for any N, and each rank pulls only 1/n_parts of every peer track (an all-to-all's volume, not an all-gather's).
+// Intersections are sums over words, so the sum of all parts' outputs (one all-reduce) is the full matrix.  Rows must be 16-byte aligned.
+int sola_pair_iou_st_rows(const uint32_t* const* row_ptrs, int N, long long words_per_track, int part, int n_parts, long long* inter_out,
+                          cudaStream_t stream) {
+  SOLA_REQUIRE(N >= 0 && words_per_track > 0 && words_per_track % 4 == 0, "pair_iou_st_rows: bad shape (words must be a multiple of 4)");
+  SOLA_REQUIRE(n_parts >= 1 && part >= 0 && part < n_parts, "pair_iou_st_rows: bad partition %d / %d", part, n_parts);
+  if (N == 0) return SOLA_OK;
+  SOLA_REQUIRE(row_ptrs && inter_out, "pair_iou_st_rows: null pointer");
+  SOLA_CUDA(cudaMemsetAsync(inter_out, 0, sizeof(long long) * (size_t)N * N, stream));
+  const int nt = (N + PT - 1) / PT;
+  const int n_tiles = nt * (nt + 1) / 2;
+  const long long all_stages = (words_per_track + STAGE_WORDS - 1) / STAGE_WORDS;
+  const long long stage_lo = all_stages * part / n_parts, stage_hi = all_stages * (part + 1) / n_parts;
+  const long long stages = stage_hi - stage_lo;
+  if (stages <= 0) return SOLA_OK;
+  long long splits = ((long long)num_sms() * 4 + n_tiles - 1) / n_tiles;
+  if (splits > stages) splits = stages;
+  const long long min_splits = (stages + (1 << 20) - 1) >> 20;
+  if (splits < min_splits) splits = min_splits;
+  if (splits < 1) splits = 1;
+  const size_t smem = (size_t)NSTAGE * (2 * PT) * KQ * sizeof(uint4);
+  SOLA_CUDA(cudaFuncSetAttribute(pair_iou_st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pair_iou_st_kernel<<<(unsigned)(splits * n_tiles), ST_THREADS, smem, stream>>>(
+      nullptr, row_ptrs, N, words_per_track, nt, n_tiles, (int)splits, 0, 1, stage_lo, stage_hi,
+      reinterpret_cast<unsigned long long*>(inter_out));
+  return check_launch("pair_iou_st_rows kernel");
+}
+
+// inter_inout += the N x N intersections over these words (no memset): lets a caller walk the word axis in chunks — e.g. chunks
+// pulled from peer GPUs on one stream while the previous chunk is being reduced on another (sharding.PeerPlanes).
+int sola_pair_iou_st_accumulate(const uint32_t* packed, int N, long long words_per_track, long long* inter_inout, cudaStream_t stream) {
+  return launch_pair_iou_st(packed, N, words_per_track, inter_inout, nullptr, 0, 1, stream, true);
+}
+
+namespace sola {
+// dst (N, n_words) <- words [word_lo, word_lo + n_words) of every row in the pointer table: 128-bit streaming loads, which go over
+// NVLink when the row lives in a peer GPU's memory.  grid.y = row, grid.x strides over the row's 16-byte vectors.
+__global__ void __launch_bounds__(256)
+pull_rows_kernel(const uint32_t* const* __restrict__ row_ptrs, long long word_lo, long long n_vec, uint4* __restrict__ dst) {
+  const uint4* src = reinterpret_cast<const uint4*>(row_ptrs[blockIdx.y] + word_lo);
+  uint4* out = dst + (long long)blockIdx.y * n_vec;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n_vec; i += 4 * stride) {          // 4 independent loads in flight per thread (NVLink latency)
+    const uint4 a = ld_stream_u4(src + i), b = ld_stream_u4(src + i + stride), c = ld_stream_u4(src + i + 2 * stride),
+                d = ld_stream_u4(src + i + 3 * stride);
+    out[i] = a; out[i + stride] = b; out[i + 2 * stride] = c; out[i + 3 * stride] = d;
+  }
+  for (; i < n_vec; i += stride) out[i] = ld_stream_u4(src + i);
+}
+}  // namespace sola
+
+int sola_pull_rows(const uint32_t* const* row_ptrs, int N, long long word_lo, long long n_words, uint32_t* dst, cudaStream_t stream) {
+  SOLA_REQUIRE(N >= 0 && word_lo >= 0 && n_words >= 0 && word_lo % 4 == 0 && n_words % 4 == 0, "pull_rows: word range must be 16-byte aligned");
+  if (N == 0 || n_words == 0) return SOLA_OK;
+  SOLA_REQUIRE(row_ptrs && dst && aligned16(dst), "pull_rows: null / misaligned pointer");
+  SOLA_REQUIRE(N <= 65535, "pull_rows: too many rows");
+  const long long n_vec = n_words / 4;
+  long long bx = (n_vec + 256 * 4 - 1) / (256 * 4);
+  const long long cap = ((long long)num_sms() * 8 + N - 1) / N;         // ~8 CTAs per SM over the whole grid
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)N);
+  sola::pull_rows_kernel<<<grid, 256, 0, stream>>>(row_ptrs, word_lo, n_vec, reinterpret_cast<uint4*>(dst));
+  return check_launch("pull_rows kernel");
 }
 
 int sola_pair_iou_gather(const uint32_t* tracks, const uint32_t* prompts, const int* frame_idx, int N, int P, int T,

@@ -310,6 +310,16 @@ def pairwise_inter_matrix(tracks: PackedMasks) -> torch.Tensor:
     return inter
 
 
+def pairwise_inter_matrix_words(w: torch.Tensor) -> torch.Tensor:
+    """(N, words) int32 rows of packed bits (any slice of the word axis of N tracks) -> int64 (N, N) intersection counts."""
+    assert w.dim() == 2 and w.dtype == torch.int32 and w.is_cuda and w.is_contiguous()
+    N = int(w.shape[0])
+    inter = torch.empty((N, N), dtype=torch.int64, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.call("sola_pair_iou_st", w.data_ptr(), N, max(int(w.shape[1]), 1), inter.data_ptr(), None, _stream(w))
+    return inter
+
+
 def pairwise_inter_matrix_part(tracks: PackedMasks, part: int, n_parts: int) -> torch.Tensor:
     """This part's share of the N x N intersection matrix (pair tiles part, part + n_parts, ...; zeros elsewhere)."""
     w = tracks.words.contiguous()
@@ -318,6 +328,36 @@ def pairwise_inter_matrix_part(tracks: PackedMasks, part: int, n_parts: int) -> 
     inter = torch.empty((N, N), dtype=torch.int64, device=w.device)
     with torch.cuda.device(w.device):
         _lib.call("sola_pair_iou_st_part", w.data_ptr(), N, words, int(part), int(n_parts), inter.data_ptr(), _stream(w))
+    return inter
+
+
+def pairwise_inter_matrix_rows(row_ptrs: torch.Tensor, words_per_track: int, part: int = 0, n_parts: int = 1) -> torch.Tensor:
+    """N x N intersection share from a device int64 table of per-track plane pointers (tracks may live on peer GPUs)."""
+    assert row_ptrs.dtype == torch.int64 and row_ptrs.is_cuda and row_ptrs.is_contiguous()
+    N = int(row_ptrs.numel())
+    inter = torch.empty((N, N), dtype=torch.int64, device=row_ptrs.device)
+    with torch.cuda.device(row_ptrs.device):
+        _lib.call("sola_pair_iou_st_rows", row_ptrs.data_ptr(), N, int(words_per_track), int(part), int(n_parts), inter.data_ptr(), _stream(row_ptrs))
+    return inter
+
+
+def pull_rows(row_ptrs: torch.Tensor, word_lo: int, n_words: int, out: torch.Tensor) -> torch.Tensor:
+    """out (N, n_words) int32 <- words [word_lo, word_lo + n_words) of every row of the pointer table (peer rows: over NVLink)."""
+    assert row_ptrs.dtype == torch.int64 and row_ptrs.is_cuda and row_ptrs.is_contiguous()
+    N = int(row_ptrs.numel())
+    assert out.dtype == torch.int32 and out.is_contiguous() and out.numel() == N * n_words and out.device == row_ptrs.device
+    with torch.cuda.device(out.device):
+        _lib.call("sola_pull_rows", row_ptrs.data_ptr(), N, int(word_lo), int(n_words), out.data_ptr(), _stream(out))
+    return out
+
+
+def pairwise_inter_accumulate(w: torch.Tensor, inter: torch.Tensor) -> torch.Tensor:
+    """inter (N, N) int64 += intersections over the (N, words) int32 rows `w` (a chunk of the word axis)."""
+    assert w.dim() == 2 and w.dtype == torch.int32 and w.is_cuda and w.is_contiguous()
+    N = int(w.shape[0])
+    assert inter.shape == (N, N) and inter.dtype == torch.int64 and inter.is_contiguous() and inter.device == w.device
+    with torch.cuda.device(w.device):
+        _lib.call("sola_pair_iou_st_accumulate", w.data_ptr(), N, int(w.shape[1]), inter.data_ptr(), _stream(w))
     return inter
 
 

@@ -69,21 +69,46 @@ def allreduce_jf(sum_J: float, sum_F: float, sum_JF: float, n_units: int, int_to
             "int_totals": i[1:].numpy().copy()}
 
 
-def pairwise_inter_matrix_sharded(local_tracks, group=None) -> torch.Tensor:
+def word_slices(words: int, world: int, align: int = 32) -> List[Tuple[int, int]]:
+    """Partition of the word axis used by every K-split path (host mirror of sola_pair_iou_st_rows): rank r owns the 32-word
+    stages [stages*r/world, stages*(r+1)/world), i.e. words [32*lo, min(32*hi, words))."""
+    stages = (words + align - 1) // align
+    out = []
+    for r in range(world):
+        lo, hi = stages * r // world, stages * (r + 1) // world
+        out.append((min(lo * align, words), min(hi * align, words)))
+    return out
+
+
+def pairwise_inter_matrix_sharded(local_tracks, group=None, split: str = "words") -> torch.Tensor:
     """BASELINE config 5 (one video with more candidate tracks than one GPU should binarise): every rank holds the packed
-    planes of ITS tracks (n_local, T, H, Wp) — equal n_local on every rank.  The path has a real exchange step here:
-      1. NCCL all-gather of the packed tracks (1/32 of the mask bytes; 13.3 GB in total for 256 x 200 x 1080p),
-      2. each rank computes its share of the 64 x 64 pair tiles of the upper triangle (sola_pair_iou_st_part),
+    planes of ITS tracks (n_local, T, H, Wp) — equal n_local on every rank.  The path has a real exchange step here.
+    split="words" (default): intersections are sums over words, so the WORD axis is partitioned —
+      1. NCCL all-to-all: rank r receives words [lo_r, hi_r) of every track (each rank moves 1/world of an all-gather's bytes),
+      2. each rank computes the full N x N matrix over its slice (sola_pair_iou_st; balanced for any N),
       3. one all-reduce(SUM) of the int64 N x N matrix (512 KB at N = 256).
-    Returns the full symmetric matrix on every rank; integer sums, so the result is identical for any world size."""
+    split="tiles": all-gather every track (13.3 GB for 256 x 200 x 1080p native planes), then 64 x 64 pair tiles dealt round-robin.
+    Returns the full symmetric matrix on every rank; integer sums, so the result is identical for any world size and split.
+    PeerPlanes (below) is the fused version of split="words": no NCCL exchange, the K2 kernel reads the peers over NVLink."""
     from . import packed as P
     w = local_tracks.words.contiguous()
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return P.pairwise_inter_matrix(local_tracks)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    full = torch.empty((world * w.shape[0], *w.shape[1:]), dtype=w.dtype, device=w.device)
-    dist.all_gather_into_tensor(full, w, group=group)
-    inter = P.pairwise_inter_matrix_part(P.PackedMasks(full, local_tracks.H, local_tracks.W), rank, world)
+    if split == "words":
+        n_local = int(w.shape[0])
+        flat = w.view(n_local, -1)
+        sl = word_slices(int(flat.shape[1]), world)
+        send = [flat[:, lo:hi].contiguous() for lo, hi in sl]
+        mine = sl[rank][1] - sl[rank][0]
+        recv = torch.empty((world, n_local, mine), dtype=w.dtype, device=w.device)
+        dist.all_to_all(list(recv.unbind(0)), send, group=group)
+        inter = P.pairwise_inter_matrix_words(recv.view(world * n_local, mine)) if mine > 0 else \
+            torch.zeros((world * n_local, world * n_local), dtype=torch.int64, device=w.device)
+    else:
+        full = torch.empty((world * w.shape[0], *w.shape[1:]), dtype=w.dtype, device=w.device)
+        dist.all_gather_into_tensor(full, w, group=group)
+        inter = P.pairwise_inter_matrix_part(P.PackedMasks(full, local_tracks.H, local_tracks.W), rank, world)
     dist.all_reduce(inter, op=dist.ReduceOp.SUM, group=group)
     return inter
 
@@ -97,3 +122,67 @@ def pair_tile_owner(n_tracks: int, world: int, tile: int = 64):
             out.append((ti, tj, idx % world))
             idx += 1
     return out
+
+
+class PeerPlanes:
+    """Packed planes of this rank's tracks in NVLink-mapped symmetric memory (torch.distributed._symmetric_memory), so that every
+    GPU can read every rank's tracks directly and the NCCL exchange disappears.  The word axis is partitioned over the ranks
+    (word_slices): each rank needs 1/world of every track.  Two ways to consume the peers' memory:
+      mode="pull"   (default) the rank's slice is walked in chunks; `sola_pull_rows` copies chunk c+1 of all N tracks out of the
+                    peers' memory (each remote word crosses NVLink exactly once) on a side stream while the TMA-staged K2 kernel
+                    reduces chunk c on the main stream (`sola_pair_iou_st_accumulate`) — transfer and math overlap chunk by chunk;
+      mode="direct" one K2 launch whose stage loads (cp.async) read the peers' rows in place (`sola_pair_iou_st_rows`); every row
+                    tile is re-read once per pair tile it belongs to, so NVLink carries ~N/128 times the bytes of "pull".
+
+        peers = PeerPlanes(n_local, T, h, w, device)             # collective: allocates + rendezvous once
+        S.binarize_pack_resize(logits, resized_out=peers.local)  # producers write straight into the shared buffer
+        inter = peers.pairwise_inter_matrix()                    # barrier, exchange fused with K2 over this rank's slice, all-reduce
+    """
+
+    def __init__(self, n_local: int, T: int, H: int, W: int, device, group=None, n_chunks: int = 4):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import packed as P
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        Wp = (W + 31) // 32
+        self.buf = symm_mem.empty((n_local, T, H, Wp), dtype=torch.int32, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        self.local = P.PackedMasks(self.buf, H, W)
+        self.words = T * H * Wp
+        self.n_tracks = n_local * self.world
+        assert self.words % 4 == 0, "each track's planes must be a multiple of 16 bytes"
+        ptrs = [int(self.handle.buffer_ptrs[r]) + i * self.words * 4 for r in range(self.world) for i in range(n_local)]
+        self.row_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        lo, hi = word_slices(self.words, self.world)[self.rank]
+        self.chunks = [(lo + a, lo + b) for a, b in word_slices(hi - lo, max(1, n_chunks)) if b > a]
+        cw = max([b - a for a, b in self.chunks], default=0)
+        self.scratch = [torch.empty((self.n_tracks, cw), dtype=torch.int32, device=device) for _ in range(2)] if cw else []
+        self.side = torch.cuda.Stream(device=device)
+
+    def pairwise_inter_matrix(self, mode: str = "pull") -> torch.Tensor:
+        from . import packed as P
+        self.handle.barrier()                 # every rank's planes are written (stream-ordered device barrier over the signal pads)
+        if mode == "direct":
+            inter = P.pairwise_inter_matrix_rows(self.row_ptrs, self.words, self.rank, self.world)
+        else:
+            N = self.n_tracks
+            inter = torch.zeros((N, N), dtype=torch.int64, device=self.row_ptrs.device)
+            main = torch.cuda.current_stream(self.row_ptrs.device)
+            self.side.wait_stream(main)
+            freed = [None, None]              # event: the K2 launch that last read scratch[k] has finished
+            for c, (a, b) in enumerate(self.chunks):
+                k = c & 1
+                view = self.scratch[k].view(-1)[: N * (b - a)].view(N, b - a)
+                with torch.cuda.stream(self.side):
+                    if freed[k] is not None:
+                        self.side.wait_event(freed[k])
+                    P.pull_rows(self.row_ptrs, a, b - a, view)
+                    pulled = torch.cuda.Event()
+                    pulled.record(self.side)
+                main.wait_event(pulled)
+                P.pairwise_inter_accumulate(view, inter)
+                freed[k] = torch.cuda.Event()
+                freed[k].record(main)
+        dist.all_reduce(inter, op=dist.ReduceOp.SUM, group=self.group)
+        self.handle.barrier()                 # nobody overwrites its planes while a peer may still be reading them
+        return inter

@@ -168,6 +168,33 @@ def test_pairwise_matrix_parts_sum_to_full(N, parts):
     np.testing.assert_array_equal(full, _np_inter(m))
 
 
+@pytest.mark.parametrize("N,parts", [(70, 1), (96, 4), (33, 2)])
+def test_pairwise_matrix_from_row_pointer_table(N, parts):
+    """sola_pair_iou_st_rows (the fused exchange + K2 entry): tracks addressed through a table of row pointers — here rows
+    scattered over several separate allocations in shuffled order, as the peers' buffers are on a multi-GPU box."""
+    import sola_b200 as S
+    rng = np.random.default_rng(N + 7)
+    m = rng.random((N, 3, 20, 64)) > 0.6
+    m[5] = False
+    packed = S.pack_masks(m)
+    words = packed.words[0].numel()
+    assert words % 4 == 0
+    chunks = [packed.words[i:i + 9].clone() for i in range(0, N, 9)]            # separate device allocations
+    ptrs = torch.tensor([chunks[i // 9].data_ptr() + (i % 9) * words * 4 for i in range(N)], dtype=torch.int64, device="cuda")
+    shares = [S.packed.pairwise_inter_matrix_rows(ptrs, words, p, parts).cpu().numpy() for p in range(parts)]
+    np.testing.assert_array_equal(sum(shares), _np_inter(m))
+    np.testing.assert_array_equal(sum(shares), S.pairwise_inter_matrix(packed).cpu().numpy())
+    # the pipelined form: pull word chunks through the pointer table, accumulate chunk by chunk (sharding.PeerPlanes mode="pull")
+    from sola_b200 import sharding
+    inter = torch.zeros((N, N), dtype=torch.int64, device="cuda")
+    for lo, hi in sharding.word_slices(words, 3):
+        chunk = torch.empty((N, hi - lo), dtype=torch.int32, device="cuda")
+        S.packed.pull_rows(ptrs, lo, hi - lo, chunk)
+        assert torch.equal(chunk, packed.words.view(N, -1)[:, lo:hi])
+        S.packed.pairwise_inter_accumulate(chunk, inter)
+    np.testing.assert_array_equal(inter.cpu().numpy(), _np_inter(m))
+
+
 def test_survey_named_entry_points(golden):
     """pairwise_iou_matrix / gathered_iou / greedy_filter / jf_batch compose to the same results."""
     import sola_b200 as S

@@ -127,3 +127,17 @@ def test_pair_tile_partition_covers_upper_triangle_once():
         assert all(a <= b for a, b, _ in tiles) and all(0 <= r < world for _, _, r in tiles)
         counts = np.bincount([r for _, _, r in tiles], minlength=world)
         assert counts.max() - counts.min() <= 1                                   # round-robin: balanced to within one tile
+
+
+def test_word_slices_partition_the_word_axis():
+    """K-split of BASELINE config 5: contiguous, 32-word aligned, covers [0, words) exactly once for any world size."""
+    from sola_b200 import sharding
+    for words in (4, 32, 100, 3240000, 12345676):
+        for world in (1, 2, 3, 8):
+            sl = sharding.word_slices(words, world)
+            assert len(sl) == world and sl[0][0] == 0 and sl[-1][1] == words
+            for (a, b), (c, d) in zip(sl, sl[1:]):
+                assert b == c and a <= b
+            assert all(a % 32 == 0 for a, _ in sl)
+            sizes = [b - a for a, b in sl]
+            assert max(sizes) - min(sizes) <= 32 or words < 32 * world
