@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--streams", type=int, default=1, choices=[1, 2], help="videos in flight on separate CUDA streams")
+    ap.add_argument("--tail-priority", action="store_true",
+                    help="run everything after the fused K1+R1 (R2, K2 gather, K2 N x N, read-backs) on a HIGH-priority side stream, so the "
+                         "INT-bound K2 of video k shares the SMs with the HBM-bound K1+R1 of video k+1")
     ap.add_argument("--no-fuse", action="store_true", help="run K1 and R1 as two kernels instead of the fused one")
     ap.add_argument("--st-native", action="store_true",
                     help="N x N spatio-temporal IoU on the native 720x1280 planes instead of the 540x960 resized masklets the "
@@ -121,9 +124,10 @@ class ClockSampler:
 # the step (product path)
 # ---------------------------------------------------------------------------------------------------------------
 class Workload:
-    def __init__(self, device, seed, n_tracks, n_frames, n_streams=1, fused=True, st_native=False):
+    def __init__(self, device, seed, n_tracks, n_frames, n_streams=1, fused=True, st_native=False, tail_priority=False):
         import sola_b200 as S
         self.n_streams = n_streams
+        self.tail_stream = torch.cuda.Stream(device=device, priority=-1) if tail_priority else None
         self.fused = fused
         self.st_native = st_native
         from sola_b200 import synth
@@ -148,8 +152,9 @@ class Workload:
         self.jobs = [mk(), mk()]
         # one stream per in-flight video: the HBM-bound K1 of video k+1 overlaps the ALU/XU-bound R1 + K2 of video k
         self.streams = [torch.cuda.Stream(device=self.device) for _ in self.jobs] if self.n_streams > 1 else [None, None]
-        self.packed_slots = [self.packed, self.S.PackedMasks.empty((self.N, self.T), self.H, self.W, self.device)] if self.n_streams > 1 else [self.packed, self.packed]
-        self.counts_slots = [self.counts, torch.empty_like(self.counts)] if self.n_streams > 1 else [self.counts, self.counts]
+        two = self.n_streams > 1 or self.tail_stream is not None              # two videos in flight need two sets of output buffers
+        self.packed_slots = [self.packed, self.S.PackedMasks.empty((self.N, self.T), self.H, self.W, self.device)] if two else [self.packed, self.packed]
+        self.counts_slots = [self.counts, torch.empty_like(self.counts)] if two else [self.counts, self.counts]
 
     def enqueue(self, slot, logits=None, prompt_masks=None, record_k1=False):
         """Device half of one step (no synchronisation): K1, R1, R2, K2-gather, K2 N x N, async read-back."""
@@ -178,6 +183,13 @@ class Workload:
             self.k1_events.append((e0, e1))
         if not self.fused:
             resized = S.resize_bilinear_bin(packed)                                                                        # R1
+        if self.tail_stream is not None:
+            done = torch.cuda.Event()
+            done.record()
+            with torch.cuda.stream(self.tail_stream):
+                self.tail_stream.wait_event(done)
+                job._enqueue_tail(packed, resized, counts, prompt_masks)
+            return
         job._enqueue_tail(packed, resized, counts, prompt_masks)                                                           # R2, K2 gather, K2 N x N, read-backs
 
     def finish(self, slot):
@@ -330,8 +342,12 @@ def main():
         dist.init_process_group(backend="nccl", device_id=device)
     import sola_b200 as S
     S.load_library()
+    from sola_b200 import sharding
+    # N > 1: one process per GPU, each bound to its GPU's local CPUs before any pinned allocation (the N = 1 run keeps every core:
+    # its cpu_baseline leg must see the whole host)
+    cpus = sharding.bind_to_gpu_cpus(local_rank) if (world > 1 and not os.environ.get("SOLA_BENCH_NO_AFFINITY")) else []
 
-    w = Workload(device, seed=1234 + 2 + 1000 * rank, n_tracks=n_tracks, n_frames=n_frames, n_streams=args.streams, fused=not args.no_fuse, st_native=args.st_native)
+    w = Workload(device, seed=1234 + 2 + 1000 * rank, n_tracks=n_tracks, n_frames=n_frames, n_streams=args.streams, fused=not args.no_fuse, st_native=args.st_native, tail_priority=args.tail_priority)
     w.make_jobs()
     torch.cuda.synchronize()
 
@@ -429,7 +445,7 @@ def main():
             h2d = w.logits.numel() * 4 + host_prompts.numel()
             d2h = int(3 * n_tracks * n_frames * 4 + n_tracks * n_tracks * 8 + 3 * n_tracks * n_tracks * 4)
             e2e = {"value": world * n_tracks * n_frames * n_e2e / (float(te.item()) * 1e-3), "unit": UNIT,
-                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h, "steps": n_e2e,
+                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h, "steps": n_e2e, "host_cpus_bound": len(cpus),
                    "note": "pinned host fp32 logits + uint8 prompt masks copied H2D every step (chunked, overlapped with K1); "
                            "stability counts, IoU count matrices and the N x N intersection matrix read back"}
             del host_chunks, dev_logits

@@ -89,7 +89,7 @@ pack_flat_kernel(const T* __restrict__ in, int frame_px, int ctas_per_frame, Thr
 
   __shared__ int red[3][K1_WARPS];
   n_mid = warp_sum(n_mid);
-  if (MODE == MODE_THRESH3) { n_hi = warp_sum(n_hi); n_lo = warp_sum(n_lo); }
+  if (MODE == MODE_THRESH3) { n_hi = warp_sum(stab_decode<T>(n_hi)); n_lo = warp_sum(stab_decode<T>(n_lo)); }
   if (lane == 0) { red[0][warp] = n_mid; red[1][warp] = n_hi; red[2][warp] = n_lo; }
   __syncthreads();
   if (threadIdx.x < 3) {

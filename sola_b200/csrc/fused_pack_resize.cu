@@ -65,7 +65,8 @@ fused_pack_resize_kernel(const T* __restrict__ logits, int n_frames, int frames_
   for (int f = f_begin; f < f_end; ++f) {
     const T* src = logits + ((long long)f * H + tlo) * W;
     uint32_t* dst = packed ? packed + f * FW + (long long)tlo * Wp : nullptr;
-    int n_mid = 0, n_hi = 0, n_lo = 0;
+    int n_mid = 0, n_hi = 0, n_lo = 0;      // n_hi / n_lo in chunk_extract3's per-dtype encoding (stab_decode)
+    int b_hi = 0, b_lo = 0;                 // plain counts from the ownership-boundary chunks
 
     auto do_chunk = [&](int c, auto full_tag) {
       constexpr bool FULLCHUNK = decltype(full_tag)::value;
@@ -97,7 +98,7 @@ fused_pack_resize_kernel(const T* __restrict__ logits, int n_frames, int frames_
 #pragma unroll
         for (int j = 0; j < L; ++j)
           if (w0 + E * j + lane / L < owned_words) own |= slot << (E * j);
-        n_mid += __popc(xm & own); n_hi += __popc(xh & own); n_lo += __popc(xl & own);
+        n_mid += __popc(xm & own); b_hi += __popc(xh & own); b_lo += __popc(xl & own);
       }
       const uint32_t word = transpose_slots<E>(xm, lane);
       const int wi = w0 + out_word_in_chunk;
@@ -112,7 +113,7 @@ fused_pack_resize_kernel(const T* __restrict__ logits, int n_frames, int frames_
 
     const int n_area = resize_tile_from_smem(tile, Wp, tb, nrows, ow, resized + f * oFW + (long long)oy0 * owp);
 
-    n_mid = warp_sum(n_mid); n_hi = warp_sum(n_hi); n_lo = warp_sum(n_lo);
+    n_mid = warp_sum(n_mid); n_hi = warp_sum(stab_decode<T>(n_hi) + b_hi); n_lo = warp_sum(stab_decode<T>(n_lo) + b_lo);
     const int s_area = warp_sum(n_area);
     if (lane == 0) { red[0][warp] = n_mid; red[1][warp] = n_hi; red[2][warp] = n_lo; red[3][warp] = s_area; }
     __syncthreads();                                                 // also: everyone finished reading the tile
@@ -190,7 +191,7 @@ band_pack_generic_kernel(const T* __restrict__ logits, int n_frames, int frames_
     const int n_chunks = (n_flat_px + FU_CHUNK_PX - 1) / FU_CHUNK_PX;
     const int cnt_lo_px = off0, cnt_hi_px = off0 + owned_rows * W;             // pixels whose counts belong to this band
     const T* src = logits + s0;
-    int n_mid = 0, n_hi = 0, n_lo = 0;
+    int n_mid = 0, n_hi = 0, n_lo = 0, b_hi = 0, b_lo = 0;      // as in the fused kernel: encoded / plain stability counts
     for (int c = warp; c < n_chunks; c += FU_WARPS) {
       const int px0 = c * FU_CHUNK_PX;
       uint4 raw[L];
@@ -221,7 +222,7 @@ band_pack_generic_kernel(const T* __restrict__ logits, int n_frames, int frames_
           const int a = min(max(cnt_lo_px - p, 0), E), b = min(max(cnt_hi_px - p, 0), E);
           if (b > a) own |= ((b - a >= 32 ? 0xffffffffu : ((1u << (b - a)) - 1u)) << a) << (E * j);
         }
-        n_mid += __popc(xm & own); n_hi += __popc(xh & own); n_lo += __popc(xl & own);
+        n_mid += __popc(xm & own); b_hi += __popc(xh & own); b_lo += __popc(xl & own);
       }
       const uint32_t word = transpose_slots<E>(xm, lane);
       const int k = (px0 >> 5) + out_word_in_chunk;
@@ -246,7 +247,7 @@ band_pack_generic_kernel(const T* __restrict__ logits, int n_frames, int frames_
       __syncthreads();
       n_area = resize_tile_from_smem(tile, Wp, tb, nrows, ow, resized + f * oFW + (long long)oy0 * owp);
     }
-    n_mid = warp_sum(n_mid); n_hi = warp_sum(n_hi); n_lo = warp_sum(n_lo);
+    n_mid = warp_sum(n_mid); n_hi = warp_sum(stab_decode<T>(n_hi) + b_hi); n_lo = warp_sum(stab_decode<T>(n_lo) + b_lo);
     const int s_area = RESIZE ? warp_sum(n_area) : 0;
     if (lane == 0) { red[0][warp] = n_mid; red[1][warp] = n_hi; red[2][warp] = n_lo; red[3][warp] = s_area; }
     __syncthreads();                                                           // also: flat / tile free for the next frame

@@ -11,7 +11,7 @@ enum PackMode { MODE_THRESH3 = 0, MODE_THRESH1 = 1, MODE_NONZERO = 2 };
 
 struct Thresholds {
   float mid, hi, lo;
-  uint32_t hi_bf2, lo_bf2;      // floor-to-bf16 of hi / lo, replicated in both halves (bf16 count path, see vec_count2)
+  uint32_t hi_bf2, lo_bf2, mid_bf2;   // floor-to-bf16 of hi / lo / mid, replicated in both halves (bf16 packed-compare path)
 };
 
 // largest bf16 value <= t, as its 16 bits: for a bf16 x, (x > t) == (x > bf16_floor(t)), so the packed bf16 compare is exact
@@ -33,6 +33,7 @@ inline Thresholds make_thresholds(double thr, double off) {
   t.lo = (float)(thr - off) + 0.0f;
   t.hi_bf2 = bf16_floor_bits(t.hi) * 0x00010001u;
   t.lo_bf2 = bf16_floor_bits(t.lo) * 0x00010001u;
+  t.mid_bf2 = bf16_floor_bits(t.mid) * 0x00010001u;
   return t;
 }
 
@@ -164,49 +165,60 @@ __device__ __forceinline__ uint32_t transpose_slots(uint32_t x, int lane) {
   return x;
 }
 
-// ---- bf16 count path ---------------------------------------------------------------------------------------------------
-// For the two stability thresholds only the COUNT matters.  With bf16 logits a 32-bit word holds two elements, and the packed
-// compare `set.gt.bf16x2` + packed add run on the fma/half pipe: 2 instructions per PAIR per threshold and no alu-pipe work,
-// instead of unpack + FADD + funnel shift per ELEMENT.  Sums stay exact (<= 32 per half per chunk, bf16 is exact to 256).
-struct PairCounts {
-  __nv_bfloat162 hi, lo;
-  __device__ __forceinline__ void reset() { hi = __float2bfloat162_rn(0.f); lo = hi; }
-  __device__ __forceinline__ int total_hi() const { return (int)__low2float(hi) + (int)__high2float(hi); }
-  __device__ __forceinline__ int total_lo() const { return (int)__low2float(lo) + (int)__high2float(lo); }
-};
-
-__device__ __forceinline__ void vec_count2(const uint4& raw, const Thresholds& th, PairCounts& pc) {
-  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-  const __nv_bfloat162 t_hi = *reinterpret_cast<const __nv_bfloat162*>(&th.hi_bf2);
-  const __nv_bfloat162 t_lo = *reinterpret_cast<const __nv_bfloat162*>(&th.lo_bf2);
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&w[c]);
-    pc.hi = __hadd2(pc.hi, __hgt2(x2, t_hi));          // 1.0 / 0.0 per half; NaN -> 0.0 (ordered compare)
-    pc.lo = __hadd2(pc.lo, __hgt2(x2, t_lo));
-  }
+// ---- bf16 packed-compare path ---------------------------------------------------------------------------------------------
+// With bf16 logits a 32-bit word holds two elements and `set.gt.bf16x2` with a bit-mask result (SASS HSET2.BF16_V2.BM) compares both
+// halves in ONE fma/half-pipe instruction: 0xFFFF per half that passes, NaN -> 0 (ordered compare), -0 > +0 false.  The
+// thresholds are floored to bf16 first, which is exact: for a bf16 x, (x > t) == (x > bf16_floor(t)).
+//   * stability counts: the masks are SUBTRACTED from a 32-bit accumulator, two masks per IADD3.  Subtracting 0x0000FFFF adds
+//     1 - 65536 and subtracting 0xFFFF0000 adds 65536 (mod 2^32), so after a low-half hits and b high-half hits
+//     acc = a + 65536 * (b - a)  — decoded once per frame by stab_decode (a < 65536 per thread per frame by a wide margin).
+//     0.5 HSET2 + 0.25 IADD3 per element per threshold instead of unpack + FADD + funnel shift per element.
+//   * stored plane: PRMT gathers one byte of each of four masks (4 elements -> bytes 0x00 / 0xFF), two LOP3 keep bit k of byte k
+//     (elements 0-3) and bit 4+k of byte k (elements 4-7), and a multiply by 0x01010101 sums the four bytes into the top byte =
+//     the 8 predicate bits in element order, which one funnel shift pushes into the private word.
+__device__ __forceinline__ uint32_t gt2_mask(uint32_t x2, uint32_t t2) {
+  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&x2), *reinterpret_cast<const __nv_bfloat162*>(&t2));
 }
 
-// One chunk's predicate extraction.  Returns the stored plane's private word in xm; counts either as bit words (xh, xl — needed
-// when a range mask must be applied) or, for bf16 with WANT_BITS == false, directly as integers in n_hi / n_lo.
+__device__ __forceinline__ uint32_t vec_bits8_bf16(const uint4& raw, uint32_t t2) {
+  const uint32_t m0 = gt2_mask(raw.x, t2), m1 = gt2_mask(raw.y, t2), m2 = gt2_mask(raw.z, t2), m3 = gt2_mask(raw.w, t2);
+  const uint32_t p_lo = __byte_perm(m0, m1, 0x6420);         // bytes: elements 0,1,2,3 as 0x00 / 0xFF
+  const uint32_t p_hi = __byte_perm(m2, m3, 0x6420);         //        elements 4,5,6,7
+  const uint32_t t = (p_lo & 0x08040201u) | (p_hi & 0x80402010u);
+  return t * 0x01010101u;                                    // top byte = predicate bits of elements 0..7
+}
+
+__device__ __forceinline__ void vec_count2(const uint4& raw, const Thresholds& th, int& acc_hi, int& acc_lo) {
+  acc_hi = acc_hi - (int)gt2_mask(raw.x, th.hi_bf2) - (int)gt2_mask(raw.y, th.hi_bf2);
+  acc_hi = acc_hi - (int)gt2_mask(raw.z, th.hi_bf2) - (int)gt2_mask(raw.w, th.hi_bf2);
+  acc_lo = acc_lo - (int)gt2_mask(raw.x, th.lo_bf2) - (int)gt2_mask(raw.y, th.lo_bf2);
+  acc_lo = acc_lo - (int)gt2_mask(raw.z, th.lo_bf2) - (int)gt2_mask(raw.w, th.lo_bf2);
+}
+
+// Stability accumulators as chunk_extract3<.., WANT_BITS = false> leaves them: plain counts for fp32, the packed form above for bf16.
+template <typename T> __device__ __forceinline__ int stab_decode(int acc) { return acc; }
+template <> __device__ __forceinline__ int stab_decode<__nv_bfloat16>(int acc) {
+  const int a = acc & 0xffff;
+  return 2 * a + ((acc - a) >> 16);
+}
+
+// One chunk's predicate extraction.  Returns the stored plane's private word in xm; the two stability thresholds either as bit
+// words (xh, xl — WANT_BITS, needed when a range mask must be applied) or accumulated into acc_hi / acc_lo in the per-dtype
+// encoding that stab_decode<T> undoes (never mix plain counts into those accumulators).
 template <typename T, int L, bool WANT_BITS>
 __device__ __forceinline__ void chunk_extract3(const uint4 (&raw)[L], const Thresholds& th, uint32_t& xm, uint32_t& xh, uint32_t& xl,
-                                               int& n_hi, int& n_lo) {
+                                               int& acc_hi, int& acc_lo) {
   xm = xh = xl = 0;
   if (sizeof(T) == 2 && !WANT_BITS) {
-    PairCounts pc;
-    pc.reset();
 #pragma unroll
     for (int j = L - 1; j >= 0; --j) {
-      vec_push<MODE_THRESH1>(raw[j], th, T(), xm, xh, xl);
-      vec_count2(raw[j], th, pc);
+      xm = __funnelshift_l(vec_bits8_bf16(raw[j], th.mid_bf2), xm, 8);
+      vec_count2(raw[j], th, acc_hi, acc_lo);
     }
-    n_hi += pc.total_hi();
-    n_lo += pc.total_lo();
   } else {
 #pragma unroll
     for (int j = L - 1; j >= 0; --j) vec_push<MODE_THRESH3>(raw[j], th, T(), xm, xh, xl);
-    if (!WANT_BITS) { n_hi += __popc(xh); n_lo += __popc(xl); }
+    if (!WANT_BITS) { acc_hi += __popc(xh); acc_lo += __popc(xl); }
   }
 }
 

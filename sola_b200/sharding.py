@@ -37,6 +37,28 @@ def shard_balanced(costs: Sequence[float], rank: int, world: int) -> List[int]:
     return sorted(mine)
 
 
+def bind_to_gpu_cpus(device_index: int) -> List[int]:
+    """Pin this process to the CPUs NVML reports as local to the GPU (same NUMA node / PCIe root), intersected with the CPUs the
+    process may use.  One process per GPU: pinned host staging buffers allocated afterwards are first-touched on the GPU's own
+    node, so H2D copies of several ranks do not queue on one socket's memory controllers.  Returns the CPU list now in force
+    ([] = left unchanged: NVML unavailable, or no overlap with the allowed set)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        local = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        pick = sorted(local & allowed)
+        if not pick:
+            return []
+        os.sched_setaffinity(0, pick)
+        return pick
+    except Exception:
+        return []
+
+
 def init_process_group_from_env(device: torch.device | None = None) -> Tuple[int, int]:
     """torchrun-style init: NCCL when a CUDA device is given, gloo otherwise."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
