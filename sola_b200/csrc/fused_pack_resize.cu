@@ -56,7 +56,7 @@ fused_pack_resize_kernel(const T* __restrict__ logits, int n_frames, int frames_
   const int owned_words = (own_end - tlo) * Wp;
   const int n_px = (yend - tlo + 1) * W;
   const int n_chunks = (n_px + FU_CHUNK_PX - 1) / FU_CHUNK_PX;
-  tb.build(oy0, tlo, H, W, oh, ow, sy, sx);
+  tb.build(oy0, tlo, H, W, oh, ow, sy, sx, Wp);
   const long long FW = (long long)H * Wp, oFW = (long long)oh * owp;
   const int out_word_in_chunk = E * (lane % L) + lane / L;
   const uint32_t slot = (E >= 32) ? 0xffffffffu : ((1u << E) - 1u);
@@ -169,7 +169,7 @@ band_pack_generic_kernel(const T* __restrict__ logits, int n_frames, int frames_
     tlo = band == 0 ? 0 : ylo;
     own_end = band == n_bands - 1 ? H : bilinear_axis(oy0 + R1_TR, sy, H).i0;
     yend = max(yhi, own_end - 1);
-    tb.build(oy0, tlo, H, W, oh, ow, sy, sx);
+    tb.build(oy0, tlo, H, W, oh, ow, sy, sx, Wp);
   } else {
     tlo = band * BAND_ROWS;
     own_end = min(H, tlo + BAND_ROWS);
@@ -296,7 +296,8 @@ static FusedPlan plan_fused(const void* base, long long n_frames, int H, int W, 
   }
   p.max_tile_rows = (int)rows;
   p.max_flat_words = (int)((rows * W + 2 * E + 31) / 32) + 2;
-  p.smem = (size_t)owp * 32 * sizeof(XParam) + R1_TR * sizeof(YParam) + (size_t)owp * sizeof(int4) + (size_t)rows * Wp * sizeof(uint32_t);
+  p.smem = (size_t)owp * 32 * sizeof(XParam) + R1_TR * sizeof(YParam) + (size_t)owp * sizeof(int4) + (size_t)rows * Wp * sizeof(uint32_t)
+           + 16;                                                         // phase A of R1 may read 2 (masked-out) words past the tile
   if (p.generic) p.smem += (size_t)p.max_flat_words * sizeof(uint32_t);
   if (p.smem > 160 * 1024) return p;
   int occ = 4;

@@ -42,24 +42,49 @@ __device__ __forceinline__ int popc4_and(const uint4& a, const uint4& b) {
 // against 64 for LOP3, so the plain AND+POPC+IADD loop is POPC-bound.  Per pair we keep bit-sliced counters `ones`, `twos`
 // and feed the four AND-ed words of a k-quad through three 3:2 compressors; only the weight-4 carry word is popcounted:
 //   4 AND + 6 LOP3 + 1 POPC per 4 words  (2.5 alu ops and 0.25 POPC per word instead of 1 and 1).
-// total = 4 * acc4 + 2 * popc(twos) + popc(ones) at the end — exactly the same integer.
-struct Csa { uint32_t ones, twos; int acc4; };
+// The compressors are written as explicit 3-input LOP3s (majority 0xE8, parity 0x96): left to itself the compiler fuses the ANDs
+// into a chain of half adders (a ^ (b & c), a & b & c, or) that costs 12 LOP3 per quad instead of 10.
+// A hybrid that sends a fixed subset of the k-quads of every stage (PLAIN) down the plain route — 4 AND + 4 POPC, adds on the fma
+// pipe — to put the idle POPC pipe to work was measured and is NOT faster (dense 64 x 80 x 540 x 960: 0.618 ms pure carry-save,
+// 0.639 / 0.652 ms with 2 / 3 plain quads of 8; profiles/r1_k2_variants.jsonl): at 2 CTAs x 8 warps per SM the loop is bound by
+// dependent-issue latency, not by either pipe.  The template stays for experiments (SOLA_K2_PLAIN=2|3); default is pure carry-save.
+// total = acc + 2 * popc(twos) + popc(ones) — exactly the same integer in every variant.
+struct Csa { uint32_t ones, twos; int acc; };
 
-__device__ __forceinline__ void csa32(uint32_t& carry, uint32_t& sum, uint32_t a, uint32_t b, uint32_t c) {
-  const uint32_t u = a ^ b;
-  carry = (a & b) | (u & c);
-  sum = u ^ c;
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
 }
 
 __device__ __forceinline__ void csa_quad(Csa& st, const uint4& a, const uint4& b) {
-  uint32_t t1, t2, f;
-  csa32(t1, st.ones, st.ones, a.x & b.x, a.y & b.y);
-  csa32(t2, st.ones, st.ones, a.z & b.z, a.w & b.w);
-  csa32(f, st.twos, st.twos, t1, t2);
-  st.acc4 += __popc(f);
+  const uint32_t x0 = a.x & b.x, x1 = a.y & b.y, x2 = a.z & b.z, x3 = a.w & b.w;
+  const uint32_t t1 = lop3_maj(st.ones, x0, x1), s1 = lop3_xor3(st.ones, x0, x1);
+  const uint32_t t2 = lop3_maj(s1, x2, x3);
+  st.ones = lop3_xor3(s1, x2, x3);
+  const uint32_t f = lop3_maj(st.twos, t1, t2);
+  st.twos = lop3_xor3(st.twos, t1, t2);
+  st.acc = __popc(f) * 4 + st.acc;
 }
 
-__device__ __forceinline__ int csa_total(const Csa& st) { return 4 * st.acc4 + 2 * __popc(st.twos) + __popc(st.ones); }
+__device__ __forceinline__ void plain_quad(Csa& st, const uint4& a, const uint4& b) {
+  st.acc += __popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w);
+}
+
+// PLAIN = k-quads of a stage (bit q set) that take the plain POPC route: 0 = none (default), 0x24 = quads 2 and 5 of the 8
+constexpr int K2_PLAIN_DEFAULT = 0x00;
+template <int PLAIN>
+__device__ __forceinline__ void acc_quad(Csa& st, const uint4& a, const uint4& b, int q /* compile-time after unrolling */) {
+  if ((PLAIN >> q) & 1) plain_quad(st, a, b);
+  else csa_quad(st, a, b);
+}
+
+__device__ __forceinline__ int csa_total(const Csa& st) { return st.acc + 2 * __popc(st.twos) + __popc(st.ones); }
 
 // tile list: (ti, tj) with ti <= tj, enumerated row-major over the upper triangle
 __device__ __forceinline__ void tile_from_index(int idx, int nt, int& ti, int& tj) {
@@ -126,7 +151,7 @@ __device__ __forceinline__ void st_tile_body(const uint32_t* __restrict__ packed
 #pragma unroll
         for (int rj = 0; rj < 4; ++rj) {
           if (DIAG && rj < ri) continue;               // mirror entry is produced by another (ri, rj)
-          csa_quad(acc[ri][rj], a[ri], b[rj]);
+          acc_quad<K2_PLAIN_DEFAULT>(acc[ri][rj], a[ri], b[rj], q);
         }
       }
     }
@@ -192,7 +217,7 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
 
 constexpr int TMA_BOX_BYTES = PT * STAGE_WORDS * 4;      // 64 rows x 128 B
 
-template <bool DIAG>
+template <bool DIAG, int PLAIN>
 __device__ __forceinline__ void st_tile_body_tma(const CUtensorMap* __restrict__ map, int N, int ti, int tj, long long s_begin,
                                                  long long s_end, unsigned char* smem, uint64_t* full,
                                                  unsigned long long* __restrict__ inter) {
@@ -236,7 +261,7 @@ __device__ __forceinline__ void st_tile_body_tma(const CUtensorMap* __restrict__
 #pragma unroll
         for (int rj = 0; rj < 4; ++rj) {
           if (DIAG && rj < ri) continue;
-          csa_quad(acc[ri][rj], a[ri], b[rj]);
+          acc_quad<PLAIN>(acc[ri][rj], a[ri], b[rj], q);
         }
       }
     }
@@ -256,6 +281,7 @@ __device__ __forceinline__ void st_tile_body_tma(const CUtensorMap* __restrict__
     }
 }
 
+template <int PLAIN>
 __global__ void __launch_bounds__(ST_THREADS)
 pair_iou_st_tma_kernel(const __grid_constant__ CUtensorMap map, int N, long long words, int nt, int n_tiles, int splits,
                        int tile_first, int tile_step, unsigned long long* __restrict__ inter) {
@@ -273,8 +299,8 @@ pair_iou_st_tma_kernel(const __grid_constant__ CUtensorMap map, int N, long long
   const long long s_begin = stages * split / splits, s_end = stages * (split + 1) / splits;
   // round the dynamic-smem base up to 1024 B by OFFSET (a pointer cast would demote the tile reads to generic loads)
   unsigned char* boxes = smem_tma + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_tma) & 1023u)) & 1023u);
-  if (ti == tj) st_tile_body_tma<true>(&map, N, ti, tj, s_begin, s_end, boxes, full, inter);
-  else st_tile_body_tma<false>(&map, N, ti, tj, s_begin, s_end, boxes, full, inter);
+  if (ti == tj) st_tile_body_tma<true, PLAIN>(&map, N, ti, tj, s_begin, s_end, boxes, full, inter);
+  else st_tile_body_tma<false, PLAIN>(&map, N, ti, tj, s_begin, s_end, boxes, full, inter);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -428,9 +454,17 @@ static int launch_pair_iou_st(const uint32_t* packed, int N, long long words_per
       CUtensorMap map;
       if (make_track_map(packed, N, words_per_track, &map)) {
         // TMA-staged tiles (UTMALDG): one elected thread per stage instead of 4 cp.async per thread
-        SOLA_CUDA(cudaFuncSetAttribute(pair_iou_st_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
-        pair_iou_st_tma_kernel<<<(unsigned)(splits * n_tiles), ST_THREADS, smem + 1024, stream>>>(
-            map, N, words_per_track, nt, n_tiles, (int)splits, part, n_parts, reinterpret_cast<unsigned long long*>(inter_out));
+        // SOLA_K2_PLAIN = 0 (default: pure carry-save) / 2 / 3 plain quads of 8: the POPC : LOP3 balance (experiments)
+        static const int plain_sel = [] { const char* e = getenv("SOLA_K2_PLAIN"); return e ? atoi(e) : 0; }();
+        auto launch = [&](auto kernel) -> int {
+          SOLA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
+          kernel<<<(unsigned)(splits * n_tiles), ST_THREADS, smem + 1024, stream>>>(
+              map, N, words_per_track, nt, n_tiles, (int)splits, part, n_parts, reinterpret_cast<unsigned long long*>(inter_out));
+          return SOLA_OK;
+        };
+        const int lrc = plain_sel == 2 ? launch(pair_iou_st_tma_kernel<0x24>)
+                      : plain_sel == 3 ? launch(pair_iou_st_tma_kernel<0x92>) : launch(pair_iou_st_tma_kernel<K2_PLAIN_DEFAULT>);
+        if (lrc != SOLA_OK) return lrc;
       } else {
         SOLA_CUDA(cudaFuncSetAttribute(pair_iou_st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         pair_iou_st_kernel<<<(unsigned)(splits * n_tiles), ST_THREADS, smem, stream>>>(

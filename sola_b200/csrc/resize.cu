@@ -54,7 +54,7 @@ resize_bilinear_tiled_kernel(const uint32_t* __restrict__ in, int n_frames, int 
   const int ylo = bilinear_axis(oy0, sy, H).i0;
   const int yhi = bilinear_axis(oy0 + nrows - 1, sy, H).i1;
   const int n_in_words = (yhi - ylo + 1) * Wp;
-  tb.build(oy0, ylo, H, W, oh, ow, sy, sx);
+  tb.build(oy0, ylo, H, W, oh, ow, sy, sx, Wp);
   const long long FW = (long long)H * Wp, oFW = (long long)oh * owp;
   const bool vec16 = ((Wp & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);   // every row block starts 16-byte aligned
 
@@ -250,7 +250,8 @@ int sola_resize_bilinear_bin_packed(const uint32_t* in_packed, long long n_frame
   long long max_in_rows = (long long)ceil((double)R1_TR * (double)sy) + 3;
   if (max_in_rows > H) max_in_rows = H;
   const size_t smem = (size_t)owp * 32 * sizeof(XParam) + R1_TR * sizeof(YParam) + (size_t)owp * sizeof(int4) +
-                      2 * (size_t)max_in_rows * Wp * sizeof(uint32_t);   // == R1Tables::bytes(owp) + double-buffered tile
+                      2 * (size_t)max_in_rows * Wp * sizeof(uint32_t) + 16;   // == R1Tables::bytes(owp) + double-buffered tile
+                                                                              //    (+ the 2 masked-out words phase A may read past it)
   if (smem <= 200 * 1024) {
     SOLA_CUDA(cudaFuncSetAttribute(resize_bilinear_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = (oh + R1_TR - 1) / R1_TR;
