@@ -307,6 +307,38 @@ def cpu_arm(n_tracks, n_frames, steps, warmup, sample_tracks=4, device="cpu"):
     return value, full, sample
 
 
+def jf_stage(device):
+    """The J&F half of the metric (BASELINE configs 1 / 4), untimed with respect to the step above and informative only: the drop-in
+    Evaluator.compute_J + compute_F call on config 1 (30 x 480 x 854 fp32 masklets resident on the device, one read-back per call),
+    the K3 count kernel on a 320-frame 720p batch, and the boundary-F extension."""
+    import sola_b200 as S
+    from sola_b200 import evaluator, synth
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    p1, g1 = synth.jf_pair(30, 480, 854, seed=1235, device=device)
+    p1f, g1f = p1.float(), g1.float()
+    ms1 = timed(lambda: evaluator.compute_JF(p1f, g1f), 50)
+    T = 320
+    a = (synth.smooth_logits(T, 720, 1280, 5, device=device, cell=120) > 0).float()
+    b = (synth.smooth_logits(T, 720, 1280, 6, device=device, cell=120) > 0).float()
+    ms3 = timed(lambda: S.frame_counts(a, b), 10)
+    pa, pb = S.pack_masks(a), S.pack_masks(b)
+    msb = timed(lambda: S.boundary_counts(pa, pb), 3)
+    return {"config1_compute_J_and_F_call": {"ms": ms1, "masklet_frames_per_s": 30 / ms1 * 1e3, "shape": "30 x 480 x 854 fp32, incl. read-back"},
+            "K3_counts_fp32_720p": {"GBps": 2 * a.numel() * 4 / ms3 / 1e6, "masklet_frames_per_s": T / ms3 * 1e3},
+            "boundary_F_720p": {"masklet_frames_per_s": T / msb * 1e3}}
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -478,6 +510,11 @@ def main():
                      "bytes_per_launch": w.k1_bytes, "ms_per_launch": k1_ms, "share_of_step": k1_ms / (max_ms / args.steps),
                      "traffic": None},
     }
+    if world == 1:
+        try:
+            line["jf_stage"] = jf_stage(device)
+        except Exception as ex:
+            line["jf_stage"] = {"error": repr(ex)[:200]}
     if not args.no_cpu_baseline and world == 1:
         v, full, sample = cpu_arm(n_tracks, n_frames, 1, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample}

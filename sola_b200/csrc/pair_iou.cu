@@ -281,8 +281,8 @@ __device__ __forceinline__ void st_tile_body_tma(const CUtensorMap* __restrict__
     }
 }
 
-template <int PLAIN>
-__global__ void __launch_bounds__(ST_THREADS)
+template <int PLAIN, int MIN_CTAS = 0>
+__global__ void __launch_bounds__(ST_THREADS, MIN_CTAS)
 pair_iou_st_tma_kernel(const __grid_constant__ CUtensorMap map, int N, long long words, int nt, int n_tiles, int splits,
                        int tile_first, int tile_step, unsigned long long* __restrict__ inter) {
   extern __shared__ __align__(1024) unsigned char smem_tma[];          // SWIZZLE_128B needs 1024-byte aligned boxes
@@ -462,8 +462,13 @@ static int launch_pair_iou_st(const uint32_t* packed, int N, long long words_per
               map, N, words_per_track, nt, n_tiles, (int)splits, part, n_parts, reinterpret_cast<unsigned long long*>(inter_out));
           return SOLA_OK;
         };
+        // SOLA_K2_OCC (experiments): 3 = register-capped build (80 regs, 3 CTAs per SM), 2 = 128 regs at 2 CTAs per SM;
+        // default: ptxas' own choice (96 regs, 2 CTAs per SM)
+        static const int occ_sel = [] { const char* e = getenv("SOLA_K2_OCC"); return e ? atoi(e) : 0; }();
         const int lrc = plain_sel == 2 ? launch(pair_iou_st_tma_kernel<0x24>)
-                      : plain_sel == 3 ? launch(pair_iou_st_tma_kernel<0x92>) : launch(pair_iou_st_tma_kernel<K2_PLAIN_DEFAULT>);
+                      : plain_sel == 3 ? launch(pair_iou_st_tma_kernel<0x92>)
+                      : occ_sel == 3 ? launch(pair_iou_st_tma_kernel<K2_PLAIN_DEFAULT, 3>)
+                      : occ_sel == 2 ? launch(pair_iou_st_tma_kernel<K2_PLAIN_DEFAULT, 2>) : launch(pair_iou_st_tma_kernel<K2_PLAIN_DEFAULT>);
         if (lrc != SOLA_OK) return lrc;
       } else {
         SOLA_CUDA(cudaFuncSetAttribute(pair_iou_st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -22,7 +22,7 @@ del logits
 ref = S.pairwise_inter_matrix(resized)
 words = resized.words[0].numel()
 pairs = 64 * 63 // 2
-out = {"variant": os.environ.get("SOLA_K2_PLAIN", "2")}
+out = {"plain": os.environ.get("SOLA_K2_PLAIN", "0"), "occ": os.environ.get("SOLA_K2_OCC", "default")}
 ms = timed(lambda: S.pairwise_inter_matrix(resized))
 out["object_like_64x80x540x960"] = {"ms": ms, "pair_words_per_s": pairs * words / ms * 1e3, "checksum": int(ref.sum().item())}
 dense = S.PackedMasks(torch.randint(-2**31, 2**31 - 1, resized.words.shape, dtype=torch.int32, device="cuda"), resized.H, resized.W)
