@@ -78,6 +78,16 @@ int sola_frame_counts_packed(const uint32_t* a, const uint32_t* b, int Na, int N
  * One launch covers a whole J&F sweep of differently-shaped units (evaluator.py:174-225). */
 int sola_frame_counts_packed_ragged(const uint32_t* a, const uint32_t* b, const long long* word_offsets, int n_frames,
                                     int* inter, int* area_a, int* area_b, sola_stream_t stream);
+/* The J&F accumulators of one (video, expression) unit: inter[t] = |pred_t ∩ gt_t|, uni[t] = |pred_t ∪ gt_t| (int32 [T]) and
+ * tp_fp_fn int64 [3] = the volume sums behind Evaluator.compute_F (evaluator.py:239-247), exact.  J = mean_t(uni ? inter/uni : 1)
+ * (evaluator.py:227-237).  Inputs: raw {0,1} planes (T, frame_px) fp32 / uint8 with nonzero = foreground, or bit-packed
+ * (T, frame_words). */
+int sola_jf_f32(const float* pred, const float* gt, long long T, long long frame_px, int* inter, int* uni, long long* tp_fp_fn,
+                sola_stream_t stream);
+int sola_jf_u8(const uint8_t* pred, const uint8_t* gt, long long T, long long frame_px, int* inter, int* uni, long long* tp_fp_fn,
+               sola_stream_t stream);
+int sola_jf_packed(const uint32_t* pred, const uint32_t* gt, long long T, long long frame_words, int* inter, int* uni,
+                   long long* tp_fp_fn, sola_stream_t stream);
 /* OR over the selected packed tracks: tracks (K, words), select u8 [K] (NULL = all) -> out (words).
  * replaces np.logical_or accumulation in dataloader.py:285-299 (GT objects) and :319-350 (selected SAM2 tracks). */
 int sola_or_merge(const uint32_t* tracks, const uint8_t* select, int K, long long words, uint32_t* out, sola_stream_t stream);
@@ -148,7 +158,7 @@ int sola_rle_decode_runs(const int* run_plane, const int* run_start, const int* 
 int sola_rle_encode_transitions(const uint32_t* packed, long long n_planes, int H, int W, uint32_t* scratch_colmajor,
                                 int cap, int* out_pos, int* out_n, sola_stream_t stream);
 
-/* ---- boundary F (extension; no reference implementation — DAVIS definition, see oracle/boundary_oracle.py) --
+/* ---- boundary F (extension, SURVEY.md §8(b)'s `sola_boundary_f`; no reference implementation — DAVIS definition, see oracle/boundary_oracle.py) --
  * pred, gt packed (n_frames, H, Wp); radius = bound_pix; counts int32 [n_frames] each:
  * n_fg = |bmap(pred)|, n_gt = |bmap(gt)|, fg_match = |bmap(pred) & dilate(bmap(gt))|, gt_match = |bmap(gt) & dilate(bmap(pred))|. */
 int sola_boundary_counts(const uint32_t* pred, const uint32_t* gt, long long n_frames, int H, int W, int radius,

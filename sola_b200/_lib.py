@@ -29,6 +29,9 @@ SIGNATURES = {
     "sola_frame_counts_u8": [_P, _P, _LL, _LL, _P, _P, _P, _P],
     "sola_frame_counts_packed": [_P, _P, _I, _I, _I, _LL, _P, _P, _P, _P],
     "sola_frame_counts_packed_ragged": [_P, _P, _P, _I, _P, _P, _P, _P],
+    "sola_jf_f32": [_P, _P, _LL, _LL, _P, _P, _P, _P],
+    "sola_jf_u8": [_P, _P, _LL, _LL, _P, _P, _P, _P],
+    "sola_jf_packed": [_P, _P, _LL, _LL, _P, _P, _P, _P],
     "sola_or_merge": [_P, _P, _I, _LL, _P, _P],
     "sola_pair_iou_st": [_P, _I, _LL, _P, _P, _P],
     "sola_pair_iou_st_part": [_P, _I, _LL, _I, _I, _P, _P],

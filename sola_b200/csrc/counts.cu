@@ -233,6 +233,32 @@ or_merge_kernel(const uint32_t* __restrict__ tracks, const uint8_t* __restrict__
   }
 }
 
+// J&F accumulators from the three per-frame counts: uni[t] holds |pred_t| on entry and |pred_t ∪ gt_t| on exit;
+// totals[0..2] += (tp, fp, fn) over all frames — the volume sums of Evaluator.compute_F (evaluator.py:239-247) as exact integers.
+__global__ void __launch_bounds__(256)
+jf_finalize_kernel(const int* __restrict__ inter, int* __restrict__ uni, const int* __restrict__ area_gt, long long T,
+                   unsigned long long* __restrict__ totals) {
+  long long tp = 0, fp = 0, fn = 0;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < T; t += (long long)gridDim.x * blockDim.x) {
+    const int i = inter[t], a = uni[t], b = area_gt[t];
+    uni[t] = a + b - i;
+    tp += i; fp += a - i; fn += b - i;
+  }
+  __shared__ long long red[3][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    tp += __shfl_xor_sync(FULL, tp, d); fp += __shfl_xor_sync(FULL, fp, d); fn += __shfl_xor_sync(FULL, fn, d);
+  }
+  if (lane == 0) { red[0][warp] = tp; red[1][warp] = fp; red[2][warp] = fn; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    long long s = 0;
+    for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+    if (s) atomicAdd(totals + threadIdx.x, (unsigned long long)s);
+  }
+}
+
 }  // namespace sola
 
 using namespace sola;
@@ -272,6 +298,52 @@ int sola_frame_counts_packed_ragged(const uint32_t* a, const uint32_t* b, const 
   const int grid = min(n_frames, num_sms() * 8);
   packed_counts_ragged_kernel<<<grid, 256, 0, stream>>>(a, b, word_offsets, n_frames, inter, area_a, area_b);
   return check_launch("packed_counts_ragged kernel");
+}
+
+// ---- sola_jf_*: the J&F accumulators of one (video, expression) unit in the shape SURVEY.md §8(b) names -----------------------
+// inter[t] = |pred_t ∩ gt_t|, uni[t] = |pred_t ∪ gt_t| (J_t = 1 if uni == 0 else inter / uni, evaluator.py:227-237) and
+// tp_fp_fn[0..2] = volume sums for the reference's Dice-style F (evaluator.py:239-247).  One count pass + a T-element finalize;
+// the |gt_t| scratch is a stream-ordered allocation.
+}  // extern "C"
+
+template <typename CountFn>
+static int jf_common(long long T, int* inter, int* uni, long long* tp_fp_fn, cudaStream_t stream, CountFn count) {
+  SOLA_REQUIRE(T >= 0 && T < (1ll << 31), "jf: bad frame count");
+  SOLA_REQUIRE(tp_fp_fn, "jf: null totals pointer");
+  SOLA_CUDA(cudaMemsetAsync(tp_fp_fn, 0, 3 * sizeof(long long), stream));
+  if (T == 0) return SOLA_OK;
+  SOLA_REQUIRE(inter && uni, "jf: null pointer");
+  int* area_gt = nullptr;
+  SOLA_CUDA(cudaMallocAsync(&area_gt, sizeof(int) * (size_t)T, stream));
+  int rc = count(inter, uni, area_gt);
+  if (rc == SOLA_OK) {
+    const int blocks = (int)((T + 255) / 256 < 1024 ? (T + 255) / 256 : 1024);
+    jf_finalize_kernel<<<blocks, 256, 0, stream>>>(inter, uni, area_gt, T, reinterpret_cast<unsigned long long*>(tp_fp_fn));
+    rc = check_launch("jf_finalize kernel");
+  }
+  cudaFreeAsync(area_gt, stream);
+  return rc;
+}
+
+extern "C" {
+
+int sola_jf_f32(const float* pred, const float* gt, long long T, long long frame_px, int* inter, int* uni, long long* tp_fp_fn,
+                cudaStream_t stream) {
+  return jf_common(T, inter, uni, tp_fp_fn, stream,
+                   [&](int* i, int* a, int* b) { return launch_raw_counts<float>(pred, gt, T, frame_px, i, a, b, stream); });
+}
+
+int sola_jf_u8(const uint8_t* pred, const uint8_t* gt, long long T, long long frame_px, int* inter, int* uni, long long* tp_fp_fn,
+               cudaStream_t stream) {
+  return jf_common(T, inter, uni, tp_fp_fn, stream,
+                   [&](int* i, int* a, int* b) { return launch_raw_counts<uint8_t>(pred, gt, T, frame_px, i, a, b, stream); });
+}
+
+int sola_jf_packed(const uint32_t* pred, const uint32_t* gt, long long T, long long frame_words, int* inter, int* uni,
+                   long long* tp_fp_fn, cudaStream_t stream) {
+  return jf_common(T, inter, uni, tp_fp_fn, stream, [&](int* i, int* a, int* b) {
+    return sola_frame_counts_packed(pred, gt, 1, 1, (int)T, frame_words, i, a, b, stream);
+  });
 }
 
 int sola_or_merge(const uint32_t* tracks, const uint8_t* select, int K, long long words, uint32_t* out, cudaStream_t stream) {

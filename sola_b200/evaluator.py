@@ -77,6 +77,20 @@ def compute_JF(pred_masklet, gt_masklet):
     return J_from_counts(c[0], c[1], c[2]), F_from_counts(c[0], c[1], c[2])
 
 
+def jf_from_accumulators(inter, uni, totals):
+    """(J, F) from the device accumulators of packed.jf_accumulators / the C ABI's sola_jf_*: J = np.mean of the per-frame ratios with
+    the union == 0 -> 1.0 rule (evaluator.py:231-236); F = 2PR/(P+R) from tp / fp / fn with the tp == 0 -> 0.0 rule (evaluator.py:243-247)."""
+    i = inter.cpu().numpy().astype(np.float64) if isinstance(inter, torch.Tensor) else np.asarray(inter, np.float64)
+    u = uni.cpu().numpy().astype(np.float64) if isinstance(uni, torch.Tensor) else np.asarray(uni, np.float64)
+    tp, fp, fn = (int(x) for x in (totals.cpu().tolist() if isinstance(totals, torch.Tensor) else totals))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        J = np.mean(np.where(u == 0, 1.0, i / np.where(u == 0, 1.0, u))) if len(u) else np.float64("nan")
+    if tp == 0:
+        return J, 0.0
+    prec, rec = tp / (tp + fp), tp / (tp + fn)
+    return J, 2 * prec * rec / (prec + rec)
+
+
 def compute_F_boundary(pred_masklet, gt_masklet, bound_th: float = 0.008) -> float:
     pp = pred_masklet if isinstance(pred_masklet, P.PackedMasks) else P.pack_masks(pred_masklet)
     gp = gt_masklet if isinstance(gt_masklet, P.PackedMasks) else P.pack_masks(gt_masklet)

@@ -278,6 +278,33 @@ def frame_counts_ragged(a_words: torch.Tensor, b_words: torch.Tensor, word_offse
     return out
 
 
+def jf_accumulators(pred, gt):
+    """The J&F accumulators of one (video, expression) unit, on the device: (inter int32 [T], union int32 [T], int64 [tp, fp, fn]).
+    pred / gt: raw {0,1} masklets (T, H, W) fp32 or uint8, or PackedMasks (T, H, Wp).  J = mean(union ? inter / union : 1)
+    (evaluator.py:227-237); F from the exact volume sums (evaluator.py:239-247) — see evaluator.jf_from_accumulators."""
+    if isinstance(pred, PackedMasks):
+        assert isinstance(gt, PackedMasks) and (pred.H, pred.W) == (gt.H, gt.W)
+        a, b = pred.words.contiguous(), gt.words.contiguous()
+        T, per_frame, fn = pred.n_frames, pred.frame_words, "sola_jf_packed"
+    else:
+        a = to_device(pred)
+        b = to_device(gt, device=a.device)
+        assert a.shape == b.shape, f"shape mismatch {tuple(a.shape)} vs {tuple(b.shape)}"
+        if not (a.dtype == torch.uint8 and b.dtype == torch.uint8):
+            a, b = a.float(), b.float()
+        if a.dim() == 2:
+            a, b = a[None], b[None]
+        a, b = a.contiguous(), b.contiguous()
+        T, per_frame = int(a.shape[0]), int(np.prod(a.shape[1:], dtype=np.int64))
+        fn = "sola_jf_f32" if a.dtype == torch.float32 else "sola_jf_u8"
+    inter = torch.empty((T,), dtype=torch.int32, device=a.device)
+    uni = torch.empty((T,), dtype=torch.int32, device=a.device)
+    totals = torch.empty((3,), dtype=torch.int64, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.call(fn, a.data_ptr(), b.data_ptr(), T, per_frame, inter.data_ptr(), uni.data_ptr(), totals.data_ptr(), _stream(a))
+    return inter, uni, totals
+
+
 def or_merge(tracks: PackedMasks, select=None) -> PackedMasks:
     """tracks (K, T, H, Wp) -> (T, H, Wp): OR of the tracks with select[k] != 0 (all when select is None).
     With nothing selected the result is all-zero planes (dataloader.py:346-349)."""

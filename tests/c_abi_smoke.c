@@ -1,6 +1,7 @@
 /* Pure-C client of libsola_maskpath.so: no Python, no torch — the drop-in boundary is a C ABI.
  * Build: nvcc (or gcc + -lcudart) tests/c_abi_smoke.c -Iinclude -Lsola_b200/lib -lsola_maskpath -o c_abi_smoke
- * Checks K1 (planes + the three stability counts), K3 (per-frame counts) and the fused K1+R1 entry point against plain C loops. */
+ * Checks K1 (planes + the three stability counts), K3 (per-frame counts), the J&F accumulators and the fused K1+R1 entry point
+ * against plain C loops. */
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -52,6 +53,23 @@ int main(void) {
     int i_ = 0, na = 0, nb = 0;
     for (size_t k = (size_t)f * H * W; k < (size_t)(f + 1) * H * W; ++k) { i_ += a[k] != 0 && b[k] != 0; na += a[k] != 0; nb += b[k] != 0; }
     if (hc[f] != i_ || hc[n + f] != na || hc[2 * n + f] != nb) { printf("K3 mismatch frame %d\n", f); return 1; }
+  }
+  /* J&F accumulators: per-frame inter / union and the exact tp / fp / fn of the unit (evaluator.py:227-247) */
+  {
+    int* iu; long long* tot; int hiu[6]; long long htot[3], tp = 0, fp = 0, fn = 0;
+    CK(cudaMalloc((void**)&iu, 2 * n * sizeof(int))); CK(cudaMalloc((void**)&tot, 3 * sizeof(long long)));
+    rc = sola_jf_f32(da, db, n, (long long)H * W, iu, iu + n, tot, 0);
+    if (rc) { printf("sola_jf_f32: %s\n", sola_last_error_string()); return 1; }
+    CK(cudaMemcpy(hiu, iu, sizeof(hiu), cudaMemcpyDeviceToHost)); CK(cudaMemcpy(htot, tot, sizeof(htot), cudaMemcpyDeviceToHost));
+    for (int f = 0; f < n; ++f) {
+      int i_ = 0, u_ = 0;
+      for (size_t k = (size_t)f * H * W; k < (size_t)(f + 1) * H * W; ++k) {
+        const int pa = a[k] != 0, pb = b[k] != 0;
+        i_ += pa && pb; u_ += pa || pb; tp += pa && pb; fp += pa && !pb; fn += !pa && pb;
+      }
+      if (hiu[f] != i_ || hiu[n + f] != u_) { printf("sola_jf mismatch frame %d\n", f); return 1; }
+    }
+    if (htot[0] != tp || htot[1] != fp || htot[2] != fn) { printf("sola_jf totals mismatch\n"); return 1; }
   }
   /* fused K1 + R1: the resized planes must equal R1 applied to K1's planes */
   const int oh = 54, ow = 96, owp = (ow + 31) / 32;

@@ -175,3 +175,30 @@ def test_jf_sweep_and_evaluator_json(tmp_path):
         assert saved[v][e]["J"] == exp_out[v][e]["J"]
         assert abs(saved[v][e]["F"] - exp_out[v][e]["F"]) < 1e-6
     assert saved["v1"]["1"] == {"expression": "exp 1", "J": 0.0, "F": 0.0, "JF": 0.0}
+
+
+@pytest.mark.parametrize("shape", [(30, 480, 854), (5, 33, 47), (3, 720, 1280), (1, 7, 3)])
+def test_jf_accumulators_abi(shape):
+    """sola_jf_f32 / _u8 / _packed (the J&F entry SURVEY.md §8(b) names): per-frame inter / union and exact tp / fp / fn, and the
+    (J, F) they give against the oracle's restatement of evaluator.py:227-247."""
+    import sola_b200 as S
+    from sola_b200 import evaluator, synth
+    T, H, W = shape
+    pred, gt = synth.jf_pair(T, H, W, seed=77 + T, device="cpu")
+    p, g = pred.numpy().astype(bool), gt.numpy().astype(bool)
+    inter_ref = (p & g).reshape(T, -1).sum(1)
+    uni_ref = (p | g).reshape(T, -1).sum(1)
+    tot_ref = [int((p & g).sum()), int((p & ~g).sum()), int((~p & g).sum())]
+    pf, gf = pred.float(), gt.float()
+    for a, b in ((pf.cuda(), gf.cuda()), (pred.cuda(), gt.cuda()), (S.pack_masks(pred), S.pack_masks(gt))):
+        inter, uni, tot = S.packed.jf_accumulators(a, b)
+        np.testing.assert_array_equal(inter.cpu().numpy(), inter_ref)
+        np.testing.assert_array_equal(uni.cpu().numpy(), uni_ref)
+        assert tot.cpu().tolist() == tot_ref
+        J, F = evaluator.jf_from_accumulators(inter, uni, tot)
+        assert J == O.compute_J(pf, gf)
+        assert abs(F - O.compute_F(pf, gf)) < 1e-6            # north-star tolerance; equal whenever the reference's fp32 sums are exact
+    # empty unit and all-empty prediction (tp == 0 -> F = 0; union == 0 frames -> J_t = 1)
+    z = torch.zeros((4, 20, 40), dtype=torch.uint8, device="cuda")
+    inter, uni, tot = S.packed.jf_accumulators(z, z)
+    assert evaluator.jf_from_accumulators(inter, uni, tot) == (1.0, 0.0) and tot.cpu().tolist() == [0, 0, 0]
