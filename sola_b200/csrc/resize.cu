@@ -44,7 +44,8 @@ resize_bilinear_tiled_kernel(const uint32_t* __restrict__ in, int n_frames, int 
   R1Tables tb;
   tb.carve(r1_smem, owp);
   uint32_t* tile = reinterpret_cast<uint32_t*>(r1_smem + R1Tables::bytes(owp));   // [2][max_in_rows * Wp]
-  const int tile_words_max = max_in_rows * Wp;
+  const int tile_words_max = max_in_rows * Wp + 4;       // + 4 words: phase A may read 2 (masked-out) words past the last row, and those
+                                                         //   must not alias the other buffer while cp.async is filling it
   const int tid = threadIdx.x, lane = tid & 31;
   const int oy0 = blockIdx.x * R1_TR;
   const int nrows = min(R1_TR, oh - oy0);
@@ -250,8 +251,8 @@ int sola_resize_bilinear_bin_packed(const uint32_t* in_packed, long long n_frame
   long long max_in_rows = (long long)ceil((double)R1_TR * (double)sy) + 3;
   if (max_in_rows > H) max_in_rows = H;
   const size_t smem = (size_t)owp * 32 * sizeof(XParam) + R1_TR * sizeof(YParam) + (size_t)owp * sizeof(int4) +
-                      2 * (size_t)max_in_rows * Wp * sizeof(uint32_t) + 16;   // == R1Tables::bytes(owp) + double-buffered tile
-                                                                              //    (+ the 2 masked-out words phase A may read past it)
+                      2 * ((size_t)max_in_rows * Wp + 4) * sizeof(uint32_t);  // == R1Tables::bytes(owp) + double-buffered tile, each
+                                                                              //    buffer padded by 4 words (see the kernel)
   if (smem <= 200 * 1024) {
     SOLA_CUDA(cudaFuncSetAttribute(resize_bilinear_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = (oh + R1_TR - 1) / R1_TR;

@@ -11,8 +11,9 @@ for shape in [(3, 40, 64), (2, 37, 70), (4, 21, 100), (2, 5, 33), (2, 96, 160)]:
     for dt in (torch.float32, torch.bfloat16):
         xx = x.to(dt)
         p, c = S.binarize_pack_stability(xx)
-        S.binarize_pack_resize(xx, target_shape=(27, 48), want_area=True)
-        S.binarize_pack_resize(xx, target_shape=(60, 50))
+        for tgt in ((27, 48), (60, 50)):
+            fused = S.binarize_pack_resize(xx, target_shape=tgt, want_area=True)
+            assert torch.equal(fused[2].words, S.resize_bilinear_bin(p, tgt).words), "fused K1+R1 != K1 then R1"
     m = (x > 0)
     pk, area = S.pack_masks(m.float(), want_area=True)
     S.pack_masks(m.to(torch.uint8))
@@ -28,6 +29,16 @@ for shape in [(3, 40, 64), (2, 37, 70), (4, 21, 100), (2, 5, 33), (2, 96, 160)]:
 tracks = S.pack_masks((torch.randn((70, 3, 16, 64), generator=g) > 0).cuda().float())
 S.pairwise_inter_matrix(tracks)
 S.packed.pairwise_inter_matrix_part(tracks, 1, 3)
+full = S.pairwise_inter_matrix(tracks)
+words = tracks.words[0].numel()
+ptrs = torch.tensor([tracks.words[i].data_ptr() for i in range(70)], dtype=torch.int64, device="cuda")
+assert torch.equal(sum(S.packed.pairwise_inter_matrix_rows(ptrs, words, k, 2) for k in range(2)), full)       # peer-load K2 entry
+acc = torch.zeros_like(full)
+for lo, hi in ((0, 32), (32, words)):
+    chunk = torch.empty((70, hi - lo), dtype=torch.int32, device="cuda")
+    S.packed.pull_rows(ptrs, lo, hi - lo, chunk)
+    S.packed.pairwise_inter_accumulate(chunk, acc)                                                              # pull + TMA ring K2
+assert torch.equal(acc, full)
 odd = S.pack_masks((torch.randn((5, 1, 5, 70), generator=g) > 0).cuda().float())
 S.pairwise_inter_matrix(odd)
 prompts = S.pack_masks((torch.randn((9, 16, 64), generator=g) > 0).cuda().float())
@@ -39,5 +50,8 @@ job = dedup.VideoDedupJob([{"prompt_id": p["prompt_id"], "frame_idx": p["frame_i
 job.enqueue(logits.cuda(), torch.from_numpy(np.stack([p["segmentation"] for p in pr])).cuda())
 job.finish()
 evaluator.compute_JF(*synth.jf_pair(4, 50, 77, 1, device="cuda"))
+pj, gj = synth.jf_pair(4, 50, 77, 1, device="cuda")
+for a_, b_ in ((pj, gj), (pj.float(), gj.float()), (S.pack_masks(pj), S.pack_masks(gj))):
+    S.packed.jf_accumulators(a_, b_)
 torch.cuda.synchronize()
 print("sanitize smoke ok")
