@@ -25,8 +25,8 @@ constexpr int FU_THREADS = 256;
 constexpr int FU_WARPS = FU_THREADS / 32;
 constexpr int FU_CHUNK_PX = 1024;
 
-template <typename T>
-__global__ void __launch_bounds__(FU_THREADS)
+template <typename T, int MIN_CTAS = 0>
+__global__ void __launch_bounds__(FU_THREADS, MIN_CTAS)
 fused_pack_resize_kernel(const T* __restrict__ logits, int n_frames, int frames_per_slice, int H, int W, int oh, int ow,
                          float sy, float sx, int max_tile_rows, Thresholds th,
                          uint32_t* __restrict__ packed, uint32_t* __restrict__ resized,
@@ -267,6 +267,13 @@ struct FusedPlan {
   size_t smem;
 };
 
+// The fp32 kernel is built with a 5-CTA/SM register cap (48 registers, no spills): left alone ptxas takes 64 registers (4 CTAs/SM),
+// which measures 1.1 % slower on the bench (2.968 vs 2.935 ms).  SOLA_FUSED_OCC=0 selects the uncapped build for A/B runs.
+static int fused_occ() {
+  static const int v = [] { const char* e = getenv("SOLA_FUSED_OCC"); return e ? atoi(e) : 5; }();
+  return v;
+}
+
 static FusedPlan plan_fused(const void* base, long long n_frames, int H, int W, int oh, int ow, int elem_size) {
   FusedPlan p{};
   p.ok = false;
@@ -304,7 +311,8 @@ static FusedPlan plan_fused(const void* base, long long n_frames, int H, int W, 
   if (p.generic) {
     if (elem_size == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, band_pack_generic_kernel<float, true>, FU_THREADS, p.smem);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, band_pack_generic_kernel<__nv_bfloat16, true>, FU_THREADS, p.smem);
-  } else if (elem_size == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_pack_resize_kernel<float>, FU_THREADS, p.smem);
+  } else if (elem_size == 4 && fused_occ() == 5) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_pack_resize_kernel<float, 5>, FU_THREADS, p.smem);
+  else if (elem_size == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_pack_resize_kernel<float>, FU_THREADS, p.smem);
   else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_pack_resize_kernel<__nv_bfloat16>, FU_THREADS, p.smem);
   if (occ < 1) occ = 1;
   // several waves of resident CTAs: finer slices cost a table rebuild per CTA (~5 % of one frame's work) but shrink the
@@ -360,6 +368,13 @@ static int launch_fused(const T* logits, long long n_frames, int H, int W, int o
                                                                             p.max_flat_words, th, packed_out, resized_out, cnt_hi, cnt_mid,
                                                                             cnt_lo, area_resized);
     return check_launch("band_pack_generic<resize> kernel");
+  }
+  if (sizeof(T) == 4 && fused_occ() == 5) {
+    SOLA_CUDA(cudaFuncSetAttribute(fused_pack_resize_kernel<T, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    fused_pack_resize_kernel<T, 5><<<grid, FU_THREADS, p.smem, stream>>>(logits, (int)n_frames, p.frames_per_slice, H, W, oh, ow,
+                                                                         (float)H / (float)oh, (float)W / (float)ow, p.max_tile_rows, th,
+                                                                         packed_out, resized_out, cnt_hi, cnt_mid, cnt_lo, area_resized);
+    return check_launch("fused_pack_resize<occ5> kernel");
   }
   SOLA_CUDA(cudaFuncSetAttribute(fused_pack_resize_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   fused_pack_resize_kernel<T><<<grid, FU_THREADS, p.smem, stream>>>(logits, (int)n_frames, p.frames_per_slice, H, W, oh, ow,
