@@ -141,3 +141,73 @@ def test_word_slices_partition_the_word_axis():
             assert all(a % 32 == 0 for a, _ in sl)
             sizes = [b - a for a, b in sl]
             assert max(sizes) - min(sizes) <= 32 or words < 32 * world
+
+
+def _bilinear_axis_fp32(dst, scale_f32, in_size):
+    """ATen's (and csrc/resize_core.cuh's) source index: src = fmaf(dst + 0.5, scale, -0.5) clamped at 0; i1 = i0 + (i0 < in - 1).
+    The product of a <=12-bit and a 24-bit significand is exact in float64, so one rounding to fp32 reproduces the fused multiply-add."""
+    src = (np.asarray(dst, np.float64) + 0.5) * np.float64(scale_f32) - 0.5
+    src = src.astype(np.float32)
+    src = np.where(src >= 0, src, np.float32(0))
+    i0 = src.astype(np.int64)
+    return i0, i0 + (i0 < in_size - 1)
+
+
+def test_r1_window_spans_at_most_three_words_below_scale_2():
+    """Design invariant behind the branch-free phase A of R1 (resize_core.cuh, `win3`): for any scale factor < 1.99 the source pixels
+    read by one 32-pixel output word lie in at most 3 consecutive source words — checked with the kernel's own fp32 index arithmetic
+    over every width pair of a sweep that includes the BASELINE shapes."""
+    wide = [540, 960, 854, 1280, 1920, 480, 720, 1080, 333, 1000, 2048]
+    worst = 0
+    for ow in list(range(1, 160, 3)) + wide:
+        if ow < 160:
+            widths = range(max(1, ow // 3), int(ow * 1.99) + 2)
+        else:
+            widths = sorted({max(1, int(ow * r)) for r in (0.3, 0.5, 0.889, 1.0, 4 / 3, 1.5, 1.9, 1.98, 1.989)})
+        for W in widths:
+            scale = np.float32(W) / np.float32(ow)
+            if not scale < np.float32(1.99):
+                continue
+            c = np.arange((ow + 31) // 32)
+            xa = _bilinear_axis_fp32(c * 32, scale, W)[0]
+            xb = _bilinear_axis_fp32(np.minimum(c * 32 + 31, ow - 1), scale, W)[1]
+            worst = max(worst, int(((xb >> 5) - (xa >> 5)).max()))
+    assert worst <= 2
+
+
+def test_bf16_packed_compare_bit_tricks():
+    """Arithmetic identities the bf16 K1 path relies on (csrc/pack_core.cuh), emulated with numpy integers:
+    (1) subtracting HSET2 bit masks (0xFFFF per passing half) from a 32-bit accumulator and decoding a + b as 2a + ((acc - a) >> 16);
+    (2) PRMT 0x6420 + two masks + multiply by 0x01010101 puts the 8 predicate bits of a 16-byte vector, in element order, in the top byte;
+    (3) flooring a threshold to bf16 does not change `x > t` for any bf16 x."""
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        n = int(rng.integers(1, 400))
+        lo, hi = rng.random(n) < rng.random(), rng.random(n) < rng.random()
+        acc = np.uint32(0)
+        for l, h in zip(lo, hi):
+            mask = np.uint32((0xFFFF if l else 0) | ((0xFFFF if h else 0) << 16))
+            acc = np.uint32((int(acc) - int(mask)) & 0xFFFFFFFF)
+        acc_i = int(acc) - (1 << 32) if int(acc) >= (1 << 31) else int(acc)
+        a = acc_i & 0xFFFF
+        assert 2 * a + ((acc_i - a) >> 16) == int(lo.sum() + hi.sum())
+    for _ in range(500):
+        e = rng.random(8) < 0.5
+        m = [(0xFFFF if e[2 * k] else 0) | ((0xFFFF if e[2 * k + 1] else 0) << 16) for k in range(4)]
+        byte = lambda w, i: (w >> (8 * i)) & 0xFF
+        prmt = lambda x, y: byte(x, 0) | (byte(x, 2) << 8) | (byte(y, 0) << 16) | (byte(y, 2) << 24)      # selector 0x6420
+        t = (prmt(m[0], m[1]) & 0x08040201) | (prmt(m[2], m[3]) & 0x80402010)
+        top = ((t * 0x01010101) & 0xFFFFFFFF) >> 24
+        assert top == sum(int(b) << k for k, b in enumerate(e))
+    # (3): every finite bf16 x against thresholds around the interesting values
+    bits = np.arange(0, 1 << 16, dtype=np.uint32)
+    x = (bits << 16).view(np.float32)
+    x = x[np.isfinite(x)]
+    for t in (0.0, 1.0, -1.0, 0.3, -0.7, 1.0000001, -1.0000001, 1e-40, -1e-40, 3.3e38, -3.3e38):
+        t32 = np.float32(t)
+        b = int(np.array([t32]).view(np.uint32)[0])
+        h = b >> 16
+        if (b & 0xFFFF) and (b >> 31):
+            h += 1
+        t_floor = np.array([(h & 0xFFFF) << 16], dtype=np.uint32).view(np.float32)[0]
+        np.testing.assert_array_equal(x > t32, x > t_floor)
