@@ -211,3 +211,56 @@ def test_bf16_packed_compare_bit_tricks():
             h += 1
         t_floor = np.array([(h & 0xFFFF) << 16], dtype=np.uint32).view(np.float32)[0]
         np.testing.assert_array_equal(x > t32, x > t_floor)
+
+
+def test_fused_band_ownership_partitions_the_input_rows():
+    """Design invariant of the fused K1+R1 kernel (csrc/fused_pack_resize.cu): band b of 32 output rows owns input rows
+    [tlo, own_end) — every input row is owned by exactly one band (so the packed planes and the stability counts are written /
+    counted once) and every row a band's outputs read lies inside the rows it streams, for up- and down-scaling alike."""
+    TR = 32
+
+    def i0_i1(dst, scale, n):
+        src = np.float32((np.float64(dst) + 0.5) * np.float64(scale) - 0.5)
+        src = src if src >= 0 else np.float32(0)
+        a = int(src)
+        return a, a + (1 if a < n - 1 else 0)
+
+    for H in list(range(1, 100, 2)) + [180, 480, 540, 720, 1080, 1280, 2160]:
+        for oh in (1, 5, 31, 32, 33, 64, 100, 540, 960):
+            sy = np.float32(H) / np.float32(oh)
+            nb = (oh + TR - 1) // TR
+            cover = np.zeros(H, int)
+            for b in range(nb):
+                oy0 = b * TR
+                nrows = min(TR, oh - oy0)
+                ylo, yhi = i0_i1(oy0, sy, H)[0], i0_i1(oy0 + nrows - 1, sy, H)[1]
+                tlo = 0 if b == 0 else ylo
+                own_end = H if b == nb - 1 else i0_i1(oy0 + TR, sy, H)[0]
+                yend = max(yhi, own_end - 1)
+                assert tlo <= own_end
+                cover[tlo:own_end] += 1
+                for oy in (oy0, oy0 + nrows - 1):
+                    a, b1 = i0_i1(oy, sy, H)
+                    assert tlo <= a and b1 <= yend
+            assert (cover == 1).all(), (H, oh)
+
+
+def test_carry_save_accumulation_is_exact():
+    """K2's Harley-Seal step (csrc/pair_iou.cu csa_quad): ones/twos bit-sliced counters + popcount of the weight-4 carry word give
+    exactly sum(popcount(a & b)) over any number of k-quads."""
+    rng = np.random.default_rng(1)
+    maj = lambda a, b, c: (a & b) | (a & c) | (b & c)
+    pop = lambda v: bin(int(v)).count("1")
+    for _ in range(50):
+        nq = int(rng.integers(1, 40))
+        a = rng.integers(0, 1 << 32, size=(nq, 4), dtype=np.uint64)
+        b = rng.integers(0, 1 << 32, size=(nq, 4), dtype=np.uint64) & rng.integers(0, 1 << 32, size=(nq, 4), dtype=np.uint64)
+        ones = twos = 0
+        acc = 0
+        for q in range(nq):
+            x = [int(a[q, k] & b[q, k]) for k in range(4)]
+            t1, s1 = maj(ones, x[0], x[1]), ones ^ x[0] ^ x[1]
+            t2, ones = maj(s1, x[2], x[3]), s1 ^ x[2] ^ x[3]
+            f, twos = maj(twos, t1, t2), twos ^ t1 ^ t2
+            acc += 4 * pop(f)
+        assert acc + 2 * pop(twos) + pop(ones) == sum(pop(int(u & v)) for u, v in zip(a.ravel(), b.ravel()))
