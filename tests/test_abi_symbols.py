@@ -38,6 +38,14 @@ def test_library_identity_and_error_string():
     assert rc == -1
     rc = lib.sola_boundary_counts(1, 1, 1, 8, 8, 99, 1, 1, 1, 1, None)
     assert rc == -3 and b"radius" in lib.sola_last_error_string()
+    # the multi-GPU / J&F entry points validate the same way: status + message, never an exception or a crash
+    assert lib.sola_pair_iou_st_rows(None, 4, 18, 0, 1, None, None) == -1 and b"multiple of 4" in lib.sola_last_error_string()
+    assert lib.sola_pair_iou_st_rows(None, 4, 16, 2, 2, None, None) == -1 and b"partition" in lib.sola_last_error_string()
+    assert lib.sola_pull_rows(None, 4, 2, 16, None, None) == -1 and b"aligned" in lib.sola_last_error_string()
+    assert lib.sola_pull_rows(None, 0, 0, 16, None, None) == 0                       # nothing to do is not an error
+    assert lib.sola_jf_f32(None, None, -1, 16, None, None, None, None) == -1
+    assert lib.sola_jf_packed(None, None, 4, 16, None, None, None, None) == -1 and b"null" in lib.sola_last_error_string()
+    assert lib.sola_pair_iou_st_part(1, 4, 16, 3, 2, 1, None) == -1
 
 
 def test_no_cpu_fallback():
