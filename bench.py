@@ -510,6 +510,25 @@ def main():
                      "bytes_per_launch": w.k1_bytes, "ms_per_launch": k1_ms, "share_of_step": k1_ms / (max_ms / args.steps),
                      "traffic": None},
     }
+    try:
+        # secondary roofline: K2 is integer-pipe work.  Denominator = alu pipe at 64 lanes/clk/SM (B300_MICROARCH.md; LOP3 measured 64-84
+        # by tools/microbench_int.cu) x 148 SMs x the SM clock sampled during the timed region / 2.5 LOP3 per pair-word (4 AND + 6
+        # compressor LOP3 per 4 words).  Pair-words are counted densely; the kernel skips all-zero operand quads, which is why this
+        # fraction on the object-like bench masklets (~0.8) is above the dense-data one (~0.6, profiles/r1_k2_variants.jsonl).
+        oh_, ow_ = (CFG["H"], CFG["W"]) if args.st_native else S.packed.default_target_shape(CFG["H"], CFG["W"])
+        words_ = n_frames * oh_ * ((ow_ + 31) // 32)
+        pair_words = (n_tracks * (n_tracks + 1) // 2) * words_
+        sm_mhz = (line["clocks"] or {}).get("sm_mhz") or 1965.0
+        if not (k2_ms > 0):
+            raise ValueError("no K2 timing events")
+        peak_k2 = 148 * 64 * sm_mhz * 1e6 / 2.5
+        ach_k2 = pair_words / (k2_ms * 1e-3)
+        line["roofline_k2"] = {"bound": "int-alu", "kernel": "pair_iou_st_ring_kernel (K2 N x N AND-popcount, carry-save)",
+                               "achieved": ach_k2 / 1e12, "peak": peak_k2 / 1e12, "unit": "T pair-words/s", "frac": ach_k2 / peak_k2,
+                               "peak_source": "148 SMs x 64 alu lanes/clk x sampled SM clock / 2.5 LOP3 per pair-word",
+                               "pair_words_per_launch": int(pair_words), "ms_per_launch": k2_ms}
+    except Exception as ex:
+        line["roofline_k2"] = {"error": repr(ex)[:200]}
     if world == 1:
         try:
             line["jf_stage"] = jf_stage(device)
