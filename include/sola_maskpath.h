@@ -108,6 +108,12 @@ int sola_pair_iou_st_part(const uint32_t* packed, int N, long long words_per_tra
  * 1/n_parts of its peers' planes; the sum of all parts' outputs is the full matrix. */
 int sola_pair_iou_st_rows(const uint32_t* const* row_ptrs, int N, long long words_per_track, int part, int n_parts, long long* inter_out,
                           sola_stream_t stream);
+/* EXPERIMENTAL (compiled, not yet run on hardware): exchange + K2 in ONE kernel.  bases_host is a HOST array of `world` device
+ * pointers, rank r's (n_local, words_per_track) packed planes in peer-mapped memory; the K2 producer lane issues its TMA tile loads
+ * against one tensor map per rank, so the rows cross NVLink inside the kernel that reduces them.  part / n_parts partition the
+ * word axis as in sola_pair_iou_st_rows.  SOLA_ERR_UNSUPPORTED if gcd(64, n_local) < 8 or world > 8. */
+int sola_pair_iou_st_peer(const uint32_t* const* bases_host, int world, int n_local, long long words_per_track, int part, int n_parts,
+                          long long* inter_out, sola_stream_t stream);
 /* inter_inout += intersections over these words (no memset): walk the word axis in chunks (e.g. pulled from peers, see below). */
 int sola_pair_iou_st_accumulate(const uint32_t* packed, int N, long long words_per_track, long long* inter_inout, sola_stream_t stream);
 /* dst (N, n_words) <- words [word_lo, word_lo + n_words) of every row of the pointer table (rows may live in peer GPUs' memory:

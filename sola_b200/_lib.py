@@ -36,6 +36,7 @@ SIGNATURES = {
     "sola_pair_iou_st": [_P, _I, _LL, _P, _P, _P],
     "sola_pair_iou_st_part": [_P, _I, _LL, _I, _I, _P, _P],
     "sola_pair_iou_st_rows": [_P, _I, _LL, _I, _I, _P, _P],
+    "sola_pair_iou_st_peer": [_P, _I, _I, _LL, _I, _I, _P, _P],
     "sola_pair_iou_st_accumulate": [_P, _I, _LL, _P, _P],
     "sola_pull_rows": [_P, _I, _LL, _LL, _P, _P],
     "sola_pair_iou_gather": [_P, _P, _P, _I, _I, _I, _LL, _P, _P, _P, _P],

@@ -401,6 +401,112 @@ pair_iou_st_ring_kernel(const __grid_constant__ CUtensorMap map, int N, long lon
   else st_tile_body_ring<false>(&map, N, ti, tj, s_begin, s_end, boxes, full, empty, inter);
 }
 
+// ---- ring variant whose producer loads the tiles straight out of PEER GPUs' memory (EXPERIMENTAL: compiled, not yet run on hardware) --
+// One kernel that is both the exchange and the math of BASELINE config 5: every rank's packed planes sit in an NVLink-mapped buffer
+// (n_local tracks x words), one rank-2 tensor map per rank; the producer lane splits each 64-row operand tile into pieces of
+// `box_rows` rows (a divisor of 64 and of n_local, so a piece never straddles two ranks) and issues one `cp.async.bulk.tensor.2d`
+// per piece against the owner's map — the TMA unit pulls the rows over NVLink while the 8 consumer warps reduce the previous stages.
+// Rows beyond a rank's n_local (and the K tail) are zero-filled by the hardware and still count towards the stage's byte total.
+struct PeerMaps { CUtensorMap m[8]; };
+
+template <bool DIAG>
+__device__ __forceinline__ void st_tile_body_ring_peer(const PeerMaps* __restrict__ maps, int world, int n_local, int box_rows, int N,
+                                                       int ti, int tj, long long s_begin, long long s_end, unsigned char* smem,
+                                                       uint64_t* full, uint64_t* empty, unsigned long long* __restrict__ inter) {
+  const int tid = threadIdx.x;
+  const long long n_st = s_end - s_begin;
+  if (tid >= ST_THREADS) {
+    if (tid == ST_THREADS) {
+      const int pieces = PT / box_rows;
+      for (long long s = 0; s < n_st; ++s) {
+        const int buf = (int)(s % NSTAGE);
+        if (s >= NSTAGE) mbar_wait(empty + buf, (unsigned)(((s / NSTAGE) - 1) & 1));
+        unsigned char* dst = smem + (size_t)buf * 2 * TMA_BOX_BYTES;
+        mbar_expect_tx(full + buf, DIAG ? TMA_BOX_BYTES : 2 * TMA_BOX_BYTES);
+        const int w0 = (int)((s_begin + s) * STAGE_WORDS);
+        for (int op = 0; op < (DIAG ? 1 : 2); ++op) {
+          const int tile = op == 0 ? ti : tj;
+          for (int p = 0; p < pieces; ++p) {
+            const int g0 = tile * PT + p * box_rows;                    // global index of the piece's first track
+            int owner = g0 / n_local;
+            if (owner > world - 1) owner = world - 1;                   // past the last track: out-of-range rows -> hardware zero fill
+            tma_load_2d(dst + (size_t)op * TMA_BOX_BYTES + (size_t)p * box_rows * STAGE_WORDS * 4, &maps->m[owner], w0,
+                        g0 - owner * n_local, full + buf);
+          }
+        }
+      }
+    }
+    return;
+  }
+  const int tx = tid & 15, ty = tid >> 4, lane = tid & 31;
+  Csa acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = Csa{0u, 0u, 0};
+  for (long long s = 0; s < n_st; ++s) {
+    const int bufi = (int)(s % NSTAGE);
+    mbar_wait(full + bufi, (unsigned)((s / NSTAGE) & 1));
+    const uint4* A = reinterpret_cast<const uint4*>(smem + (size_t)bufi * 2 * TMA_BOX_BYTES);
+    const uint4* B = DIAG ? A : A + TMA_BOX_BYTES / 16;
+#pragma unroll
+    for (int q = 0; q < KQ; ++q) {
+      uint4 a[4], b[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int ra = ty + 16 * r, rb = tx + 16 * r;
+        a[r] = A[ra * KQ + (q ^ (ra & 7))];
+        b[r] = B[rb * KQ + (q ^ (rb & 7))];
+      }
+#pragma unroll
+      for (int ri = 0; ri < 4; ++ri) {
+        if ((a[ri].x | a[ri].y | a[ri].z | a[ri].w) == 0u) continue;
+#pragma unroll
+        for (int rj = 0; rj < 4; ++rj) {
+          if (DIAG && rj < ri) continue;
+          csa_quad(acc[ri][rj], a[ri], b[rj]);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + bufi);
+  }
+#pragma unroll
+  for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+    for (int rj = 0; rj < 4; ++rj) {
+      if (DIAG && rj < ri) continue;
+      const int i = ti * PT + ty + 16 * ri, j = tj * PT + tx + 16 * rj;
+      if (i >= N || j >= N) continue;
+      if (DIAG && ri == rj && tx < ty) continue;
+      const unsigned long long v = (unsigned long long)csa_total(acc[ri][rj]);
+      if (v == 0) continue;
+      atomicAdd(inter + (long long)i * N + j, v);
+      if (i != j) atomicAdd(inter + (long long)j * N + i, v);
+    }
+}
+
+__global__ void __launch_bounds__(RING_THREADS, 2)
+pair_iou_st_ring_peer_kernel(const __grid_constant__ PeerMaps maps, int world, int n_local, int box_rows, int nt, int n_tiles, int splits,
+                             long long stage_lo, long long stage_hi, unsigned long long* __restrict__ inter) {
+  extern __shared__ __align__(1024) unsigned char smem_peer[];
+  __shared__ uint64_t full[NSTAGE], empty[NSTAGE];
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < NSTAGE; ++b) { mbar_init(full + b, 1); mbar_init(empty + b, ST_THREADS / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int tile = blockIdx.x % n_tiles, split = blockIdx.x / n_tiles;
+  int ti, tj;
+  tile_from_index(tile, nt, ti, tj);
+  const long long stages = stage_hi - stage_lo;
+  const long long s_begin = stage_lo + stages * split / splits, s_end = stage_lo + stages * (split + 1) / splits;
+  unsigned char* boxes = smem_peer + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_peer) & 1023u)) & 1023u);
+  const int N = world * n_local;
+  if (ti == tj) st_tile_body_ring_peer<true>(&maps, world, n_local, box_rows, N, ti, tj, s_begin, s_end, boxes, full, empty, inter);
+  else st_tile_body_ring_peer<false>(&maps, world, n_local, box_rows, N, ti, tj, s_begin, s_end, boxes, full, empty, inter);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -639,6 +745,55 @@ int sola_pair_iou_st_rows(const uint32_t* const* row_ptrs, int N, long long word
       nullptr, row_ptrs, N, words_per_track, nt, n_tiles, (int)splits, 0, 1, stage_lo, stage_hi,
       reinterpret_cast<unsigned long long*>(inter_out));
   return check_launch("pair_iou_st_rows kernel");
+}
+
+// EXPERIMENTAL (compiled, not yet run on hardware): exchange + K2 in ONE kernel.  bases_host = HOST array of `world` device pointers,
+// rank r's (n_local, words_per_track) packed planes (peer-mapped symmetric memory); part p of n_parts covers its slice of the word
+// axis as in sola_pair_iou_st_rows.  Returns SOLA_ERR_UNSUPPORTED when the shape cannot be tiled (gcd(64, n_local) < 8, world > 8).
+int sola_pair_iou_st_peer(const uint32_t* const* bases_host, int world, int n_local, long long words_per_track, int part, int n_parts,
+                          long long* inter_out, cudaStream_t stream) {
+  SOLA_REQUIRE(bases_host && inter_out && world >= 1 && n_local >= 1 && words_per_track > 0 && words_per_track % 4 == 0,
+               "pair_iou_st_peer: bad arguments");
+  SOLA_REQUIRE(n_parts >= 1 && part >= 0 && part < n_parts, "pair_iou_st_peer: bad partition %d / %d", part, n_parts);
+  int box_rows = PT;
+  while (box_rows > 1 && n_local % box_rows != 0) box_rows >>= 1;
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (world > 8 || box_rows < 8 || !enc || words_per_track >= (1ll << 31)) {
+    set_error("pair_iou_st_peer: unsupported shape (world=%d, n_local=%d) or no TMA encoder", world, n_local);
+    return SOLA_ERR_UNSUPPORTED;
+  }
+  const int N = world * n_local;
+  SOLA_CUDA(cudaMemsetAsync(inter_out, 0, sizeof(long long) * (size_t)N * N, stream));
+  PeerMaps maps;
+  for (int r = 0; r < 8; ++r) {
+    const uint32_t* base = bases_host[r < world ? r : world - 1];
+    SOLA_REQUIRE(base && aligned16(base), "pair_iou_st_peer: rank %d base pointer is null or misaligned", r);
+    const cuuint64_t dims[2] = {(cuuint64_t)words_per_track, (cuuint64_t)n_local};
+    const cuuint64_t strides[1] = {(cuuint64_t)words_per_track * 4};
+    const cuuint32_t box[2] = {STAGE_WORDS, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&maps.m[r], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      set_error("pair_iou_st_peer: cuTensorMapEncodeTiled failed for rank %d", r);
+      return SOLA_ERR_CUDA;
+    }
+  }
+  const int nt = (N + PT - 1) / PT;
+  const int n_tiles = nt * (nt + 1) / 2;
+  const long long all_stages = (words_per_track + STAGE_WORDS - 1) / STAGE_WORDS;
+  const long long stage_lo = all_stages * part / n_parts, stage_hi = all_stages * (part + 1) / n_parts;
+  const long long stages = stage_hi - stage_lo;
+  if (stages <= 0) return SOLA_OK;
+  long long splits = ((long long)num_sms() * 4 + n_tiles - 1) / n_tiles;
+  if (splits > stages) splits = stages;
+  const long long min_splits = (stages + (1 << 20) - 1) >> 20;
+  if (splits < min_splits) splits = min_splits;
+  if (splits < 1) splits = 1;
+  const size_t smem = (size_t)NSTAGE * (2 * PT) * KQ * sizeof(uint4) + 1024;
+  SOLA_CUDA(cudaFuncSetAttribute(pair_iou_st_ring_peer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pair_iou_st_ring_peer_kernel<<<(unsigned)(splits * n_tiles), RING_THREADS, smem, stream>>>(
+      maps, world, n_local, box_rows, nt, n_tiles, (int)splits, stage_lo, stage_hi, reinterpret_cast<unsigned long long*>(inter_out));
+  return check_launch("pair_iou_st_ring_peer kernel");
 }
 
 // inter_inout += the N x N intersections over these words (no memset): lets a caller walk the word axis in chunks — e.g. chunks

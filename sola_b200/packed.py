@@ -368,6 +368,20 @@ def pairwise_inter_matrix_rows(row_ptrs: torch.Tensor, words_per_track: int, par
     return inter
 
 
+def pairwise_inter_matrix_peer(bases: Sequence[int], n_local: int, words_per_track: int, part: int, n_parts: int, device) -> torch.Tensor:
+    """EXPERIMENTAL (not yet run on hardware): one K2 launch whose TMA producer reads every rank's (n_local, words) planes in place —
+    `bases` are the peer-mapped device addresses of the ranks' buffers.  Returns this part's (N, N) int64 share."""
+    import ctypes
+    world = len(bases)
+    arr = (ctypes.c_void_p * world)(*[int(b) for b in bases])
+    N = world * int(n_local)
+    inter = torch.empty((N, N), dtype=torch.int64, device=device)
+    with torch.cuda.device(device):
+        _lib.call("sola_pair_iou_st_peer", ctypes.cast(arr, ctypes.c_void_p), world, int(n_local), int(words_per_track), int(part), int(n_parts),
+                  inter.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
+    return inter
+
+
 def pull_rows(row_ptrs: torch.Tensor, word_lo: int, n_words: int, out: torch.Tensor) -> torch.Tensor:
     """out (N, n_words) int32 <- words [word_lo, word_lo + n_words) of every row of the pointer table (peer rows: over NVLink)."""
     assert row_ptrs.dtype == torch.int64 and row_ptrs.is_cuda and row_ptrs.is_contiguous()

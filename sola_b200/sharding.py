@@ -155,6 +155,8 @@ class PeerPlanes:
                     reduces chunk c on the main stream (`sola_pair_iou_st_accumulate`) — transfer and math overlap chunk by chunk;
       mode="direct" one K2 launch whose stage loads (cp.async) read the peers' rows in place (`sola_pair_iou_st_rows`); every row
                     tile is re-read once per pair tile it belongs to, so NVLink carries ~N/128 times the bytes of "pull".
+      mode="tma"    EXPERIMENTAL (compiled, not yet run on hardware): as "direct" but with the warp-specialised TMA ring, one tensor
+                    map per rank (`sola_pair_iou_st_peer`).
 
         peers = PeerPlanes(n_local, T, h, w, device)             # collective: allocates + rendezvous once
         S.binarize_pack_resize(logits, resized_out=peers.local)  # producers write straight into the shared buffer
@@ -186,6 +188,9 @@ class PeerPlanes:
         self.handle.barrier()                 # every rank's planes are written (stream-ordered device barrier over the signal pads)
         if mode == "direct":
             inter = P.pairwise_inter_matrix_rows(self.row_ptrs, self.words, self.rank, self.world)
+        elif mode == "tma":               # EXPERIMENTAL, not yet run on hardware: the K2 producer's TMA loads read the peers in place
+            inter = P.pairwise_inter_matrix_peer([int(self.handle.buffer_ptrs[r]) for r in range(self.world)], self.n_tracks // self.world,
+                                                 self.words, self.rank, self.world, self.row_ptrs.device)
         else:
             N = self.n_tracks
             inter = torch.zeros((N, N), dtype=torch.int64, device=self.row_ptrs.device)

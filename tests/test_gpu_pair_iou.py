@@ -255,3 +255,19 @@ def test_gdino_unit_end_to_end_config3_shape():
             # the oracle resizes with torch-CPU, the kernel reproduces torch-CUDA: the two ATen kernels may round a 0.5 tie
             # differently on a handful of pixels (tests/test_gpu_resize.py), hence a tolerance on the IoU value only
             assert abs(got["filtered_iou"][pid] - v) < 1e-3
+
+
+@pytest.mark.parametrize("world,n_local", [(3, 16), (2, 64), (4, 8), (1, 40)])
+def test_pairwise_matrix_peer_tma_entry(world, n_local):
+    """sola_pair_iou_st_peer (experimental one-kernel exchange + K2): one tensor map per rank buffer — here `world` separate
+    allocations on one GPU stand in for the peers' NVLink-mapped buffers; the word-axis parts must sum to the full matrix."""
+    import sola_b200 as S
+    rng = np.random.default_rng(world * 100 + n_local)
+    N = world * n_local
+    m = rng.random((N, 2, 24, 64)) > 0.6
+    packed = S.pack_masks(m)
+    words = packed.words[0].numel()
+    bufs = [packed.words[r * n_local:(r + 1) * n_local].clone() for r in range(world)]
+    bases = [b.data_ptr() for b in bufs]
+    shares = [S.packed.pairwise_inter_matrix_peer(bases, n_local, words, p, 2, "cuda").cpu().numpy() for p in range(2)]
+    np.testing.assert_array_equal(sum(shares), _np_inter(m))

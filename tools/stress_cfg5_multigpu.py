@@ -30,7 +30,7 @@ def main():
                                                           "instead of the 540x960 resized masklets the reference filter compares")
     ap.add_argument("--peer", action="store_true", help="fused all-gather + K2: the resized planes are written straight into NVLink-mapped "
                                                         "symmetric memory and every rank's K2 reads its peers' planes directly (no NCCL all-gather)")
-    ap.add_argument("--peer-mode", default="pull", choices=["pull", "direct"])
+    ap.add_argument("--peer-mode", default="pull", choices=["pull", "direct", "tma"])
     ap.add_argument("--chunks", type=int, default=4, help="--peer pull: chunks of the rank's word slice (pull c+1 overlaps K2 on c)")
     ap.add_argument("--split", default="words", choices=["words", "tiles"], help="NCCL variant: all-to-all of word slices (default) or "
                                                                                 "all-gather + round-robin pair tiles")
@@ -86,7 +86,7 @@ def main():
         words = planes.words[0].numel()
         out = {"workload": f"config5-shaped: {args.tracks} tracks x {args.frames} frames x {args.H}x{args.W}", "n_gpus": world,
                "k1r1_fused_ms_max_over_ranks": float(t[0]), "planes": "native" if args.native else "resized 540x960",
-               "exchange": (f"symmetric memory, {args.chunks}-chunk pull over NVLink pipelined with the TMA K2" if args.peer_mode == "pull" else "symmetric memory, peer loads inside K2 (cp.async)") if peers is not None else ("NCCL all-to-all of word slices, then K2" if args.split == "words" else "NCCL all-gather, then K2 on round-robin pair tiles"), "pairwise_ms_max_over_ranks (exchange + K2 share + all-reduce)": float(t[1]),
+               "exchange": (f"symmetric memory, {args.chunks}-chunk pull over NVLink pipelined with the TMA K2" if args.peer_mode == "pull" else ("symmetric memory, peer TMA loads inside the ring K2" if args.peer_mode == "tma" else "symmetric memory, peer loads inside K2 (cp.async)")) if peers is not None else ("NCCL all-to-all of word slices, then K2" if args.split == "words" else "NCCL all-gather, then K2 on round-robin pair tiles"), "pairwise_ms_max_over_ranks (exchange + K2 share + all-reduce)": float(t[1]),
                "masklet_frames_per_s": args.tracks * args.frames / ((float(t[0]) + float(t[1])) * 1e-3),
                "pair_words_per_s": args.tracks * (args.tracks - 1) / 2 * words / (float(t[1]) * 1e-3),
                "symmetric": bool(np.array_equal(m, m.T)), "kept": int(alive.sum())}
