@@ -257,6 +257,8 @@ def test_gdino_unit_end_to_end_config3_shape():
             assert abs(got["filtered_iou"][pid] - v) < 1e-3
 
 
+@pytest.mark.skipif(not __import__("os").environ.get("SOLA_TEST_EXPERIMENTAL"),
+                    reason="sola_pair_iou_st_peer is compiled but not yet validated on hardware; set SOLA_TEST_EXPERIMENTAL=1 to run")
 @pytest.mark.parametrize("world,n_local", [(3, 16), (2, 64), (4, 8), (1, 40)])
 def test_pairwise_matrix_peer_tma_entry(world, n_local):
     """sola_pair_iou_st_peer (experimental one-kernel exchange + K2): one tensor map per rank buffer — here `world` separate
