@@ -80,9 +80,12 @@ def load(build_if_missing: bool = True):
         if path == _build.LIB_PATH and build_if_missing and not _build.is_current():
             try:
                 _build.build()
-            except Exception as e:  # stale-but-present library is still usable on a box without nvcc
+            except Exception as e:  # stale-but-present library is still usable on a box without nvcc — but say so
                 if not os.path.isfile(path):
                     raise SolaError(f"libsola_maskpath.so is missing and could not be built: {e}") from e
+                import warnings
+                warnings.warn(f"sola_b200: csrc/ changed since {path} was built and the rebuild failed ({e}); loading the existing library "
+                              "(a symbol mismatch with include/sola_maskpath.h raises below)", RuntimeWarning)
         if not os.path.isfile(path):
             raise SolaError(f"{path} not found — run `python -m sola_b200._build` (no CPU fallback exists)")
         lib = C.CDLL(path)
