@@ -34,6 +34,7 @@ typedef void* sola_stream_t; /* cudaStream_t */
 int sola_version(void);
 const char* sola_last_error_string(void);
 const char* sola_build_arch(void);               /* "sm_100a" */
+const char* sola_build_digest(void);             /* sha256 of the CUDA sources + flags the library was built from */
 unsigned long long sola_launch_count(void);      /* kernels launched through this library so far (process-wide) */
 
 /* ---- K1: binarise + bit-pack + stability popcounts ---------------------------------------------------------
@@ -164,11 +165,33 @@ int sola_rle_decode_runs(const int* run_plane, const int* run_start, const int* 
 int sola_rle_encode_transitions(const uint32_t* packed, long long n_planes, int H, int W, uint32_t* scratch_colmajor,
                                 int cap, int* out_pos, int* out_n, sola_stream_t stream);
 
-/* ---- boundary F (extension, SURVEY.md §8(b)'s `sola_boundary_f`; no reference implementation — DAVIS definition, see oracle/boundary_oracle.py) --
- * pred, gt packed (n_frames, H, Wp); radius = bound_pix; counts int32 [n_frames] each:
- * n_fg = |bmap(pred)|, n_gt = |bmap(gt)|, fg_match = |bmap(pred) & dilate(bmap(gt))|, gt_match = |bmap(gt) & dilate(bmap(pred))|. */
-int sola_boundary_counts(const uint32_t* pred, const uint32_t* gt, long long n_frames, int H, int W, int radius,
-                         int* n_fg, int* n_gt, int* fg_match, int* gt_match, sola_stream_t stream);
+/* ---- fused J & F: region counts + boundary-match counts in one pass over the packed planes ---------------------------------
+ * replaces  Evaluator.compute_J / compute_F                  evaluator.py:227-247   (rows 0..2: |pred ∩ gt|, |pred|, |gt| per frame)
+ *           the per-expression loop of compute_JF_metrics    evaluator.py:183-218   (one launch for a whole sweep of units)
+ * and adds the boundary measure BASELINE.json's north-star names (seg2bmap + disk dilation + match counting; the reference tree has
+ * no implementation — DAVIS definition, oracle/boundary_oracle.py):
+ *           rows 3..6: |b(pred)|, |b(gt)|, |b(pred) & dilate(b(gt))|, |b(gt) & dilate(b(pred))|, radius = bound_pix.
+ * counts_out is int32 (7, total_frames), frames numbered in unit order.  radius < 0 skips the boundary part (rows 3..6 stay 0).
+ * Limits: radius <= 31, W <= 8192. */
+typedef struct sola_jf_unit {
+  const uint32_t* pred;   /* device, (T, H, Wp) bit-packed prediction planes */
+  const uint32_t* gt;     /* device, (T, H, Wp) bit-packed ground-truth planes */
+  long long out_off;      /* [filled by sola_jf_sweep_plan] column of this unit's frame 0 in counts_out */
+  long long item0;        /* [filled by sola_jf_sweep_plan] first work item of this unit */
+  int T, H, W;
+  int radius;
+  int band_rows, n_bands; /* [filled by sola_jf_sweep_plan] */
+  int reserved0, reserved1;
+} sola_jf_unit;           /* 64 bytes */
+/* host-only: plans the row-band split of every unit (HOST array, updated in place) and the launch's shared-memory layout */
+int sola_jf_sweep_plan(sola_jf_unit* units_host, int n_units, long long* n_items_out, long long* total_frames_out,
+                       int* raw_cap_out, int* bm_cap_out);
+/* units_dev: the planned table copied to the device; the other scalars are the plan's outputs */
+int sola_jf_sweep(const sola_jf_unit* units_dev, int n_units, long long n_items, long long total_frames, int raw_cap, int bm_cap,
+                  int* counts_out, sola_stream_t stream);
+/* one unit, no table: pred, gt (n_frames, H, Wp) -> counts_out int32 (7, n_frames) */
+int sola_jf_boundary_packed(const uint32_t* pred, const uint32_t* gt, long long n_frames, int H, int W, int radius,
+                            int* counts_out, sola_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsola_maskpath.so")
 STAMP = os.path.join(LIB_DIR, "libsola_maskpath.stamp")
 
-SOURCES = ["abi.cu", "binarize_pack.cu", "counts.cu", "pair_iou.cu", "resize.cu", "fused_pack_resize.cu", "boundary.cu", "rle.cu"]
+SOURCES = ["abi.cu", "binarize_pack.cu", "counts.cu", "pair_iou.cu", "resize.cu", "fused_pack_resize.cu", "jf_fused.cu", "rle.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -41,6 +41,10 @@ def _source_digest() -> str:
     return h.hexdigest()
 
 
+def source_digest() -> str:
+    return _source_digest()
+
+
 def is_current() -> bool:
     if not (os.path.isfile(LIB_PATH) and os.path.isfile(STAMP)):
         return False
@@ -62,7 +66,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 return LIB_PATH
             srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.isfile(os.path.join(CSRC, s))]
             tmp = LIB_PATH + f".tmp{os.getpid()}"
-            cmd = [_nvcc(), *NVCC_FLAGS, "-I", CSRC, "-o", tmp, *srcs]
+            # the digest of the sources is compiled in (sola_build_digest()), so the loader can tell a stale library from a current one
+            # even when the stamp file did not travel with it
+            cmd = [_nvcc(), *NVCC_FLAGS, f'-DSOLA_SOURCE_DIGEST="{_source_digest()}"', "-I", CSRC, "-o", tmp, *srcs]
             if verbose:
                 cmd.insert(1, "-Xptxas")
                 cmd.insert(2, "-v")

@@ -16,6 +16,7 @@ SIGNATURES = {
     "sola_version": [],
     "sola_last_error_string": [],
     "sola_build_arch": [],
+    "sola_build_digest": [],
     "sola_launch_count": [],
     "sola_binarize_pack_f32": [_P, _LL, _I, _I, _D, _D, _P, _P, _P, _P, _P],
     "sola_binarize_pack_bf16": [_P, _LL, _I, _I, _D, _D, _P, _P, _P, _P, _P],
@@ -49,11 +50,14 @@ SIGNATURES = {
     "sola_bit_transpose": [_P, _LL, _I, _I, _P, _P],
     "sola_rle_decode_runs": [_P, _P, _P, _LL, _LL, _I, _I, _P, _P, _P],
     "sola_rle_encode_transitions": [_P, _LL, _I, _I, _P, _I, _P, _P, _P],
-    "sola_boundary_counts": [_P, _P, _LL, _I, _I, _I, _P, _P, _P, _P, _P],
+    "sola_jf_sweep_plan": [_P, _I, _P, _P, _P, _P],
+    "sola_jf_sweep": [_P, _I, _LL, _LL, _I, _I, _P, _P],
+    "sola_jf_boundary_packed": [_P, _P, _LL, _I, _I, _I, _P, _P],
 }
 _RESTYPES = {
     "sola_last_error_string": C.c_char_p,
     "sola_build_arch": C.c_char_p,
+    "sola_build_digest": C.c_char_p,
     "sola_launch_count": C.c_ulonglong,
 }
 
@@ -80,12 +84,15 @@ def load(build_if_missing: bool = True):
         if path == _build.LIB_PATH and build_if_missing and not _build.is_current():
             try:
                 _build.build()
-            except Exception as e:  # stale-but-present library is still usable on a box without nvcc — but say so
+            except Exception as e:
                 if not os.path.isfile(path):
                     raise SolaError(f"libsola_maskpath.so is missing and could not be built: {e}") from e
+                # a library older than csrc/ may have another ABI or other numerics under the same symbol names: refuse it
+                if os.environ.get("SOLA_ALLOW_STALE_LIB") != "1":
+                    raise SolaError(f"csrc/ changed since {path} was built and the rebuild failed ({e}); refusing the stale library "
+                                    "(set SOLA_ALLOW_STALE_LIB=1 to load it anyway)") from e
                 import warnings
-                warnings.warn(f"sola_b200: csrc/ changed since {path} was built and the rebuild failed ({e}); loading the existing library "
-                              "(a symbol mismatch with include/sola_maskpath.h raises below)", RuntimeWarning)
+                warnings.warn(f"sola_b200: loading a STALE {path} (SOLA_ALLOW_STALE_LIB=1; rebuild failed: {e})", RuntimeWarning)
         if not os.path.isfile(path):
             raise SolaError(f"{path} not found — run `python -m sola_b200._build` (no CPU fallback exists)")
         lib = C.CDLL(path)
@@ -96,6 +103,11 @@ def load(build_if_missing: bool = True):
         arch = lib.sola_build_arch().decode()
         if arch != "sm_100a":
             raise SolaError(f"library built for {arch}, expected sm_100a")
+        if path == _build.LIB_PATH and os.environ.get("SOLA_ALLOW_STALE_LIB") != "1":
+            built_from, have = lib.sola_build_digest().decode(), _build.source_digest()
+            if built_from != have:
+                raise SolaError(f"{path} was built from other sources (digest {built_from[:12]}, csrc/ is {have[:12]}); rebuild with "
+                                "`python -m sola_b200._build --force` or set SOLA_ALLOW_STALE_LIB=1")
         _lib = lib
         return lib
 

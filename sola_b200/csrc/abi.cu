@@ -37,6 +37,13 @@ const char* sola_last_error_string(void) { return sola::g_err; }
 // Compiled architecture tag, so the loader can refuse a library built for something else.
 const char* sola_build_arch(void) { return "sm_100a"; }
 
+// sha256 of csrc/ + the nvcc flags this library was compiled from (sola_b200/_build.py passes it with -D): the loader compares
+// it with the digest of the sources it sees and refuses a stale library.
+#ifndef SOLA_SOURCE_DIGEST
+#define SOLA_SOURCE_DIGEST "unknown"
+#endif
+const char* sola_build_digest(void) { return SOLA_SOURCE_DIGEST; }
+
 // Number of kernel launches issued by this library in this process (all threads); used by bench.py's gpu_launches.
 unsigned long long sola_launch_count(void) { return __atomic_load_n(&sola::g_launches, __ATOMIC_RELAXED); }
 

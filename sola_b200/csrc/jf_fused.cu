@@ -1,0 +1,454 @@
+// Fused J & F kernel — region counts AND boundary-match counts of (pred, gt) frame pairs from ONE staged tile of the packed planes.
+//
+// Per frame pair it emits the seven integers every J / F flavour on this path is a function of:
+//   [0] |pred ∩ gt|   [1] |pred|   [2] |gt|                    -> Evaluator.compute_J (evaluator.py:227-237: inter / union per frame),
+//                                                                 Evaluator.compute_F (evaluator.py:239-247: tp/fp/fn = Σ[0], Σ[1]-Σ[0], Σ[2]-Σ[0]),
+//                                                                 utils.compute_mask_metrics (track_generation/utils.py:132-174)
+//   [3] |b(pred)|  [4] |b(gt)|  [5] |b(pred) ∩ dil(b(gt))|  [6] |b(gt) ∩ dil(b(pred))|
+//                                                              -> the boundary F-measure BASELINE.json's north-star names (seg2bmap + disk
+//                                                                 dilation + match; no reference implementation — DAVIS definition restated
+//                                                                 in oracle/boundary_oracle.py, parity unpinned)
+// It replaces raw_counts / packed_counts + pack + boundary_counts_kernel (three launches, the planes read three times) in the J&F sweep.
+//
+// Work item = (unit, frame, row band).  A unit is one (video, expression): T frame pairs of one shape; a sweep mixes shapes (MeViS:
+// 360p ... 1080p), so items are enumerated over a device table of units and a persistent grid walks them.  Per item:
+//   load     the band's rows (+ r halo rows each side, + 1 row for the south neighbour) of both planes are ONE contiguous run of
+//            words each: a single elected thread fetches them with two TMA bulk copies (cp.async.bulk, mbarrier completion) — no
+//            registers, no per-thread address math, and the next item's copy is issued as soon as the current tile has been
+//            consumed, so it overlaps the dilation phase;
+//   phase 1  "column walkers": thread = (row sub-band, word column) walks DOWN its rows holding the current row's word and its
+//            east-shifted copy in registers, so every boundary word costs two shared loads per plane (the row below and its
+//            east neighbour), one funnel shift and four LOP3 (b = (s^e)|(s^s')|(s^se), last-row / last-column / corner rules);
+//            region popcounts and boundary popcounts are taken on the way for the rows the band owns; b goes to shared memory;
+//   phase 2  boundary pixels are sparse (object contours), and a word of b(pred) that is zero needs no dilation of b(gt): each warp
+//            scans the owned words, compacts the non-zero ones into a per-warp queue (ballot) and dilates ONLY those, 32 items per
+//            pass with all lanes busy.  The disk is decomposed by column offset k: dil = OR_k shift(±k)(vertical OR of half-height
+//            v[k]); walking k from r down to 0 the vertical extent only grows, so an item costs 6r shared loads + 3r LOP3 for
+//            the running ORs and 2 funnel shifts + 1 LOP3 per k.  Items whose pixels all match inside a radius-2 disk (the common
+//            case when pred ≈ gt) stop after 5 rows.
+// Everything is exact integer arithmetic; pad bits (x >= W) stay zero through every step.
+#include "tma.cuh"
+#include "jf_unit.h"
+#include <string.h>
+
+namespace sola {
+
+constexpr int JF_THREADS = 256;
+constexpr int JF_WARPS = JF_THREADS / 32;
+constexpr int JF_MAX_R = 31;
+constexpr int JF_MAX_WP = 256;                 // one walker per word column: W <= 8192
+constexpr int JF_QUEUE = 96;                   // < 32 left over + at most 64 pushed per scan step
+constexpr int JF_PRE_R = 2;                    // radius of the early-exit pre-test
+
+struct JfGeo {
+  const uint32_t* pred;
+  const uint32_t* gt;
+  long long g0, g1;          // words [g0, g1) of the unit buffers hold the rows this item reads
+  long long total_words;     // T * H * Wp
+  long long out_col;
+  int H, W, Wp, r;           // r < 0: region counts only
+  int y0, y1;                // owned rows
+  int ra;                    // first staged row
+  int NB;                    // boundary-map rows kept: (y1 - y0) + 2r, first one is frame row y0 - r
+  bool bulk;                 // both bases 16-byte aligned -> TMA bulk copies
+};
+
+__device__ __forceinline__ void jf_decode(const sola_jf_unit* __restrict__ units, int n_units, const sola_jf_unit& single,
+                                          long long item, JfGeo& g) {
+  sola_jf_unit u;
+  if (units) {
+    int lo = 0, hi = n_units - 1;                       // last unit with item0 <= item
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&units[mid].item0) <= item) lo = mid; else hi = mid - 1;
+    }
+    u = units[lo];
+  } else {
+    u = single;
+  }
+  const long long local = item - u.item0;
+  const int f = (int)(local / u.n_bands), band = (int)(local - (long long)f * u.n_bands);
+  g.pred = u.pred; g.gt = u.gt;
+  g.H = u.H; g.W = u.W; g.Wp = (u.W + 31) >> 5; g.r = u.radius;
+  const int r = u.radius < 0 ? 0 : u.radius;
+  g.y0 = band * u.band_rows;
+  g.y1 = min(u.H, g.y0 + u.band_rows);
+  g.ra = u.radius < 0 ? g.y0 : max(0, g.y0 - r);
+  const int rb = u.radius < 0 ? g.y1 : min(u.H, g.y1 + r + 1);
+  g.NB = u.radius < 0 ? 0 : (g.y1 - g.y0) + 2 * r;
+  const long long FW = (long long)u.H * g.Wp;
+  g.g0 = (long long)f * FW + (long long)g.ra * g.Wp;
+  g.g1 = (long long)f * FW + (long long)rb * g.Wp;
+  g.total_words = (long long)u.T * FW;
+  g.out_col = u.out_off + f;
+  g.bulk = aligned16(u.pred) && aligned16(u.gt);
+}
+
+// Stage words [g0, g1) of both planes at raw[(w - (g0 & ~3))]: bulk copies over the 16-byte aligned part, plain loads for what is left.
+__device__ __forceinline__ void jf_issue_load(const JfGeo& g, uint32_t* rawP, uint32_t* rawG, uint64_t* bar, int tid) {
+  const long long gs = g.g0 & ~3ll;
+  if (g.bulk) {
+    long long bulk_end = (g.g1 + 3) & ~3ll;                               // may run up to 3 words into the next rows: harmless, in bounds
+    const long long lim = g.total_words & ~3ll;                           // ... unless the buffer ends first
+    if (bulk_end > lim) bulk_end = lim;
+    const long long nbulk = bulk_end > gs ? bulk_end - gs : 0;
+    if (tid == 0) {
+      mbar_expect_tx(bar, (unsigned)(2 * nbulk * 4));
+      if (nbulk > 0) {
+        bulk_load_1d(rawP, g.pred + gs, (unsigned)(nbulk * 4), bar);
+        bulk_load_1d(rawG, g.gt + gs, (unsigned)(nbulk * 4), bar);
+      }
+    }
+    const long long t0 = gs + nbulk;                                      // tail: at most 3 words (plus the < 4-word buffers)
+    for (long long w = t0 + tid; w < g.g1; w += JF_THREADS) {
+      rawP[w - gs] = __ldg(g.pred + w);
+      rawG[w - gs] = __ldg(g.gt + w);
+    }
+  } else {
+    if (tid == 0) mbar_expect_tx(bar, 0u);                                // keep the phase protocol uniform
+    for (long long w = g.g0 + tid; w < g.g1; w += JF_THREADS) {
+      rawP[w - gs] = __ldg(g.pred + w);
+      rawG[w - gs] = __ldg(g.gt + w);
+    }
+  }
+}
+
+// Dilation of the boundary map `src` (pointer to the item's own word, row pitch BP) by the disk (r, v[]), restricted to what the
+// item needs: returns popc(need & dil).  Stops as soon as every needed pixel is matched.
+__device__ __forceinline__ int jf_match_word(const uint32_t* __restrict__ src, int BP, int r, const unsigned char* __restrict__ v,
+                                             const unsigned char* __restrict__ v_pre, uint32_t need) {
+  if (r > JF_PRE_R) {
+    // pre-test: the same decomposition on the radius-2 disk (a subset of the real one): 5 rows instead of 2r+1
+    uint32_t L = src[-1], C = src[0], R = src[1], dil = 0;
+    int vh = 0;
+#pragma unroll
+    for (int k = JF_PRE_R; k >= 0; --k) {
+      const int vk = v_pre[k];
+      while (vh < vk) {
+        ++vh;
+        const uint32_t* up = src - vh * BP; const uint32_t* dn = src + vh * BP;
+        L |= up[-1] | dn[-1]; C |= up[0] | dn[0]; R |= up[1] | dn[1];
+      }
+      dil |= k ? (__funnelshift_l(L, C, k) | __funnelshift_r(C, R, k)) : C;
+    }
+    if ((need & ~dil) == 0u) return __popc(need);
+  }
+  uint32_t L = src[-1], C = src[0], R = src[1], dil = 0;
+  int vh = 0;
+  for (int k = r; k >= 0; --k) {
+    const int vk = v[k];
+    while (vh < vk) {
+      ++vh;
+      const uint32_t* up = src - vh * BP; const uint32_t* dn = src + vh * BP;
+      L |= up[-1] | dn[-1]; C |= up[0] | dn[0]; R |= up[1] | dn[1];
+    }
+    // a source pixel at x-k lands on x (shift towards higher bits, refilled from the left word) and one at x+k on x (the mirror)
+    dil |= k ? (__funnelshift_l(L, C, k) | __funnelshift_r(C, R, k)) : C;
+    if ((need & ~dil) == 0u) return __popc(need);
+  }
+  return __popc(need & dil);
+}
+
+__global__ void __launch_bounds__(JF_THREADS, 2)
+jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_jf_unit single, long long n_items, int raw_cap,
+                int bm_cap, int* __restrict__ counts, long long total_frames) {
+  extern __shared__ __align__(16) uint32_t jf_smem[];
+  uint32_t* rawP = jf_smem;
+  uint32_t* rawG = rawP + raw_cap;
+  uint32_t* bmF = rawG + raw_cap;
+  uint32_t* bmG = bmF + bm_cap;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t queue[JF_WARPS][JF_QUEUE];
+  __shared__ int red[7][JF_WARPS];
+  __shared__ unsigned char vtab[JF_MAX_R + 1], vpre[JF_PRE_R + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  if (tid <= JF_PRE_R) {
+    const int rem = JF_PRE_R * JF_PRE_R - tid * tid;
+    int v = 0;
+    while ((v + 1) * (v + 1) <= rem) ++v;
+    vpre[tid] = (unsigned char)v;
+  }
+  __syncthreads();
+
+  long long item = blockIdx.x;
+  if (item >= n_items) return;
+  JfGeo g, gn;
+  jf_decode(units, n_units, single, item, g);
+  jf_issue_load(g, rawP, rawG, &bar, tid);
+  unsigned parity = 0;
+  int r_cached = -1;
+
+  for (; item < n_items; item += gridDim.x) {
+    const long long next = item + gridDim.x;
+    const bool has_next = next < n_items;
+    if (has_next) jf_decode(units, n_units, single, next, gn);
+    const int Wp = g.Wp, BP = Wp + 2, r = g.r < 0 ? 0 : g.r;
+    const int off = (int)(g.g0 & 3ll);
+    if (g.r >= 0) {
+      if (r != r_cached && tid <= r) {                     // disk table: v[k] = floor(sqrt(r^2 - k^2))
+        const int rem = r * r - tid * tid;
+        int v = 0;
+        while ((v + 1) * (v + 1) <= rem) ++v;
+        vtab[tid] = (unsigned char)v;
+      }
+      r_cached = r;
+      for (int j = tid; j < g.NB; j += JF_THREADS) {       // zero halo columns of both boundary maps
+        bmF[j * BP] = 0u; bmF[j * BP + Wp + 1] = 0u;
+        bmG[j * BP] = 0u; bmG[j * BP + Wp + 1] = 0u;
+      }
+    }
+    __syncthreads();                                        // plain-load words of the tile are visible; previous item fully retired
+    mbar_wait(&bar, parity);
+    parity ^= 1u;
+
+    int n_i = 0, n_p = 0, n_g = 0, n_bf = 0, n_bg = 0, fm = 0, gm = 0;
+    if (g.r < 0) {
+      // region counts only: flat pass over the owned words
+      const int n_words = (g.y1 - g.y0) * Wp;
+      for (int i = tid; i < n_words; i += JF_THREADS) {
+        const uint32_t p = rawP[off + i], q = rawG[off + i];
+        n_p += __popc(p); n_g += __popc(q); n_i += __popc(p & q);
+      }
+    } else {
+      // ---- phase 1: column walkers build both boundary maps ------------------------------------------------------------------
+      const int c = tid % Wp, s = tid / Wp;
+      const int n_sub = min(JF_THREADS / Wp, g.NB);
+      if (s < n_sub) {
+        int j = (int)((long long)s * g.NB / n_sub);
+        const int j_end = (int)((long long)(s + 1) * g.NB / n_sub);
+        int by = g.y0 - r + j;
+        const uint32_t lastbit = (c == Wp - 1) ? (1u << ((g.W - 1) & 31)) : 0u;
+        const bool east = c + 1 < Wp;
+        const int base = off + c - g.ra * Wp;               // raw index of (row y, column c) = base + y * Wp
+        bool have = false;
+        uint32_t p0 = 0, pe0 = 0, q0 = 0, qe0 = 0;
+        for (; j < j_end; ++j, ++by) {
+          uint32_t bp = 0u, bq = 0u;
+          if (by >= 0 && by < g.H) {
+            const int i0 = base + by * Wp;
+            if (!have) {
+              p0 = rawP[i0]; q0 = rawG[i0];
+              const uint32_t pn = east ? rawP[i0 + 1] : 0u, qn = east ? rawG[i0 + 1] : 0u;
+              pe0 = __funnelshift_r(p0, pn, 1); qe0 = __funnelshift_r(q0, qn, 1);
+            }
+            const bool owned = by >= g.y0 && by < g.y1;
+            if (owned) { n_p += __popc(p0); n_g += __popc(q0); n_i += __popc(p0 & q0); }
+            if (by + 1 < g.H) {
+              const uint32_t p1 = rawP[i0 + Wp], q1 = rawG[i0 + Wp];
+              const uint32_t pn = east ? rawP[i0 + Wp + 1] : 0u, qn = east ? rawG[i0 + Wp + 1] : 0u;
+              const uint32_t pe1 = __funnelshift_r(p1, pn, 1), qe1 = __funnelshift_r(q1, qn, 1);
+              const uint32_t ps = p0 ^ p1, qs = q0 ^ q1;
+              bp = (p0 ^ pe0) | ps | (p0 ^ pe1);
+              bq = (q0 ^ qe0) | qs | (q0 ^ qe1);
+              bp = (bp & ~lastbit) | (ps & lastbit);         // last column: seg ^ south only
+              bq = (bq & ~lastbit) | (qs & lastbit);
+              p0 = p1; pe0 = pe1; q0 = q1; qe0 = qe1;
+              have = true;
+            } else {
+              bp = (p0 ^ pe0) & ~lastbit;                    // last row: seg ^ east, corner forced to 0
+              bq = (q0 ^ qe0) & ~lastbit;
+              have = false;
+            }
+            if (owned) { n_bf += __popc(bp); n_bg += __popc(bq); }
+          } else {
+            have = false;
+          }
+          bmF[j * BP + c + 1] = bp;
+          bmG[j * BP + c + 1] = bq;
+        }
+      }
+    }
+    __syncthreads();                                        // boundary maps complete; the raw tile is dead
+    if (has_next) jf_issue_load(gn, rawP, rawG, &bar, tid);  // next tile streams in while this one is matched
+
+    if (g.r >= 0) {
+      // ---- phase 2: dilate only where a boundary pixel needs an answer -------------------------------------------------------
+      const int n_own = (g.y1 - g.y0) * Wp;
+      const unsigned magic = (unsigned)((0x100000000ull + (unsigned)Wp - 1) / (unsigned)Wp);   // idx / Wp == umulhi(idx, magic) for idx * Wp < 2^32
+      const unsigned lt = (1u << lane) - 1u;
+      uint32_t* q = queue[warp];
+      int n = 0;
+      for (int base = warp * 32; base < n_own; base += JF_THREADS) {
+        const int idx = base + lane;
+        const bool valid = idx < n_own;
+        const int row = (int)__umulhi((unsigned)idx, magic), col = idx - row * Wp;
+        const int o = (r + row) * BP + col + 1;
+        const uint32_t bf = valid ? bmF[o] : 0u, bg = valid ? bmG[o] : 0u;
+        const unsigned mF = __ballot_sync(FULL, bf != 0u), mG = __ballot_sync(FULL, bg != 0u);
+        if (bf) q[n + __popc(mF & lt)] = (uint32_t)o;
+        n += __popc(mF);
+        if (bg) q[n + __popc(mG & lt)] = (uint32_t)o | 0x80000000u;
+        n += __popc(mG);
+        __syncwarp();
+        while (n >= 32) {
+          n -= 32;
+          const uint32_t e = q[n + lane];
+          const int eo = (int)(e & 0x7fffffffu);
+          if (e >> 31) gm += jf_match_word(bmF + eo, BP, r, vtab, vpre, bmG[eo]);
+          else fm += jf_match_word(bmG + eo, BP, r, vtab, vpre, bmF[eo]);
+          __syncwarp();
+        }
+      }
+      if (lane < n) {
+        const uint32_t e = q[lane];
+        const int eo = (int)(e & 0x7fffffffu);
+        if (e >> 31) gm += jf_match_word(bmF + eo, BP, r, vtab, vpre, bmG[eo]);
+        else fm += jf_match_word(bmG + eo, BP, r, vtab, vpre, bmF[eo]);
+      }
+    }
+
+    n_i = warp_sum(n_i); n_p = warp_sum(n_p); n_g = warp_sum(n_g);
+    if (g.r >= 0) { n_bf = warp_sum(n_bf); n_bg = warp_sum(n_bg); fm = warp_sum(fm); gm = warp_sum(gm); }
+    if (lane == 0) {
+      red[0][warp] = n_i; red[1][warp] = n_p; red[2][warp] = n_g; red[3][warp] = n_bf; red[4][warp] = n_bg; red[5][warp] = fm; red[6][warp] = gm;
+    }
+    __syncthreads();
+    if (tid < (g.r >= 0 ? 7 : 3)) {
+      int sum = 0;
+#pragma unroll
+      for (int w = 0; w < JF_WARPS; ++w) sum += red[tid][w];
+      if (sum) atomicAdd(counts + (long long)tid * total_frames + g.out_col, sum);
+    }
+    g = gn;
+  }
+}
+
+// ---- host side: row-band plan ------------------------------------------------------------------------------------------------
+struct JfPlan { long long n_items, total_frames; int raw_cap, bm_cap; size_t smem; };
+
+static size_t jf_unit_smem(int Wp, int r, int rows, bool boundary, int* raw_cap, int* bm_cap) {
+  const int rr = boundary ? r : 0;
+  const int rc = (((rows + (boundary ? 2 * rr + 1 : 0)) * Wp + 8) + 3) & ~3;
+  const int bc = boundary ? (rows + 2 * rr) * (Wp + 2) : 0;
+  if (raw_cap) *raw_cap = rc;
+  if (bm_cap) *bm_cap = bc;
+  return (size_t)(2 * rc + 2 * bc) * sizeof(uint32_t);
+}
+
+// Largest band height whose tile fits `budget` bytes; 0 if not even one row fits.
+static int jf_max_band_rows(int H, int Wp, int r, bool boundary, size_t budget) {
+  int lo = 0, hi = H;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) / 2;
+    if (jf_unit_smem(Wp, r, mid, boundary, nullptr, nullptr) <= budget) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+constexpr size_t JF_BUDGET_2CTA = 100 * 1024;     // two resident CTAs per SM: one loads / walks while the other dilates
+constexpr size_t JF_BUDGET_1CTA = 200 * 1024;     // tall halos (1080p: r = 18): fewer, taller bands beat occupancy
+
+static int jf_plan(sola_jf_unit* units, int n_units, JfPlan* plan) {
+  // one budget for the whole launch: the small one unless some unit would then spend > 30 % of its rows on halo
+  size_t budget = JF_BUDGET_2CTA;
+  for (int pass = 0; pass < 2; ++pass) {
+    bool retry = false;
+    long long items = 0, frames = 0;
+    int raw_cap = 4, bm_cap = 0;
+    for (int i = 0; i < n_units; ++i) {
+      sola_jf_unit& u = units[i];
+      SOLA_REQUIRE(u.T >= 0 && u.H > 0 && u.W > 0, "jf_sweep: unit %d has a bad shape T=%d H=%d W=%d", i, u.T, u.H, u.W);
+      SOLA_REQUIRE(u.T == 0 || (u.pred && u.gt), "jf_sweep: unit %d has a null plane pointer", i);
+      const int Wp = (u.W + 31) >> 5;
+      const bool boundary = u.radius >= 0;
+      if (u.radius > JF_MAX_R || Wp > JF_MAX_WP) {
+        set_error("jf_sweep: unit %d unsupported (radius %d > %d or width %d > %d)", i, u.radius, JF_MAX_R, u.W, JF_MAX_WP * 32);
+        return SOLA_ERR_UNSUPPORTED;
+      }
+      const int bmax = jf_max_band_rows(u.H, Wp, u.radius, boundary, budget);
+      if (bmax < 1) {
+        if (pass == 0) { retry = true; break; }
+        set_error("jf_sweep: unit %d (%dx%d, radius %d) does not fit shared memory", i, u.H, u.W, u.radius);
+        return SOLA_ERR_UNSUPPORTED;
+      }
+      u.n_bands = (u.H + bmax - 1) / bmax;
+      u.band_rows = (u.H + u.n_bands - 1) / u.n_bands;
+      u.n_bands = (u.H + u.band_rows - 1) / u.band_rows;
+      if (pass == 0 && boundary && u.n_bands > 1 && (2 * u.radius + 1) * 10 > 3 * u.band_rows) { retry = true; break; }
+      u.item0 = items;
+      u.out_off = frames;
+      items += (long long)u.T * u.n_bands;
+      frames += u.T;
+      int rc, bc;
+      jf_unit_smem(Wp, u.radius, u.band_rows, boundary, &rc, &bc);
+      if (rc > raw_cap) raw_cap = rc;
+      if (bc > bm_cap) bm_cap = bc;
+    }
+    if (retry) { budget = JF_BUDGET_1CTA; continue; }
+    plan->n_items = items; plan->total_frames = frames; plan->raw_cap = raw_cap; plan->bm_cap = bm_cap;
+    plan->smem = (size_t)(2 * raw_cap + 2 * bm_cap) * sizeof(uint32_t);
+    return SOLA_OK;
+  }
+  return SOLA_ERR_UNSUPPORTED;
+}
+
+static int jf_launch(const sola_jf_unit* units_dev, int n_units, const sola_jf_unit& single, long long n_items, long long total_frames,
+                     int raw_cap, int bm_cap, int* counts_out, cudaStream_t stream) {
+  if (total_frames <= 0) return SOLA_OK;
+  SOLA_REQUIRE(counts_out, "jf_sweep: null output");
+  SOLA_CUDA(cudaMemsetAsync(counts_out, 0, sizeof(int) * 7 * (size_t)total_frames, stream));
+  if (n_items <= 0) return SOLA_OK;
+  const size_t smem = (size_t)(2 * raw_cap + 2 * bm_cap) * sizeof(uint32_t);
+  SOLA_REQUIRE(raw_cap % 4 == 0 && smem <= 220 * 1024, "jf_sweep: bad shared-memory plan (raw_cap %d, bm_cap %d)", raw_cap, bm_cap);
+  SOLA_CUDA(cudaFuncSetAttribute(jf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jf_fused_kernel, JF_THREADS, smem);
+  if (occ < 1) occ = 1;
+  long long grid = (long long)num_sms() * occ;
+  if (grid > n_items) grid = n_items;
+  jf_fused_kernel<<<(unsigned)grid, JF_THREADS, smem, stream>>>(units_dev, n_units, single, n_items, raw_cap, bm_cap, counts_out, total_frames);
+  return check_launch("jf_fused kernel");
+}
+
+}  // namespace sola
+
+using namespace sola;
+
+extern "C" {
+
+// Host-only: fills band_rows / n_bands / item0 / out_off of every unit (frames are numbered in unit order) and reports the launch plan.
+int sola_jf_sweep_plan(sola_jf_unit* units_host, int n_units, long long* n_items_out, long long* total_frames_out, int* raw_cap_out,
+                       int* bm_cap_out) {
+  SOLA_REQUIRE(n_units >= 0 && (n_units == 0 || units_host), "jf_sweep_plan: bad arguments");
+  SOLA_REQUIRE(n_items_out && total_frames_out && raw_cap_out && bm_cap_out, "jf_sweep_plan: null output");
+  JfPlan p{0, 0, 4, 0, 0};
+  if (n_units > 0) {
+    const int rc = jf_plan(units_host, n_units, &p);
+    if (rc != SOLA_OK) return rc;
+  }
+  *n_items_out = p.n_items; *total_frames_out = p.total_frames; *raw_cap_out = p.raw_cap; *bm_cap_out = p.bm_cap;
+  return SOLA_OK;
+}
+
+// counts_out int32 (7, total_frames): rows = inter, |pred|, |gt|, |b(pred)|, |b(gt)|, fg_match, gt_match (rows 3..6 stay 0 for units
+// planned with radius < 0).  units_dev = the planned table copied to the device.
+int sola_jf_sweep(const sola_jf_unit* units_dev, int n_units, long long n_items, long long total_frames, int raw_cap, int bm_cap,
+                  int* counts_out, cudaStream_t stream) {
+  SOLA_REQUIRE(n_units >= 0 && n_items >= 0 && total_frames >= 0, "jf_sweep: bad arguments");
+  if (n_units == 0 || total_frames == 0) return SOLA_OK;
+  SOLA_REQUIRE(units_dev, "jf_sweep: null unit table");
+  sola_jf_unit none;
+  memset(&none, 0, sizeof(none));
+  return jf_launch(units_dev, n_units, none, n_items, total_frames, raw_cap, bm_cap, counts_out, stream);
+}
+
+// One unit, no table: pred, gt (n_frames, H, Wp) -> counts_out int32 (7, n_frames).  radius < 0: region counts only.
+int sola_jf_boundary_packed(const uint32_t* pred, const uint32_t* gt, long long n_frames, int H, int W, int radius, int* counts_out,
+                            cudaStream_t stream) {
+  SOLA_REQUIRE(n_frames >= 0 && n_frames < (1ll << 31) && H > 0 && W > 0, "jf_boundary_packed: bad shape");
+  if (n_frames == 0) return SOLA_OK;
+  SOLA_REQUIRE(pred && gt && counts_out, "jf_boundary_packed: null pointer");
+  sola_jf_unit u;
+  memset(&u, 0, sizeof(u));
+  u.pred = pred; u.gt = gt; u.T = (int)n_frames; u.H = H; u.W = W; u.radius = radius;
+  JfPlan p{0, 0, 4, 0, 0};
+  const int rc = jf_plan(&u, 1, &p);
+  if (rc != SOLA_OK) return rc;
+  return jf_launch(nullptr, 1, u, p.n_items, p.total_frames, p.raw_cap, p.bm_cap, counts_out, stream);
+}
+
+}  // extern "C"

@@ -64,6 +64,9 @@ class GreedyState:
                     self.status[k] = NOT_TRACKED
                     self.members.append(k)
         self.frame_idx = np.array([p["frame_idx"] for p in self.prompts], dtype=np.int64)
+        if self.frame_idx.size and (self.frame_idx.min() < 0 or self.frame_idx.max() >= n_frames):
+            # masklets[prompt_id][frame_idx] raises in the reference (generate_tokens_grid.py:273); never compare against a wrong frame
+            raise IndexError(f"prompt frame_idx outside [0, {n_frames}): min {self.frame_idx.min()}, max {self.frame_idx.max()}")
         self._members_arr = np.asarray(self.members, dtype=np.int64)
 
     # -- batching ------------------------------------------------------------------------------------------------
@@ -264,6 +267,8 @@ class VideoDedupJob:
         self.mode, self.rules = mode, rules
         self.device = P._dev(device)
         self.frame_idx = np.array([p["frame_idx"] for p in self.prompt_meta], dtype=np.int32)
+        if self.frame_idx.size and (self.frame_idx.min() < 0 or self.frame_idx.max() >= n_frames):
+            raise IndexError(f"prompt frame_idx outside [0, {n_frames})")
         self.frame_idx_dev = P.to_device(self.frame_idx, device=self.device)
         self.event = torch.cuda.Event()
         self._host = None

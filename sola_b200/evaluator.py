@@ -98,58 +98,70 @@ def compute_F_boundary(pred_masklet, gt_masklet, bound_th: float = 0.008) -> flo
     return F_boundary_from_counts(c[0], c[1], c[2], c[3])
 
 
-class JFSweep:
-    """Batched J&F over many (video, expression) units of different shapes: masks are uploaded as uint8 (1 B/px
-    instead of the reference's fp32 4 B/px, evaluator.py:199-200), counted on the device, and read back ONCE.
+def compute_JF_all(pred_masklet, gt_masklet, bound_th: float = 0.008):
+    """(J, F_ref_dice, F_boundary) of one unit from ONE launch of the fused kernel (csrc/jf_fused.cu) and one read-back:
+    J per evaluator.py:227-237, F per evaluator.py:239-247, F_boundary per the DAVIS definition (oracle/boundary_oracle.py)."""
+    pp = pred_masklet if isinstance(pred_masklet, P.PackedMasks) else P.pack_masks(pred_masklet)
+    gp = gt_masklet if isinstance(gt_masklet, P.PackedMasks) else P.pack_masks(gt_masklet)
+    c = P.jf_boundary_counts(pp, gp, bound_th).cpu().numpy()
+    return (float(J_from_counts(c[0], c[1], c[2])), float(F_from_counts(c[0], c[1], c[2])),
+            F_boundary_from_counts(c[3], c[4], c[5], c[6]))
 
-    add() enqueues; finish() synchronises and returns the per-unit results in insertion order plus the integer
-    accumulators that make multi-GPU reductions bit-reproducible."""
+
+def _as_packed(m, device) -> P.PackedMasks:
+    """A masklet in any accepted form -> (T, H, Wp) PackedMasks on `device` (uint8 / bool / fp32 arrays are uploaded as they are
+    — 1 B/px for the dataloader's uint8 masks instead of the reference's fp32 4 B/px, evaluator.py:199-200 — and bit-packed there)."""
+    if isinstance(m, P.PackedMasks):
+        return m if m.words.dim() == 3 else m.reshape_lead(m.n_frames)
+    x = P.to_device(m, device=device)
+    if x.dim() == 2:
+        x = x[None]
+    return P.pack_masks(x)
+
+
+class JFSweep:
+    """Batched J&F over many (video, expression) units of different shapes.  add() uploads / bit-packs a unit and returns
+    immediately; finish() runs ONE launch of the fused J&F kernel over every unit added (region counts and, with
+    `with_boundary`, the boundary-match counts from the same staged tile), reads the (7, total_frames) count table back ONCE and
+    evaluates the reference's formulas on the host in float64.  It also returns the integer accumulators
+    [Σ inter, Σ|pred|, Σ|gt|] that make multi-GPU reductions bit-reproducible."""
 
     def __init__(self, device=None, with_boundary: bool = False, bound_th: float = 0.008):
         self.device = P._dev(device)
         self.with_boundary = with_boundary
         self.bound_th = bound_th
-        self._keys, self._counts, self._bcounts = [], [], []
+        self._keys, self._pairs = [], []
 
     def add(self, key, pred_masklet, gt_masklet) -> None:
         """pred_masklet None reproduces evaluator.py:194-197 (J = F = JF = 0)."""
         self._keys.append(key)
         if pred_masklet is None:
-            self._counts.append(None)
-            self._bcounts.append(None)
+            self._pairs.append(None)
             return
-        p = P.to_device(pred_masklet, device=self.device)
-        g = P.to_device(gt_masklet, device=self.device)
-        self._counts.append(P.frame_counts(p, g))
-        if self.with_boundary:
-            self._bcounts.append(P.boundary_counts(P.pack_masks(p), P.pack_masks(g), self.bound_th))
-        else:
-            self._bcounts.append(None)
+        p, g = _as_packed(pred_masklet, self.device), _as_packed(gt_masklet, self.device)
+        assert (p.H, p.W) == (g.H, g.W) and p.n_frames == g.n_frames, f"pred / gt masklets differ in shape for {key!r}"
+        self._pairs.append((p, g))
 
     def finish(self):
-        live = [c for c in self._counts if c is not None]
-        flat = torch.cat(live, dim=1).cpu().numpy() if live else np.zeros((3, 0), np.int32)
-        bflat = None
-        if self.with_boundary:
-            blive = [c for c in self._bcounts if c is not None]
-            bflat = torch.cat(blive, dim=1).cpu().numpy() if blive else np.zeros((4, 0), np.int32)
-        results, pos = [], 0
+        live = [pg for pg in self._pairs if pg is not None]
+        plan = P.JFSweepPlan(live, with_boundary=self.with_boundary, bound_th=self.bound_th)
+        flat = plan.run().cpu().numpy() if live else np.zeros((7, 0), np.int32)
+        results, k = [], 0
         totals = np.zeros(3, dtype=np.int64)
-        for key, c in zip(self._keys, self._counts):
-            if c is None:
+        for key, pg in zip(self._keys, self._pairs):
+            if pg is None:
                 results.append((key, {"J": 0.0, "F": 0.0, "JF": 0.0}))
                 continue
-            T = c.shape[1]
+            pos, T = plan.offsets[k], plan.frames[k]
+            k += 1
             u = flat[:, pos:pos + T]
             J, F = float(J_from_counts(u[0], u[1], u[2])), float(F_from_counts(u[0], u[1], u[2]))
             rec = {"J": J, "F": F, "JF": (J + F) / 2}
-            if bflat is not None:
-                b = bflat[:, pos:pos + T]
-                rec["F_boundary"] = F_boundary_from_counts(b[0], b[1], b[2], b[3])
-            totals += u.sum(axis=1, dtype=np.int64)
+            if self.with_boundary:
+                rec["F_boundary"] = F_boundary_from_counts(u[3], u[4], u[5], u[6])
+            totals += u[:3].sum(axis=1, dtype=np.int64)
             results.append((key, rec))
-            pos += T
-        self._keys, self._counts, self._bcounts = [], [], []
+        self._keys, self._pairs = [], []
         return results, totals
 
 

@@ -159,7 +159,9 @@ def binarize_pack_resize(logits, mask_threshold: float = 0.0, threshold_offset: 
     packed = None
     if want_packed or not fusable:
         packed = out if out is not None else PackedMasks.empty(lead, H, W, x.device)
-        assert packed.words.is_contiguous() and packed.n_frames == n
+        assert packed.words.is_contiguous() and packed.n_frames == n and (packed.H, packed.W) == (H, W), \
+            f"out= must be contiguous ({n} frames, {H}x{W}); got {packed.n_frames} frames, {packed.H}x{packed.W}"
+        assert packed.words.device == x.device
     resized = resized_out if resized_out is not None else PackedMasks.empty(lead, oh, ow, x.device)
     assert resized.words.is_contiguous() and resized.n_frames == n and (resized.H, resized.W) == (oh, ow)
     counts = counts_out if counts_out is not None else torch.empty((3, n), dtype=torch.int32, device=x.device)
@@ -229,7 +231,11 @@ def unpack_masks(packed: PackedMasks, dtype=torch.float32, one_value: int = 1) -
 def frame_counts(a, b) -> torch.Tensor:
     """Raw {0,1} planes a, b of identical shape (T, H, W) or (H, W), fp32 or uint8 -> int32 (3, T) device
     tensor [inter, area_a, area_b] per frame, in ONE pass over both inputs."""
-    a, b = to_device(a), to_device(b, device=a.device if isinstance(a, torch.Tensor) and a.is_cuda else None)
+    # both operands on ONE device: a CUDA input's device wins, else the current device
+    dev = next((t.device for t in (a, b) if isinstance(t, torch.Tensor) and t.is_cuda), None)
+    a, b = to_device(a, device=dev), to_device(b, device=dev)
+    if b.device != a.device:
+        b = b.to(a.device)
     assert a.shape == b.shape, f"shape mismatch {tuple(a.shape)} vs {tuple(b.shape)}"
     if a.dtype != b.dtype or a.dtype not in (torch.float32, torch.uint8):
         both_u8 = a.dtype == torch.uint8 and b.dtype == torch.uint8
@@ -422,6 +428,12 @@ def gathered_inter(tracks: PackedMasks, prompts: PackedMasks, frame_idx) -> torc
         tw = tw[None]
     N, T = int(tw.shape[0]), int(tw.shape[1])
     P = int(pw.shape[0])
+    if not (isinstance(frame_idx, torch.Tensor) and frame_idx.is_cuda):
+        # the reference indexes masklets[prompt_id][frame_idx] (generate_tokens_grid.py:273): out of range raises there, so it must
+        # here too (device-resident index tensors are validated by their owner, dedup.GreedyState; the kernel clamps for memory safety)
+        fi_host = np.asarray(frame_idx.cpu() if isinstance(frame_idx, torch.Tensor) else frame_idx, dtype=np.int64)
+        if fi_host.size and (fi_host.min() < 0 or fi_host.max() >= T):
+            raise IndexError(f"frame_idx out of range for masklets of {T} frames: min {fi_host.min()}, max {fi_host.max()}")
     fi = to_device(np.asarray(frame_idx, dtype=np.int32) if not isinstance(frame_idx, torch.Tensor) else frame_idx.to(torch.int32), device=tw.device)
     assert fi.numel() == P
     out = torch.empty((3, N, P), dtype=torch.int32, device=tw.device)
@@ -490,22 +502,93 @@ def resize_nearest(mask, oh: int, ow: int) -> PackedMasks:
 
 
 # ---------------------------------------------------------------------------------------------------------
-# boundary F (extension)
+# fused J & F (region counts + boundary-match counts)
 # ---------------------------------------------------------------------------------------------------------
+
+def bound_pix_for(H: int, W: int, bound_th: float = 0.008) -> int:
+    """DAVIS rule: bound_th >= 1 is a pixel radius, else a fraction of the frame diagonal (ceil)."""
+    import math
+    return int(bound_th) if bound_th >= 1 else int(math.ceil(bound_th * math.sqrt(H * H + W * W)))
+
+
+import ctypes as _C
+
+
+class JfUnit(_C.Structure):
+    """ctypes mirror of `sola_jf_unit` (include/sola_maskpath.h): 64 bytes."""
+    _fields_ = [("pred", _C.c_void_p), ("gt", _C.c_void_p), ("out_off", _C.c_longlong), ("item0", _C.c_longlong),
+                ("T", _C.c_int), ("H", _C.c_int), ("W", _C.c_int), ("radius", _C.c_int),
+                ("band_rows", _C.c_int), ("n_bands", _C.c_int), ("reserved0", _C.c_int), ("reserved1", _C.c_int)]
+
+
+assert _C.sizeof(JfUnit) == 64
+
+
+class JFSweepPlan:
+    """A planned J&F sweep over units of different shapes: ONE launch of the fused kernel for all of them.
+
+        plan = JFSweepPlan([(pred0, gt0), (pred1, gt1), ...], with_boundary=True)      # PackedMasks pairs, (T_u, H_u, Wp_u) each
+        counts = plan.run()          # int32 (7, total_frames) on the device; frames in unit order, plan.offsets[u] = first column of unit u
+
+    The plan keeps references to the planes; run() may be called repeatedly (the bench times it)."""
+
+    def __init__(self, pairs: Sequence[Tuple["PackedMasks", "PackedMasks"]], with_boundary: bool = True, bound_th: float = 0.008):
+        self.pairs = []
+        self.device = None
+        n = len(pairs)
+        arr = (JfUnit * max(n, 1))()
+        for k, (p, g) in enumerate(pairs):
+            assert isinstance(p, PackedMasks) and isinstance(g, PackedMasks)
+            assert (p.H, p.W) == (g.H, g.W) and p.n_frames == g.n_frames, "pred / gt shape mismatch"
+            pw, gw = p.words.contiguous(), g.words.contiguous()
+            assert pw.is_cuda and gw.device == pw.device
+            if self.device is None:
+                self.device = pw.device
+            assert pw.device == self.device, "all units of a sweep must live on one device"
+            self.pairs.append((pw, gw))
+            u = arr[k]
+            u.pred, u.gt = pw.data_ptr(), gw.data_ptr()
+            u.T, u.H, u.W = p.n_frames, p.H, p.W
+            u.radius = bound_pix_for(p.H, p.W, bound_th) if with_boundary else -1
+        self.n_units = n
+        n_items, total, raw_cap, bm_cap = _C.c_longlong(0), _C.c_longlong(0), _C.c_int(0), _C.c_int(0)
+        _lib.call("sola_jf_sweep_plan", _C.cast(arr, _C.c_void_p), n, _C.byref(n_items), _C.byref(total), _C.byref(raw_cap), _C.byref(bm_cap))
+        self.n_items, self.total_frames, self.raw_cap, self.bm_cap = n_items.value, total.value, raw_cap.value, bm_cap.value
+        self.offsets = [arr[k].out_off for k in range(n)]
+        self.frames = [arr[k].T for k in range(n)]
+        self.bands = [(arr[k].band_rows, arr[k].n_bands) for k in range(n)]
+        self.units_dev = None
+        if n:
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)[: 64 * n].clone()
+            self.units_dev = host.to(self.device)
+        self.algorithmic_bytes = sum(2 * pw.numel() * 4 for pw, _ in self.pairs)
+
+    def run(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        dev = self.device if self.device is not None else _dev()
+        if out is None:
+            out = torch.empty((7, self.total_frames), dtype=torch.int32, device=dev)
+        assert out.shape == (7, self.total_frames) and out.dtype == torch.int32 and out.is_contiguous()
+        if self.n_units == 0 or self.total_frames == 0:
+            return out
+        with torch.cuda.device(dev):
+            _lib.call("sola_jf_sweep", self.units_dev.data_ptr(), self.n_units, self.n_items, self.total_frames, self.raw_cap, self.bm_cap,
+                      out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        return out
+
+
+def jf_boundary_counts(pred: PackedMasks, gt: PackedMasks, bound_th: float = 0.008, with_boundary: bool = True) -> torch.Tensor:
+    """One unit through the fused J&F kernel: int32 (7, n_frames) device tensor
+    [|pred ∩ gt|, |pred|, |gt|, |b(pred)|, |b(gt)|, fg_match, gt_match] (rows 3..6 zero when with_boundary is False)."""
+    assert (pred.H, pred.W) == (gt.H, gt.W) and pred.n_frames == gt.n_frames
+    pw, gw = pred.words.contiguous(), gt.words.contiguous()
+    n = pred.n_frames
+    r = bound_pix_for(pred.H, pred.W, bound_th) if with_boundary else -1
+    out = torch.empty((7, n), dtype=torch.int32, device=pw.device)
+    with torch.cuda.device(pw.device):
+        _lib.call("sola_jf_boundary_packed", pw.data_ptr(), gw.data_ptr(), n, pred.H, pred.W, r, out.data_ptr(), _stream(pw))
+    return out
+
 
 def boundary_counts(pred: PackedMasks, gt: PackedMasks, bound_th: float = 0.008) -> torch.Tensor:
     """int32 (4, n_frames) device tensor: n_fg, n_gt, fg_match, gt_match (DAVIS boundary measure)."""
-    import math
-    assert (pred.H, pred.W) == (gt.H, gt.W) and pred.n_frames == gt.n_frames
-    H, W = pred.H, pred.W
-    r = int(bound_th) if bound_th >= 1 else int(math.ceil(bound_th * math.sqrt(H * H + W * W)))
-    pw, gw = pred.words.contiguous(), gt.words.contiguous()
-    n = pred.n_frames
-    out = torch.empty((4, n), dtype=torch.int32, device=pw.device)
-    with torch.cuda.device(pw.device):
-        for s in range(0, n, 65535):
-            e = min(n, s + 65535)
-            fw = pred.frame_words
-            _lib.call("sola_boundary_counts", pw.data_ptr() + 4 * s * fw, gw.data_ptr() + 4 * s * fw, e - s, H, W, r,
-                      out[0, s:].data_ptr(), out[1, s:].data_ptr(), out[2, s:].data_ptr(), out[3, s:].data_ptr(), _stream(pw))
-    return out
+    return jf_boundary_counts(pred, gt, bound_th)[3:7]

@@ -99,3 +99,54 @@ def dedup_candidates(n: int, T: int, H: int, W: int, seed: int, device="cpu", *,
         prompts.append({"prompt_id": rank, "source": i, "frame_idx": int(frame_idx[i]), "segmentation": segs[i],
                         "area": int(areas[i])})
     return logits[torch.as_tensor(order, device=device)], prompts
+
+
+MEVIS_SHAPES = [(360, 640), (480, 854), (720, 1280), (1080, 1920)]        # MeViS valid_u mixes 360p ... 1080p (recalled)
+
+
+def object_pair(T: int, H: int, W: int, seed: int, device="cpu", *, shift: int = 3, level: float = 0.05, speckle: float = 0.0,
+                empty_frames: int = 1):
+    """(pred, gt) uint8 masklets whose errors look like a tracker's, not like noise: the prediction is the same smooth object field
+    cut at a slightly different level and displaced by up to `shift` px (IoU ~0.8-0.95, contours a few pixels apart), optionally
+    with a little speckle; a few frames are empty in both (union == 0 rule)."""
+    g = _gen(seed, device)
+    cell = max(24, min(H, W) // 6)
+    z = torch.randn((1, 1, H // cell + 4, W // cell + 4), generator=g, device=device)
+    big = torch.nn.functional.interpolate(z, size=(H + 64, W + 64), mode="bicubic", align_corners=False)[0, 0]
+    thr = torch.quantile(big.flatten()[:: max(1, big.numel() // 65536)].float(), 0.75)
+    walk = torch.cumsum(torch.randn((T, 2), generator=g, device=device) * 2.0, dim=0)
+    walk = (walk - walk.mean(0)).clamp(-24, 24).round().long() + 32
+    d = torch.randint(-shift, shift + 1, (T, 2), generator=g, device=device)
+    gt = torch.stack([big[walk[t, 0]: walk[t, 0] + H, walk[t, 1]: walk[t, 1] + W] > thr for t in range(T)])
+    pred = torch.stack([big[walk[t, 0] + d[t, 0]: walk[t, 0] + d[t, 0] + H, walk[t, 1] + d[t, 1]: walk[t, 1] + d[t, 1] + W] > thr + level
+                        for t in range(T)])
+    if speckle > 0:
+        pred = pred ^ (torch.rand((T, H, W), generator=g, device=device) < speckle)
+    gt, pred = gt.to(torch.uint8), pred.to(torch.uint8)
+    for t in range(min(empty_frames, max(T - 1, 0))):
+        k = (t * 7 + 3) % T
+        gt[k] = 0
+        pred[k] = 0
+    return pred, gt
+
+
+def mevis_like_sweep(n_videos: int, exprs_per_video: int, seed: int, device="cpu", *, t_range=(30, 200), shapes=None, pack=None):
+    """BASELINE config 4 shape: a J&F evaluation sweep over `n_videos` multi-object videos of mixed resolution and length, each with
+    `exprs_per_video` (video, expression) units.  Returns [(video_id, expression_id, pred, gt)] with uint8 (T, H, W) masklets, or —
+    when `pack` (a callable such as sola_b200.pack_masks) is given — bit-packed planes, built unit by unit so the full-size sweep never
+    holds more than one unit unpacked."""
+    rng = np.random.default_rng(seed)
+    shapes = shapes or MEVIS_SHAPES
+    units = []
+    for v in range(n_videos):
+        H, W = shapes[int(rng.integers(0, len(shapes)))]
+        T = int(rng.integers(t_range[0], t_range[1] + 1))
+        for e in range(exprs_per_video):
+            pred, gt = object_pair(T, H, W, seed * 7919 + v * 131 + e, device, shift=int(rng.integers(0, 5)),
+                                   level=float(rng.uniform(-0.08, 0.08)), empty_frames=int(rng.integers(0, 3)))
+            if rng.random() < 0.05:
+                pred = torch.zeros_like(pred)                      # nothing selected: zero planes (dataloader.py:346-349) -> tp == 0 rule
+            if pack is not None:
+                pred, gt = pack(pred), pack(gt)
+            units.append((f"v{v:03d}", f"{e}", pred, gt))
+    return units

@@ -1,7 +1,7 @@
 /* Pure-C client of libsola_maskpath.so: no Python, no torch — the drop-in boundary is a C ABI.
  * Build: nvcc (or gcc + -lcudart) tests/c_abi_smoke.c -Iinclude -Lsola_b200/lib -lsola_maskpath -o c_abi_smoke
- * Checks K1 (planes + the three stability counts), K3 (per-frame counts), the J&F accumulators and the fused K1+R1 entry point
- * against plain C loops. */
+ * Checks K1 (planes + the three stability counts), K3 (per-frame counts), the J&F accumulators, the fused J&F sweep (unit table)
+ * and the fused K1+R1 entry point against plain C loops. */
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -83,6 +83,43 @@ int main(void) {
   uint32_t *h1 = (uint32_t*)malloc((size_t)n * oh * owp * 4), *h2 = (uint32_t*)malloc((size_t)n * oh * owp * 4);
   CK(cudaMemcpy(h1, r_fused, (size_t)n * oh * owp * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(h2, r_two, (size_t)n * oh * owp * 4, cudaMemcpyDeviceToHost));
   if (memcmp(h1, h2, (size_t)n * oh * owp * 4) != 0) { printf("fused != K1 then R1\n"); return 1; }
+  /* fused J&F sweep through the unit table: the struct layout as a C client sees it; region rows and |b(pred)| vs plain C loops */
+  {
+    uint32_t* packed_b; int* jf; sola_jf_unit unit, *unit_dev; long long n_items = 0, total = 0; int raw_cap = 0, bm_cap = 0;
+    CK(cudaMalloc((void**)&packed_b, (size_t)n * H * Wp * 4));
+    rc = sola_threshold_pack_f32(d, n, H, W, 0.5, packed_b, NULL, 0);
+    if (rc) { printf("sola_threshold_pack_f32: %s\n", sola_last_error_string()); return 1; }
+    memset(&unit, 0, sizeof(unit));
+    unit.pred = packed; unit.gt = packed_b; unit.T = n; unit.H = H; unit.W = W; unit.radius = 2;
+    if (sizeof(sola_jf_unit) != 64) { printf("sola_jf_unit is %zu bytes\n", sizeof(sola_jf_unit)); return 1; }
+    rc = sola_jf_sweep_plan(&unit, 1, &n_items, &total, &raw_cap, &bm_cap);
+    if (rc || total != n || n_items < n) { printf("sola_jf_sweep_plan: %s\n", sola_last_error_string()); return 1; }
+    CK(cudaMalloc((void**)&unit_dev, sizeof(unit))); CK(cudaMemcpy(unit_dev, &unit, sizeof(unit), cudaMemcpyHostToDevice));
+    CK(cudaMalloc((void**)&jf, 7 * n * sizeof(int)));
+    rc = sola_jf_sweep(unit_dev, 1, n_items, total, raw_cap, bm_cap, jf, 0);
+    if (rc) { printf("sola_jf_sweep: %s\n", sola_last_error_string()); return 1; }
+    int hjf[21];
+    CK(cudaMemcpy(hjf, jf, sizeof(hjf), cudaMemcpyDeviceToHost));
+    for (int f = 0; f < n; ++f) {
+      int i_ = 0, na = 0, nb = 0, nbf = 0;
+      for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+          const float* fr = h + (size_t)f * H * W;
+          const int pa = fr[y * W + x] > 0.0f, pb = fr[y * W + x] > 0.5f;
+          i_ += pa && pb; na += pa; nb += pb;
+          /* seg2bmap of the prediction (DAVIS): xor with east / south / south-east, last row / column / corner rules */
+          const int e = x + 1 < W ? fr[y * W + x + 1] > 0.0f : 0, so = y + 1 < H ? fr[(y + 1) * W + x] > 0.0f : 0;
+          const int se = (x + 1 < W && y + 1 < H) ? fr[(y + 1) * W + x + 1] > 0.0f : 0;
+          int bb = (pa ^ e) | (pa ^ so) | (pa ^ se);
+          if (y == H - 1) bb = pa ^ e;
+          if (x == W - 1) bb = pa ^ so;
+          if (y == H - 1 && x == W - 1) bb = 0;
+          nbf += bb;
+        }
+      if (hjf[f] != i_ || hjf[n + f] != na || hjf[2 * n + f] != nb || hjf[3 * n + f] != nbf) { printf("sola_jf_sweep mismatch frame %d\n", f); return 1; }
+      if (hjf[5 * n + f] > hjf[3 * n + f] || hjf[6 * n + f] > hjf[4 * n + f]) { printf("match counts exceed boundary sizes\n"); return 1; }
+    }
+  }
   /* error path: status + message, no exception */
   if (sola_binarize_pack_f32(NULL, 1, 4, 4, 0.0, 1.0, NULL, NULL, NULL, NULL, 0) != SOLA_ERR_INVALID) { printf("expected SOLA_ERR_INVALID\n"); return 1; }
   printf("c_abi_smoke ok (version %d, %llu launches, last error: %s)\n", sola_version(), sola_launch_count(), sola_last_error_string());

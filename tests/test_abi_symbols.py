@@ -12,6 +12,28 @@ def _declared():
     return sorted(set(re.findall(r"\b(sola_[a-z0-9_]+)\s*\(", text)))
 
 
+def _build_digest():
+    from sola_b200 import _build
+    return _build.source_digest().encode()
+
+
+def test_stale_library_is_refused(tmp_path, monkeypatch):
+    """A library whose compiled-in source digest differs from csrc/ must not load silently (stale .so hazard)."""
+    import pytest
+    from sola_b200 import _build, _lib
+    _build.build()
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_build, "_source_digest", lambda: "0" * 64)
+    monkeypatch.setattr(_build, "build", lambda *a, **k: (_ for _ in ()).throw(RuntimeError("no nvcc")))
+    monkeypatch.delenv("SOLA_ALLOW_STALE_LIB", raising=False)
+    with pytest.raises(_lib.SolaError, match="stale|other sources"):
+        _lib.load()
+    monkeypatch.setenv("SOLA_ALLOW_STALE_LIB", "1")
+    with pytest.warns(RuntimeWarning):
+        assert _lib.load() is not None
+    monkeypatch.setattr(_lib, "_lib", None)
+
+
 def test_header_symbols_exported():
     from sola_b200 import _build, _lib
     path = _build.build()
@@ -36,8 +58,10 @@ def test_library_identity_and_error_string():
     assert rc == -1 and b"null" in lib.sola_last_error_string()
     rc = lib.sola_pair_iou_st(None, 4, 16, None, None, None)
     assert rc == -1
-    rc = lib.sola_boundary_counts(1, 1, 1, 8, 8, 99, 1, 1, 1, 1, None)
+    rc = lib.sola_jf_boundary_packed(16, 16, 1, 8, 8, 99, 16, None)
     assert rc == -3 and b"radius" in lib.sola_last_error_string()
+    assert lib.sola_jf_boundary_packed(None, None, 1, 8, 8, 3, None, None) == -1 and b"null" in lib.sola_last_error_string()
+    assert lib.sola_build_digest() == _build_digest()
     # the multi-GPU / J&F entry points validate the same way: status + message, never an exception or a crash
     assert lib.sola_pair_iou_st_rows(None, 4, 18, 0, 1, None, None) == -1 and b"multiple of 4" in lib.sola_last_error_string()
     assert lib.sola_pair_iou_st_rows(None, 4, 16, 2, 2, None, None) == -1 and b"partition" in lib.sola_last_error_string()
