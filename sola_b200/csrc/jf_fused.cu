@@ -113,40 +113,164 @@ __device__ __forceinline__ void jf_issue_load(const JfGeo& g, uint32_t* rawP, ui
   }
 }
 
-// Dilation of the boundary map `src` (pointer to the item's own word, row pitch BP) by the disk (r, v[]), restricted to what the
-// item needs: returns popc(need & dil).  Stops as soon as every needed pixel is matched.
-__device__ __forceinline__ int jf_match_word(const uint32_t* __restrict__ src, int BP, int r, const unsigned char* __restrict__ v,
-                                             const unsigned char* __restrict__ v_pre, uint32_t need) {
-  if (r > JF_PRE_R) {
-    // pre-test: the same decomposition on the radius-2 disk (a subset of the real one): 5 rows instead of 2r+1
-    uint32_t L = src[-1], C = src[0], R = src[1], dil = 0;
-    int vh = 0;
+// ---- disk dilation of one word ---------------------------------------------------------------------------------------------------
+// dil(word) = OR_k shift(±k)( OR of rows within ±v[k] ), v[k] = floor(sqrt(r^2 - k^2)).  Walking k from r down to 0 the vertical extent
+// only grows, so three running words (left / centre / right column) are kept and each extra row pair costs 6 shared loads + 3 LOP3;
+// each k costs 2 funnel shifts + 1 LOP3.  For the radii of the usual frame sizes (360p .. 1080p: 6, 8, 9, 12, 18) and for the
+// radius-2 pre-test the whole walk is unrolled at compile time (no loop control, no table reads, constant shift amounts).
+__host__ __device__ constexpr int jf_isqrt(int x) {
+  int v = 0;
+  while ((v + 1) * (v + 1) <= x) ++v;
+  return v;
+}
+
+struct DilState {
+  const uint32_t* up; const uint32_t* dn;    // rows -vh / +vh of the item's word
+  uint32_t L, C, R, dil;
+};
+
+template <int N>
+__device__ __forceinline__ void dil_grow(DilState& d, int BP) {
 #pragma unroll
-    for (int k = JF_PRE_R; k >= 0; --k) {
-      const int vk = v_pre[k];
-      while (vh < vk) {
-        ++vh;
-        const uint32_t* up = src - vh * BP; const uint32_t* dn = src + vh * BP;
-        L |= up[-1] | dn[-1]; C |= up[0] | dn[0]; R |= up[1] | dn[1];
-      }
-      dil |= k ? (__funnelshift_l(L, C, k) | __funnelshift_r(C, R, k)) : C;
-    }
-    if ((need & ~dil) == 0u) return __popc(need);
+  for (int i = 0; i < N; ++i) {
+    d.up -= BP; d.dn += BP;
+    d.L |= d.up[-1] | d.dn[-1];
+    d.C |= d.up[0] | d.dn[0];
+    d.R |= d.up[1] | d.dn[1];
   }
-  uint32_t L = src[-1], C = src[0], R = src[1], dil = 0;
+}
+
+template <int RAD, int K, int VH>
+struct DilStep {
+  static __device__ __forceinline__ void run(DilState& d, int BP) {
+    constexpr int VK = jf_isqrt(RAD * RAD - K * K);
+    dil_grow<VK - VH>(d, BP);
+    // a source pixel at x-k lands on x (shift towards higher bits, refilled from the left word) and one at x+k on x (the mirror)
+    if constexpr (K > 0) {
+      d.dil |= __funnelshift_l(d.L, d.C, K) | __funnelshift_r(d.C, d.R, K);
+      DilStep<RAD, K - 1, VK>::run(d, BP);
+    } else {
+      d.dil |= d.C;
+    }
+  }
+};
+
+template <int RAD>
+__device__ __forceinline__ uint32_t dilate_word_fixed(const uint32_t* __restrict__ src, int BP) {
+  DilState d{src, src, src[-1], src[0], src[1], 0u};
+  DilStep<RAD, RAD, 0>::run(d, BP);
+  return d.dil;
+}
+
+__device__ __forceinline__ uint32_t dilate_word_generic(const uint32_t* __restrict__ src, int BP, int r, const unsigned char* __restrict__ v) {
+  DilState d{src, src, src[-1], src[0], src[1], 0u};
   int vh = 0;
   for (int k = r; k >= 0; --k) {
     const int vk = v[k];
-    while (vh < vk) {
-      ++vh;
-      const uint32_t* up = src - vh * BP; const uint32_t* dn = src + vh * BP;
-      L |= up[-1] | dn[-1]; C |= up[0] | dn[0]; R |= up[1] | dn[1];
-    }
-    // a source pixel at x-k lands on x (shift towards higher bits, refilled from the left word) and one at x+k on x (the mirror)
-    dil |= k ? (__funnelshift_l(L, C, k) | __funnelshift_r(C, R, k)) : C;
-    if ((need & ~dil) == 0u) return __popc(need);
+    for (; vh < vk; ++vh) dil_grow<1>(d, BP);
+    d.dil |= k ? (__funnelshift_l(d.L, d.C, k) | __funnelshift_r(d.C, d.R, k)) : d.C;
   }
-  return __popc(need & dil);
+  return d.dil;
+}
+
+// RAD > 0: compile-time radius; RAD == 0: run-time radius r with the table v
+template <int RAD>
+__device__ __forceinline__ uint32_t dilate_word(const uint32_t* __restrict__ src, int BP, int r, const unsigned char* __restrict__ v) {
+  if constexpr (RAD > 0) return dilate_word_fixed<RAD>(src, BP);
+  else return dilate_word_generic(src, BP, r, v);
+}
+
+// ---- phase 2: match counting over the owned rows of one item --------------------------------------------------------------------
+// Two-level compaction keeps the lanes busy: non-zero boundary words -> queue 1; a radius-2 pre-test (5 rows; a subset of the real
+// disk, so a pixel it matches IS matched) settles the words whose pixels all have a partner within 2 px — nearly all of them when
+// pred ≈ gt; only the rest go to queue 2 and pay for the full (2r+1)-row dilation, again 32 at a time.
+template <int RAD>
+__device__ __forceinline__ void jf_phase2(const uint32_t* __restrict__ bmF, const uint32_t* __restrict__ bmG, int BP, int Wp, int r, int n_own,
+                                          const unsigned char* __restrict__ vtab, uint32_t* __restrict__ q1, uint32_t* __restrict__ q2,
+                                          int lane, int warp, int& fm, int& gm) {
+  constexpr bool PRE = (RAD == 0) || (RAD > JF_PRE_R);        // run-time radii <= 2 take the pre-test too: harmless, it is exact
+  const unsigned magic = (unsigned)((0x100000000ull + (unsigned)Wp - 1) / (unsigned)Wp);   // idx / Wp == umulhi(idx, magic) for idx * Wp < 2^32
+  const unsigned lt = (1u << lane) - 1u;
+  int n1 = 0, n2 = 0;
+  auto full_pass = [&](bool active) {
+    if (active) {
+      const uint32_t e = q2[n2 + lane];
+      const int eo = (int)(e & 0x7fffffffu);
+      const bool sel = (e >> 31) != 0u;
+      const uint32_t need = (sel ? bmG : bmF)[eo];
+      const int m = __popc(need & dilate_word<RAD>((sel ? bmF : bmG) + eo, BP, r, vtab));
+      if (sel) gm += m; else fm += m;
+    }
+    __syncwarp();
+  };
+  auto pre_pass = [&](bool active) {
+    uint32_t e = 0u;
+    bool fail = false;
+    if (active) {
+      e = q1[n1 + lane];
+      const int eo = (int)(e & 0x7fffffffu);
+      const bool sel = (e >> 31) != 0u;
+      const uint32_t need = (sel ? bmG : bmF)[eo];
+      if (PRE && r > JF_PRE_R) {
+        const uint32_t pre = dilate_word_fixed<JF_PRE_R>((sel ? bmF : bmG) + eo, BP);
+        fail = (need & ~pre) != 0u;
+        if (!fail) { if (sel) gm += __popc(need); else fm += __popc(need); }
+      } else {
+        fail = true;
+      }
+    }
+    const unsigned mfail = __ballot_sync(FULL, fail);
+    if (fail) q2[n2 + __popc(mfail & lt)] = e;
+    n2 += __popc(mfail);
+    __syncwarp();
+    if (n2 >= 32) { n2 -= 32; full_pass(true); }
+  };
+  for (int base = warp * 32; base < n_own; base += JF_THREADS) {
+    const int idx = base + lane;
+    const bool valid = idx < n_own;
+    const int row = (int)__umulhi((unsigned)idx, magic), col = idx - row * Wp;
+    const int o = (r + row) * BP + col + 1;
+    const uint32_t bf = valid ? bmF[o] : 0u, bg = valid ? bmG[o] : 0u;
+    const unsigned mF = __ballot_sync(FULL, bf != 0u), mG = __ballot_sync(FULL, bg != 0u);
+    if ((mF | mG) == 0u) continue;
+    if (bf) q1[n1 + __popc(mF & lt)] = (uint32_t)o;
+    n1 += __popc(mF);
+    if (bg) q1[n1 + __popc(mG & lt)] = (uint32_t)o | 0x80000000u;
+    n1 += __popc(mG);
+    __syncwarp();
+    while (n1 >= 32) { n1 -= 32; pre_pass(true); }
+  }
+  if (n1 > 0) { const int n = n1; n1 = 0; pre_pass(lane < n); }
+  if (n2 > 0) { const int n = n2; n2 = 0; full_pass(lane < n); }
+}
+
+// ---- phase 1 helpers: one walker step ------------------------------------------------------------------------------------------------
+struct WalkRow { uint32_t s, e; };        // a row's word and its east-shifted copy
+
+template <bool OWNED>
+__device__ __forceinline__ void jf_walk_rows(int n_rows, const uint32_t*& rp, const uint32_t*& rq, uint32_t*& bf, uint32_t*& bg, int Wp, int BP,
+                                             bool east, uint32_t lastbit, WalkRow& p, WalkRow& q, int& n_i, int& n_p, int& n_g, int& n_bf,
+                                             int& n_bg) {
+  // rows that have a row below them: b = (s ^ e) | (s ^ south) | (s ^ south-east); last column: s ^ south only
+#pragma unroll 2
+  for (int k = 0; k < n_rows; ++k) {
+    rp += Wp; rq += Wp;
+    const uint32_t p1 = rp[0], q1 = rq[0];
+    const uint32_t pn = east ? rp[1] : 0u, qn = east ? rq[1] : 0u;
+    const uint32_t pe1 = __funnelshift_r(p1, pn, 1), qe1 = __funnelshift_r(q1, qn, 1);
+    const uint32_t ps = p.s ^ p1, qs = q.s ^ q1;
+    uint32_t bp = (p.s ^ p.e) | ps | (p.s ^ pe1);
+    uint32_t bq = (q.s ^ q.e) | qs | (q.s ^ qe1);
+    bp = (bp & ~lastbit) | (ps & lastbit);
+    bq = (bq & ~lastbit) | (qs & lastbit);
+    if (OWNED) {
+      n_p += __popc(p.s); n_g += __popc(q.s); n_i += __popc(p.s & q.s);
+      n_bf += __popc(bp); n_bg += __popc(bq);
+    }
+    *bf = bp; *bg = bq;
+    bf += BP; bg += BP;
+    p.s = p1; p.e = pe1; q.s = q1; q.e = qe1;
+  }
 }
 
 __global__ void __launch_bounds__(JF_THREADS, 2)
@@ -158,19 +282,13 @@ jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_
   uint32_t* bmF = rawG + raw_cap;
   uint32_t* bmG = bmF + bm_cap;
   __shared__ uint64_t bar;
-  __shared__ uint32_t queue[JF_WARPS][JF_QUEUE];
+  __shared__ uint32_t queue1[JF_WARPS][JF_QUEUE], queue2[JF_WARPS][64];
   __shared__ int red[7][JF_WARPS];
-  __shared__ unsigned char vtab[JF_MAX_R + 1], vpre[JF_PRE_R + 1];
+  __shared__ unsigned char vtab[JF_MAX_R + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     mbar_init(&bar, 1);
     mbar_fence_init();
-  }
-  if (tid <= JF_PRE_R) {
-    const int rem = JF_PRE_R * JF_PRE_R - tid * tid;
-    int v = 0;
-    while ((v + 1) * (v + 1) <= rem) ++v;
-    vpre[tid] = (unsigned char)v;
   }
   __syncthreads();
 
@@ -189,12 +307,7 @@ jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_
     const int Wp = g.Wp, BP = Wp + 2, r = g.r < 0 ? 0 : g.r;
     const int off = (int)(g.g0 & 3ll);
     if (g.r >= 0) {
-      if (r != r_cached && tid <= r) {                     // disk table: v[k] = floor(sqrt(r^2 - k^2))
-        const int rem = r * r - tid * tid;
-        int v = 0;
-        while ((v + 1) * (v + 1) <= rem) ++v;
-        vtab[tid] = (unsigned char)v;
-      }
+      if (r != r_cached && tid <= r) vtab[tid] = (unsigned char)jf_isqrt(r * r - tid * tid);     // disk table for run-time radii
       r_cached = r;
       for (int j = tid; j < g.NB; j += JF_THREADS) {       // zero halo columns of both boundary maps
         bmF[j * BP] = 0u; bmF[j * BP + Wp + 1] = 0u;
@@ -218,86 +331,55 @@ jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_
       const int c = tid % Wp, s = tid / Wp;
       const int n_sub = min(JF_THREADS / Wp, g.NB);
       if (s < n_sub) {
-        int j = (int)((long long)s * g.NB / n_sub);
-        const int j_end = (int)((long long)(s + 1) * g.NB / n_sub);
-        int by = g.y0 - r + j;
+        const int j0 = (int)((long long)s * g.NB / n_sub), j1 = (int)((long long)(s + 1) * g.NB / n_sub);
+        const int ya = g.y0 - r + j0, yb = g.y0 - r + j1;            // this walker's frame rows [ya, yb)
         const uint32_t lastbit = (c == Wp - 1) ? (1u << ((g.W - 1) & 31)) : 0u;
         const bool east = c + 1 < Wp;
-        const int base = off + c - g.ra * Wp;               // raw index of (row y, column c) = base + y * Wp
-        bool have = false;
-        uint32_t p0 = 0, pe0 = 0, q0 = 0, qe0 = 0;
-        for (; j < j_end; ++j, ++by) {
-          uint32_t bp = 0u, bq = 0u;
-          if (by >= 0 && by < g.H) {
-            const int i0 = base + by * Wp;
-            if (!have) {
-              p0 = rawP[i0]; q0 = rawG[i0];
-              const uint32_t pn = east ? rawP[i0 + 1] : 0u, qn = east ? rawG[i0 + 1] : 0u;
-              pe0 = __funnelshift_r(p0, pn, 1); qe0 = __funnelshift_r(q0, qn, 1);
+        uint32_t* bf = bmF + j0 * BP + c + 1;
+        uint32_t* bg = bmG + j0 * BP + c + 1;
+        int y = ya;
+        for (; y < min(yb, 0); ++y) { *bf = 0u; *bg = 0u; bf += BP; bg += BP; }           // rows above the frame
+        if (y < yb && y < g.H) {
+          const uint32_t* rp = rawP + off + (y - g.ra) * Wp + c;
+          const uint32_t* rq = rawG + off + (y - g.ra) * Wp + c;
+          WalkRow p, q;
+          p.s = rp[0]; q.s = rq[0];
+          p.e = __funnelshift_r(p.s, east ? rp[1] : 0u, 1);
+          q.e = __funnelshift_r(q.s, east ? rq[1] : 0u, 1);
+          const int y_south = min(yb, g.H - 1);                      // rows [y, y_south) have a row below them
+          // halo rows before the owned range, the owned rows, halo rows after: the popcounts exist only in the middle loop
+          const int a1 = min(max(g.y0, y), y_south), a2 = min(max(g.y1, y), y_south);
+          jf_walk_rows<false>(a1 - y, rp, rq, bf, bg, Wp, BP, east, lastbit, p, q, n_i, n_p, n_g, n_bf, n_bg);
+          jf_walk_rows<true>(a2 - a1, rp, rq, bf, bg, Wp, BP, east, lastbit, p, q, n_i, n_p, n_g, n_bf, n_bg);
+          jf_walk_rows<false>(y_south - a2, rp, rq, bf, bg, Wp, BP, east, lastbit, p, q, n_i, n_p, n_g, n_bf, n_bg);
+          y = max(y, y_south);
+          if (y < yb && y == g.H - 1) {                              // last row of the frame: seg ^ east, corner forced to 0
+            const uint32_t bp = (p.s ^ p.e) & ~lastbit, bq = (q.s ^ q.e) & ~lastbit;
+            if (y >= g.y0 && y < g.y1) {
+              n_p += __popc(p.s); n_g += __popc(q.s); n_i += __popc(p.s & q.s);
+              n_bf += __popc(bp); n_bg += __popc(bq);
             }
-            const bool owned = by >= g.y0 && by < g.y1;
-            if (owned) { n_p += __popc(p0); n_g += __popc(q0); n_i += __popc(p0 & q0); }
-            if (by + 1 < g.H) {
-              const uint32_t p1 = rawP[i0 + Wp], q1 = rawG[i0 + Wp];
-              const uint32_t pn = east ? rawP[i0 + Wp + 1] : 0u, qn = east ? rawG[i0 + Wp + 1] : 0u;
-              const uint32_t pe1 = __funnelshift_r(p1, pn, 1), qe1 = __funnelshift_r(q1, qn, 1);
-              const uint32_t ps = p0 ^ p1, qs = q0 ^ q1;
-              bp = (p0 ^ pe0) | ps | (p0 ^ pe1);
-              bq = (q0 ^ qe0) | qs | (q0 ^ qe1);
-              bp = (bp & ~lastbit) | (ps & lastbit);         // last column: seg ^ south only
-              bq = (bq & ~lastbit) | (qs & lastbit);
-              p0 = p1; pe0 = pe1; q0 = q1; qe0 = qe1;
-              have = true;
-            } else {
-              bp = (p0 ^ pe0) & ~lastbit;                    // last row: seg ^ east, corner forced to 0
-              bq = (q0 ^ qe0) & ~lastbit;
-              have = false;
-            }
-            if (owned) { n_bf += __popc(bp); n_bg += __popc(bq); }
-          } else {
-            have = false;
+            *bf = bp; *bg = bq; bf += BP; bg += BP;
+            ++y;
           }
-          bmF[j * BP + c + 1] = bp;
-          bmG[j * BP + c + 1] = bq;
         }
+        for (; y < yb; ++y) { *bf = 0u; *bg = 0u; bf += BP; bg += BP; }                  // rows below the frame
       }
     }
     __syncthreads();                                        // boundary maps complete; the raw tile is dead
     if (has_next) jf_issue_load(gn, rawP, rawG, &bar, tid);  // next tile streams in while this one is matched
 
     if (g.r >= 0) {
-      // ---- phase 2: dilate only where a boundary pixel needs an answer -------------------------------------------------------
       const int n_own = (g.y1 - g.y0) * Wp;
-      const unsigned magic = (unsigned)((0x100000000ull + (unsigned)Wp - 1) / (unsigned)Wp);   // idx / Wp == umulhi(idx, magic) for idx * Wp < 2^32
-      const unsigned lt = (1u << lane) - 1u;
-      uint32_t* q = queue[warp];
-      int n = 0;
-      for (int base = warp * 32; base < n_own; base += JF_THREADS) {
-        const int idx = base + lane;
-        const bool valid = idx < n_own;
-        const int row = (int)__umulhi((unsigned)idx, magic), col = idx - row * Wp;
-        const int o = (r + row) * BP + col + 1;
-        const uint32_t bf = valid ? bmF[o] : 0u, bg = valid ? bmG[o] : 0u;
-        const unsigned mF = __ballot_sync(FULL, bf != 0u), mG = __ballot_sync(FULL, bg != 0u);
-        if (bf) q[n + __popc(mF & lt)] = (uint32_t)o;
-        n += __popc(mF);
-        if (bg) q[n + __popc(mG & lt)] = (uint32_t)o | 0x80000000u;
-        n += __popc(mG);
-        __syncwarp();
-        while (n >= 32) {
-          n -= 32;
-          const uint32_t e = q[n + lane];
-          const int eo = (int)(e & 0x7fffffffu);
-          if (e >> 31) gm += jf_match_word(bmF + eo, BP, r, vtab, vpre, bmG[eo]);
-          else fm += jf_match_word(bmG + eo, BP, r, vtab, vpre, bmF[eo]);
-          __syncwarp();
-        }
-      }
-      if (lane < n) {
-        const uint32_t e = q[lane];
-        const int eo = (int)(e & 0x7fffffffu);
-        if (e >> 31) gm += jf_match_word(bmF + eo, BP, r, vtab, vpre, bmG[eo]);
-        else fm += jf_match_word(bmG + eo, BP, r, vtab, vpre, bmF[eo]);
+      uint32_t* q1 = queue1[warp];
+      uint32_t* q2 = queue2[warp];
+      switch (r) {
+        case 6: jf_phase2<6>(bmF, bmG, BP, Wp, r, n_own, vtab, q1, q2, lane, warp, fm, gm); break;       // 360 x 640
+        case 8: jf_phase2<8>(bmF, bmG, BP, Wp, r, n_own, vtab, q1, q2, lane, warp, fm, gm); break;       // 480 x 854
+        case 9: jf_phase2<9>(bmF, bmG, BP, Wp, r, n_own, vtab, q1, q2, lane, warp, fm, gm); break;       // 540 x 960
+        case 12: jf_phase2<12>(bmF, bmG, BP, Wp, r, n_own, vtab, q1, q2, lane, warp, fm, gm); break;     // 720 x 1280
+        case 18: jf_phase2<18>(bmF, bmG, BP, Wp, r, n_own, vtab, q1, q2, lane, warp, fm, gm); break;     // 1080 x 1920
+        default: jf_phase2<0>(bmF, bmG, BP, Wp, r, n_own, vtab, q1, q2, lane, warp, fm, gm); break;
       }
     }
 

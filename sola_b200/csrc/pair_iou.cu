@@ -15,7 +15,7 @@
 //   * each of the 256 threads accumulates a strided 4 x 4 micro-tile (rows ty+16r, cols tx+16r) in int32
 //     registers; diagonal tiles stage their 64 rows once and skip the strictly-lower micro-tile entries;
 //   * partial sums leave the CTA as 64-bit atomics on the N x N output (a few hundred adds per address).
-#include "common.cuh"
+#include "tma.cuh"
 #include <cuda.h>
 #include <stdlib.h>          // CUtensorMap + enums only; the encoder is fetched at run time through cudaGetDriverEntryPoint
 
@@ -25,30 +25,22 @@ constexpr int PT = 64;            // tile side (tracks)
 constexpr int KQ = 8;             // uint4 per row per stage -> 32 words = 128 B per row per stage
 constexpr int STAGE_WORDS = KQ * 4;
 constexpr int NSTAGE = 4;
-constexpr int ST_THREADS = 256;
+constexpr int ST_THREADS = 256;   // consumer threads: 16 x 16, each a strided 4 x 4 micro-tile of pairs
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(src_bytes));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
-
-__device__ __forceinline__ int popc4_and(const uint4& a, const uint4& b) {
-  return __popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w);
-}
 
 // Carry-save accumulation (Harley-Seal): POPC issues at 16 lanes/clk/SM on sm_100 (measured, profiles/r1_microbench_int_b200.jsonl)
 // against 64 for LOP3, so the plain AND+POPC+IADD loop is POPC-bound.  Per pair we keep bit-sliced counters `ones`, `twos`
 // and feed the four AND-ed words of a k-quad through three 3:2 compressors; only the weight-4 carry word is popcounted:
 //   4 AND + 6 LOP3 + 1 POPC per 4 words  (2.5 alu ops and 0.25 POPC per word instead of 1 and 1).
 // The compressors are written as explicit 3-input LOP3s (majority 0xE8, parity 0x96): left to itself the compiler fuses the ANDs
-// into a chain of half adders (a ^ (b & c), a & b & c, or) that costs 12 LOP3 per quad instead of 10.
-// A hybrid that sends a fixed subset of the k-quads of every stage (PLAIN) down the plain route — 4 AND + 4 POPC, adds on the fma
-// pipe — to put the idle POPC pipe to work was measured and is NOT faster (dense 64 x 80 x 540 x 960: 0.618 ms pure carry-save,
-// 0.639 / 0.652 ms with 2 / 3 plain quads of 8; profiles/r1_k2_variants.jsonl): at 2 CTAs x 8 warps per SM the loop is bound by
-// dependent-issue latency, not by either pipe.  The template stays for experiments (SOLA_K2_PLAIN=2|3); default is pure carry-save.
-// total = acc + 2 * popc(twos) + popc(ones) — exactly the same integer in every variant.
+// into a chain of half adders (a ^ (b & c), a & b & c, or) that costs 12 LOP3 per quad instead of 10.  (A hybrid that sends some
+// k-quads down the plain POPC route to use the idle POPC pipe measured 3-5 % slower, profiles/r1_k2_variants.jsonl.)
+// total = acc + 2 * popc(twos) + popc(ones).
 struct Csa { uint32_t ones, twos; int acc; };
 
 __device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
@@ -72,18 +64,6 @@ __device__ __forceinline__ void csa_quad(Csa& st, const uint4& a, const uint4& b
   st.acc = __popc(f) * 4 + st.acc;
 }
 
-__device__ __forceinline__ void plain_quad(Csa& st, const uint4& a, const uint4& b) {
-  st.acc += __popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w);
-}
-
-// PLAIN = k-quads of a stage (bit q set) that take the plain POPC route: 0 = none (default), 0x24 = quads 2 and 5 of the 8
-constexpr int K2_PLAIN_DEFAULT = 0x00;
-template <int PLAIN>
-__device__ __forceinline__ void acc_quad(Csa& st, const uint4& a, const uint4& b, int q /* compile-time after unrolling */) {
-  if ((PLAIN >> q) & 1) plain_quad(st, a, b);
-  else csa_quad(st, a, b);
-}
-
 __device__ __forceinline__ int csa_total(const Csa& st) { return st.acc + 2 * __popc(st.twos) + __popc(st.ones); }
 
 // tile list: (ti, tj) with ti <= tj, enumerated row-major over the upper triangle
@@ -93,18 +73,80 @@ __device__ __forceinline__ void tile_from_index(int idx, int nt, int& ti, int& t
   ti = i; tj = i + idx;
 }
 
+// ---- the one consumer: a stage (64 or 2 x 64 rows x 32 words, in shared memory) into the thread's 4 x 4 carry-save accumulators ----
+// Where a stage's 16-byte chunk q of operand row r lives depends on who staged it:
+struct StageKQ {        // cp.async loader: k-quad major, [q][row]; rows of operand B follow the 64 rows of A (same rows when DIAG)
+  const uint4* buf; int rows, b_off;
+  __device__ __forceinline__ uint4 a(int q, int r) const { return buf[q * rows + r]; }
+  __device__ __forceinline__ uint4 b(int q, int r) const { return buf[q * rows + b_off + r]; }
+};
+struct StageSwz {       // TMA loader, SWIZZLE_128B: chunk q of row r sits at chunk q ^ (r & 7) of the row's 128 bytes
+  const uint4* A; const uint4* B;
+  __device__ __forceinline__ uint4 a(int q, int r) const { return A[r * KQ + (q ^ (r & 7))]; }
+  __device__ __forceinline__ uint4 b(int q, int r) const { return B[r * KQ + (q ^ (r & 7))]; }
+};
+
+struct K2Acc {
+  Csa c[4][4];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) c[a][b] = Csa{0u, 0u, 0};
+  }
+};
+
+template <bool DIAG, class Stage>
+__device__ __forceinline__ void consume_stage(const Stage& st, int tx, int ty, K2Acc& acc) {
+#pragma unroll
+  for (int q = 0; q < KQ; ++q) {
+    uint4 a[4], b[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      a[r] = st.a(q, ty + 16 * r);
+      b[r] = st.b(q, tx + 16 * r);
+    }
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) {
+      // masklets are mostly background: an all-zero quad of row i contributes nothing to any of its pairs (the carry-save
+      // state is unchanged by zero inputs), so skip its 4 compressor chains.  The 16 lanes that share `ty` agree on this.
+      if ((a[ri].x | a[ri].y | a[ri].z | a[ri].w) == 0u) continue;
+#pragma unroll
+      for (int rj = 0; rj < 4; ++rj) {
+        if (DIAG && rj < ri) continue;                 // mirror entry is produced by another (ri, rj)
+        csa_quad(acc.c[ri][rj], a[ri], b[rj]);
+      }
+    }
+  }
+}
+
+// partial sums leave the CTA as 64-bit atomics on the N x N output (both mirror halves)
 template <bool DIAG>
-__device__ __forceinline__ void st_tile_body(const uint32_t* __restrict__ packed, const uint32_t* const* __restrict__ row_ptrs, int N,
-                                             long long words, int ti, int tj, long long s_begin, long long s_end, uint4* smem,
-                                             unsigned long long* __restrict__ inter) {
+__device__ __forceinline__ void store_tile(const K2Acc& acc, int N, int ti, int tj, int tx, int ty, unsigned long long* __restrict__ inter) {
+#pragma unroll
+  for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+    for (int rj = 0; rj < 4; ++rj) {
+      if (DIAG && rj < ri) continue;
+      const int i = ti * PT + ty + 16 * ri, j = tj * PT + tx + 16 * rj;
+      if (i >= N || j >= N) continue;
+      if (DIAG && ri == rj && tx < ty) continue;       // lower half of the 16x16 diagonal blocks
+      const unsigned long long v = (unsigned long long)csa_total(acc.c[ri][rj]);
+      if (v == 0) continue;
+      atomicAdd(inter + (long long)i * N + j, v);
+      if (i != j) atomicAdd(inter + (long long)j * N + i, v);
+    }
+}
+
+// ---- cp.async-staged kernel: rows come from one (N, words) buffer or from a table of per-track pointers (peer GPUs' memory) --------
+template <bool DIAG>
+__device__ __forceinline__ void st_tile_cpasync(const uint32_t* __restrict__ packed, const uint32_t* const* __restrict__ row_ptrs, int N,
+                                                long long words, int ti, int tj, long long s_begin, long long s_end, uint4* smem,
+                                                unsigned long long* __restrict__ inter) {
   constexpr int ROWS = DIAG ? PT : 2 * PT;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  Csa acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = Csa{0u, 0u, 0};
-
+  K2Acc acc;
+  acc.clear();
   // stage loader: ROWS*KQ 16-byte copies, thread t copies (row = c / KQ, q = c % KQ) for c = t, t+256, ...
   auto issue = [&](long long stage, int buf) {
     uint4* dst = smem + (size_t)buf * (2 * PT) * KQ;
@@ -116,13 +158,11 @@ __device__ __forceinline__ void st_tile_body(const uint32_t* __restrict__ packed
       const long long w = w0 + q * 4;
       long long remain = (words - w) * 4;               // bytes left in this track row
       int nbytes = (track < N && remain > 0) ? (int)(remain < 16 ? remain : 16) : 0;
-      // row base: one contiguous (N, words) buffer, or a table of per-track pointers (tracks living on peer GPUs, read over NVLink)
       const uint32_t* base = row_ptrs ? row_ptrs[track < N ? track : 0] : packed + (long long)(track < N ? track : 0) * words;
       const uint32_t* src = base + (nbytes ? w : 0);
       cp_async16(dst + q * ROWS + row, src, nbytes);
     }
   };
-
   const long long n_st = s_end - s_begin;
 #pragma unroll
   for (int p = 0; p < NSTAGE - 1; ++p) {
@@ -134,43 +174,10 @@ __device__ __forceinline__ void st_tile_body(const uint32_t* __restrict__ packed
     __syncthreads();
     if (s + NSTAGE - 1 < n_st) issue(s_begin + s + NSTAGE - 1, (int)((s + NSTAGE - 1) % NSTAGE));
     cp_async_commit();
-    const uint4* buf = smem + (size_t)(s % NSTAGE) * (2 * PT) * KQ;
-#pragma unroll
-    for (int q = 0; q < KQ; ++q) {
-      uint4 a[4], b[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        a[r] = buf[q * ROWS + ty + 16 * r];
-        b[r] = buf[q * ROWS + (DIAG ? 0 : PT) + tx + 16 * r];
-      }
-#pragma unroll
-      for (int ri = 0; ri < 4; ++ri) {
-        // masklets are mostly background: an all-zero quad of row i contributes nothing to any of its pairs (the carry-save
-        // state is unchanged by zero inputs), so skip its 4 compressor chains.  The 16 lanes that share `ty` agree on this.
-        if ((a[ri].x | a[ri].y | a[ri].z | a[ri].w) == 0u) continue;
-#pragma unroll
-        for (int rj = 0; rj < 4; ++rj) {
-          if (DIAG && rj < ri) continue;               // mirror entry is produced by another (ri, rj)
-          acc_quad<K2_PLAIN_DEFAULT>(acc[ri][rj], a[ri], b[rj], q);
-        }
-      }
-    }
+    consume_stage<DIAG>(StageKQ{smem + (size_t)(s % NSTAGE) * (2 * PT) * KQ, ROWS, DIAG ? 0 : PT}, tx, ty, acc);
   }
   cp_async_wait<0>();
-
-#pragma unroll
-  for (int ri = 0; ri < 4; ++ri)
-#pragma unroll
-    for (int rj = 0; rj < 4; ++rj) {
-      if (DIAG && rj < ri) continue;
-      const int i = ti * PT + ty + 16 * ri, j = tj * PT + tx + 16 * rj;
-      if (i >= N || j >= N) continue;
-      if (DIAG && ri == rj && tx < ty) continue;       // lower half of the 16x16 diagonal blocks
-      const unsigned long long v = (unsigned long long)csa_total(acc[ri][rj]);
-      if (v == 0) continue;
-      atomicAdd(inter + (long long)i * N + j, v);
-      if (i != j) atomicAdd(inter + (long long)j * N + i, v);
-    }
+  store_tile<DIAG>(acc, N, ti, tj, tx, ty, inter);
 }
 
 __global__ void __launch_bounds__(ST_THREADS)
@@ -185,139 +192,23 @@ pair_iou_st_kernel(const uint32_t* __restrict__ packed, const uint32_t* const* _
   tile_from_index(tile, nt, ti, tj);
   const long long stages = stage_hi - stage_lo;
   const long long s_begin = stage_lo + stages * split / splits, s_end = stage_lo + stages * (split + 1) / splits;
-  if (ti == tj) st_tile_body<true>(packed, row_ptrs, N, words, ti, tj, s_begin, s_end, smem_st, inter);
-  else st_tile_body<false>(packed, row_ptrs, N, words, ti, tj, s_begin, s_end, smem_st, inter);
+  if (ti == tj) st_tile_cpasync<true>(packed, row_ptrs, N, words, ti, tj, s_begin, s_end, smem_st, inter);
+  else st_tile_cpasync<false>(packed, row_ptrs, N, words, ti, tj, s_begin, s_end, smem_st, inter);
 }
 
-// ---- TMA-staged variant (default) --------------------------------------------------------------------------------------
-// The (rows x 32 words) stage tiles are regular, so they are fetched by the TMA unit instead of 4 cp.async per thread:
-// a rank-2 tensor map over packed[N][words] (uint32), box = 32 words x 64 rows = 8 KB, SWIZZLE_128B.  One elected thread
-// arms the stage's mbarrier with the byte count and issues one (diagonal tile) or two `cp.async.bulk.tensor.2d` per stage;
-// out-of-range rows (>= N) and the K tail are zero-filled by the hardware.  With the 128-byte swizzle the 16-byte chunk q of
-// row r lives at chunk q ^ (r & 7), so 8 lanes reading 8 consecutive rows at the same q touch 8 different bank groups.
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  unsigned done = 0;
-  for (long long spin = 0; !done; ++spin) {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
-    if (spin > (1ll << 26)) __trap();                    // never hang the GPU on a lost transaction
-  }
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
-                   "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"(c0), "r"(c1),
-               "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-
+// ---- TMA-staged, warp-specialised ring (default) ---------------------------------------------------------------------------------
+// The (rows x 32 words) stage tiles are regular, so they are fetched by the TMA unit: a rank-2 tensor map over packed[N][words]
+// (uint32), box = 32 words x 64 rows = 8 KB, SWIZZLE_128B, hardware zero fill for rows >= N and for the K tail.  A 9th warp's elected
+// lane is the producer (arms the stage's `full` mbarrier with the byte count, issues `cp.async.bulk.tensor.2d`); the 8 consumer
+// warps hand each stage buffer back through an `empty` mbarrier (one arrive per warp), so there is no CTA-wide barrier in the stage
+// loop and a warp that skipped many all-zero quads runs up to NSTAGE-1 stages ahead of its slowest sibling.
+constexpr int RING_THREADS = ST_THREADS + 32;
 constexpr int TMA_BOX_BYTES = PT * STAGE_WORDS * 4;      // 64 rows x 128 B
 
-template <bool DIAG, int PLAIN>
-__device__ __forceinline__ void st_tile_body_tma(const CUtensorMap* __restrict__ map, int N, int ti, int tj, long long s_begin,
-                                                 long long s_end, unsigned char* smem, uint64_t* full,
-                                                 unsigned long long* __restrict__ inter) {
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  Csa acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = Csa{0u, 0u, 0};
-  auto issue = [&](long long stage, int buf) {         // one thread
-    unsigned char* dst = smem + (size_t)buf * 2 * TMA_BOX_BYTES;
-    mbar_expect_tx(full + buf, DIAG ? TMA_BOX_BYTES : 2 * TMA_BOX_BYTES);
-    tma_load_2d(dst, map, (int)(stage * STAGE_WORDS), ti * PT, full + buf);
-    if (!DIAG) tma_load_2d(dst + TMA_BOX_BYTES, map, (int)(stage * STAGE_WORDS), tj * PT, full + buf);
-  };
-  const long long n_st = s_end - s_begin;
-  if (tid == 0)
-    for (int p = 0; p < NSTAGE - 1; ++p)
-      if (p < n_st) issue(s_begin + p, p);
-  for (long long s = 0; s < n_st; ++s) {
-    const int bufi = (int)(s % NSTAGE);
-    __syncthreads();                                    // everyone has finished reading the buffer that is refilled next
-    if (tid == 0 && s + NSTAGE - 1 < n_st) issue(s_begin + s + NSTAGE - 1, (int)((s + NSTAGE - 1) % NSTAGE));
-    mbar_wait(full + bufi, (unsigned)((s / NSTAGE) & 1));
-    const uint4* A = reinterpret_cast<const uint4*>(smem + (size_t)bufi * 2 * TMA_BOX_BYTES);
-    const uint4* B = DIAG ? A : A + TMA_BOX_BYTES / 16;
-#pragma unroll
-    for (int q = 0; q < KQ; ++q) {
-      uint4 a[4], b[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int ra = ty + 16 * r, rb = tx + 16 * r;
-        a[r] = A[ra * KQ + (q ^ (ra & 7))];
-        b[r] = B[rb * KQ + (q ^ (rb & 7))];
-      }
-#pragma unroll
-      for (int ri = 0; ri < 4; ++ri) {
-        // masklets are mostly background: an all-zero quad of row i contributes nothing to any of its pairs (the carry-save
-        // state is unchanged by zero inputs), so skip its 4 compressor chains.  The 16 lanes that share `ty` agree on this.
-        if ((a[ri].x | a[ri].y | a[ri].z | a[ri].w) == 0u) continue;
-#pragma unroll
-        for (int rj = 0; rj < 4; ++rj) {
-          if (DIAG && rj < ri) continue;
-          acc_quad<PLAIN>(acc[ri][rj], a[ri], b[rj], q);
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int ri = 0; ri < 4; ++ri)
-#pragma unroll
-    for (int rj = 0; rj < 4; ++rj) {
-      if (DIAG && rj < ri) continue;
-      const int i = ti * PT + ty + 16 * ri, j = tj * PT + tx + 16 * rj;
-      if (i >= N || j >= N) continue;
-      if (DIAG && ri == rj && tx < ty) continue;
-      const unsigned long long v = (unsigned long long)csa_total(acc[ri][rj]);
-      if (v == 0) continue;
-      atomicAdd(inter + (long long)i * N + j, v);
-      if (i != j) atomicAdd(inter + (long long)j * N + i, v);
-    }
-}
-
-template <int PLAIN, int MIN_CTAS = 0>
-__global__ void __launch_bounds__(ST_THREADS, MIN_CTAS)
-pair_iou_st_tma_kernel(const __grid_constant__ CUtensorMap map, int N, long long words, int nt, int n_tiles, int splits,
-                       int tile_first, int tile_step, unsigned long long* __restrict__ inter) {
-  extern __shared__ __align__(1024) unsigned char smem_tma[];          // SWIZZLE_128B needs 1024-byte aligned boxes
-  __shared__ uint64_t full[NSTAGE];
-  if (threadIdx.x == 0) {
-    for (int b = 0; b < NSTAGE; ++b) mbar_init(full + b, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  const int tile = tile_first + (blockIdx.x % n_tiles) * tile_step, split = blockIdx.x / n_tiles;
-  int ti, tj;
-  tile_from_index(tile, nt, ti, tj);
-  const long long stages = (words + STAGE_WORDS - 1) / STAGE_WORDS;
-  const long long s_begin = stages * split / splits, s_end = stages * (split + 1) / splits;
-  // round the dynamic-smem base up to 1024 B by OFFSET (a pointer cast would demote the tile reads to generic loads)
-  unsigned char* boxes = smem_tma + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_tma) & 1023u)) & 1023u);
-  if (ti == tj) st_tile_body_tma<true, PLAIN>(&map, N, ti, tj, s_begin, s_end, boxes, full, inter);
-  else st_tile_body_tma<false, PLAIN>(&map, N, ti, tj, s_begin, s_end, boxes, full, inter);
-}
-
-// ---- warp-specialised ring variant ---------------------------------------------------------------------------------------
-// Same tiles, same math, but no CTA-wide barrier in the stage loop: a 9th warp is the TMA producer, the 8 consumer warps release
-// each stage buffer through an `empty` mbarrier (one arrive per warp).  A warp that skipped many all-zero quads runs up to NSTAGE-1
-// stages ahead of its slowest sibling instead of waiting for it at every stage (ncu on the __syncthreads version: ~1.1 warps per
-// issue slot stalled on the barrier).
-constexpr int RING_THREADS = ST_THREADS + 32;
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-
-template <bool DIAG>
-__device__ __forceinline__ void st_tile_body_ring(const CUtensorMap* __restrict__ map, int N, int ti, int tj, long long s_begin,
-                                                  long long s_end, unsigned char* smem, uint64_t* full, uint64_t* empty,
-                                                  unsigned long long* __restrict__ inter) {
+// `load_stage(dst, w0, bar)` issues the TMA loads of one stage (operand A at dst, B at dst + TMA_BOX_BYTES) after the expect_tx.
+template <bool DIAG, class LoadStage>
+__device__ __forceinline__ void st_tile_ring(LoadStage load_stage, int N, int ti, int tj, long long s_begin, long long s_end,
+                                             unsigned char* smem, uint64_t* full, uint64_t* empty, unsigned long long* __restrict__ inter) {
   const int tid = threadIdx.x;
   const long long n_st = s_end - s_begin;
   if (tid >= ST_THREADS) {                              // producer warp: one lane drives the TMA unit
@@ -325,60 +216,44 @@ __device__ __forceinline__ void st_tile_body_ring(const CUtensorMap* __restrict_
       for (long long s = 0; s < n_st; ++s) {
         const int buf = (int)(s % NSTAGE);
         if (s >= NSTAGE) mbar_wait(empty + buf, (unsigned)(((s / NSTAGE) - 1) & 1));     // all 8 warps have left this buffer
-        unsigned char* dst = smem + (size_t)buf * 2 * TMA_BOX_BYTES;
         mbar_expect_tx(full + buf, DIAG ? TMA_BOX_BYTES : 2 * TMA_BOX_BYTES);
-        tma_load_2d(dst, map, (int)((s_begin + s) * STAGE_WORDS), ti * PT, full + buf);
-        if (!DIAG) tma_load_2d(dst + TMA_BOX_BYTES, map, (int)((s_begin + s) * STAGE_WORDS), tj * PT, full + buf);
+        load_stage(smem + (size_t)buf * 2 * TMA_BOX_BYTES, (int)((s_begin + s) * STAGE_WORDS), full + buf);
       }
     }
     return;
   }
   const int tx = tid & 15, ty = tid >> 4, lane = tid & 31;
-  Csa acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = Csa{0u, 0u, 0};
+  K2Acc acc;
+  acc.clear();
   for (long long s = 0; s < n_st; ++s) {
     const int bufi = (int)(s % NSTAGE);
     mbar_wait(full + bufi, (unsigned)((s / NSTAGE) & 1));
     const uint4* A = reinterpret_cast<const uint4*>(smem + (size_t)bufi * 2 * TMA_BOX_BYTES);
-    const uint4* B = DIAG ? A : A + TMA_BOX_BYTES / 16;
-#pragma unroll
-    for (int q = 0; q < KQ; ++q) {
-      uint4 a[4], b[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int ra = ty + 16 * r, rb = tx + 16 * r;
-        a[r] = A[ra * KQ + (q ^ (ra & 7))];
-        b[r] = B[rb * KQ + (q ^ (rb & 7))];
-      }
-#pragma unroll
-      for (int ri = 0; ri < 4; ++ri) {
-        if ((a[ri].x | a[ri].y | a[ri].z | a[ri].w) == 0u) continue;       // all-zero quad of row i: nothing to add for its pairs
-#pragma unroll
-        for (int rj = 0; rj < 4; ++rj) {
-          if (DIAG && rj < ri) continue;
-          csa_quad(acc[ri][rj], a[ri], b[rj]);
-        }
-      }
-    }
+    consume_stage<DIAG>(StageSwz{A, DIAG ? A : A + TMA_BOX_BYTES / 16}, tx, ty, acc);
     __syncwarp();                                       // every lane of this warp is done reading the buffer
     if (lane == 0) mbar_arrive(empty + bufi);
   }
-#pragma unroll
-  for (int ri = 0; ri < 4; ++ri)
-#pragma unroll
-    for (int rj = 0; rj < 4; ++rj) {
-      if (DIAG && rj < ri) continue;
-      const int i = ti * PT + ty + 16 * ri, j = tj * PT + tx + 16 * rj;
-      if (i >= N || j >= N) continue;
-      if (DIAG && ri == rj && tx < ty) continue;
-      const unsigned long long v = (unsigned long long)csa_total(acc[ri][rj]);
-      if (v == 0) continue;
-      atomicAdd(inter + (long long)i * N + j, v);
-      if (i != j) atomicAdd(inter + (long long)j * N + i, v);
-    }
+  store_tile<DIAG>(acc, N, ti, tj, tx, ty, inter);
+}
+
+struct RingSetup { unsigned char* boxes; int ti, tj; long long s_begin, s_end; };
+
+__device__ __forceinline__ RingSetup ring_setup(unsigned char* dyn_smem, uint64_t* full, uint64_t* empty, int nt, int n_tiles, int splits,
+                                                int tile_first, int tile_step, long long stage_lo, long long stage_hi) {
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < NSTAGE; ++b) { mbar_init(full + b, 1); mbar_init(empty + b, ST_THREADS / 32); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  RingSetup r;
+  const int tile = tile_first + (blockIdx.x % n_tiles) * tile_step, split = blockIdx.x / n_tiles;
+  tile_from_index(tile, nt, r.ti, r.tj);
+  const long long stages = stage_hi - stage_lo;
+  r.s_begin = stage_lo + stages * split / splits;
+  r.s_end = stage_lo + stages * (split + 1) / splits;
+  // round the dynamic-smem base up to 1024 B by OFFSET (SWIZZLE_128B boxes; a pointer cast would demote the tile reads to generic loads)
+  r.boxes = dyn_smem + ((1024u - (smem_u32(dyn_smem) & 1023u)) & 1023u);
+  return r;
 }
 
 __global__ void __launch_bounds__(RING_THREADS, 2)
@@ -386,22 +261,21 @@ pair_iou_st_ring_kernel(const __grid_constant__ CUtensorMap map, int N, long lon
                         int tile_first, int tile_step, unsigned long long* __restrict__ inter) {
   extern __shared__ __align__(1024) unsigned char smem_ring[];
   __shared__ uint64_t full[NSTAGE], empty[NSTAGE];
-  if (threadIdx.x == 0) {
-    for (int b = 0; b < NSTAGE; ++b) { mbar_init(full + b, 1); mbar_init(empty + b, ST_THREADS / 32); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  const RingSetup r = ring_setup(smem_ring, full, empty, nt, n_tiles, splits, tile_first, tile_step, 0, (words + STAGE_WORDS - 1) / STAGE_WORDS);
+  const CUtensorMap* m = &map;
+  const int ti = r.ti, tj = r.tj;
+  if (ti == tj) {
+    st_tile_ring<true>([=](unsigned char* dst, int w0, uint64_t* bar) { tma_load_2d(dst, m, w0, ti * PT, bar); },
+                       N, ti, tj, r.s_begin, r.s_end, r.boxes, full, empty, inter);
+  } else {
+    st_tile_ring<false>([=](unsigned char* dst, int w0, uint64_t* bar) {
+      tma_load_2d(dst, m, w0, ti * PT, bar);
+      tma_load_2d(dst + TMA_BOX_BYTES, m, w0, tj * PT, bar);
+    }, N, ti, tj, r.s_begin, r.s_end, r.boxes, full, empty, inter);
   }
-  __syncthreads();
-  const int tile = tile_first + (blockIdx.x % n_tiles) * tile_step, split = blockIdx.x / n_tiles;
-  int ti, tj;
-  tile_from_index(tile, nt, ti, tj);
-  const long long stages = (words + STAGE_WORDS - 1) / STAGE_WORDS;
-  const long long s_begin = stages * split / splits, s_end = stages * (split + 1) / splits;
-  unsigned char* boxes = smem_ring + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_ring) & 1023u)) & 1023u);
-  if (ti == tj) st_tile_body_ring<true>(&map, N, ti, tj, s_begin, s_end, boxes, full, empty, inter);
-  else st_tile_body_ring<false>(&map, N, ti, tj, s_begin, s_end, boxes, full, empty, inter);
 }
 
-// ---- ring variant whose producer loads the tiles straight out of PEER GPUs' memory (EXPERIMENTAL: compiled, not yet run on hardware) --
+// ---- the same ring with a producer that loads the tiles straight out of PEER GPUs' memory ------------------------------------------
 // One kernel that is both the exchange and the math of BASELINE config 5: every rank's packed planes sit in an NVLink-mapped buffer
 // (n_local tracks x words), one rank-2 tensor map per rank; the producer lane splits each 64-row operand tile into pieces of
 // `box_rows` rows (a divisor of 64 and of n_local, so a piece never straddles two ranks) and issues one `cp.async.bulk.tensor.2d`
@@ -409,102 +283,32 @@ pair_iou_st_ring_kernel(const __grid_constant__ CUtensorMap map, int N, long lon
 // Rows beyond a rank's n_local (and the K tail) are zero-filled by the hardware and still count towards the stage's byte total.
 struct PeerMaps { CUtensorMap m[8]; };
 
-template <bool DIAG>
-__device__ __forceinline__ void st_tile_body_ring_peer(const PeerMaps* __restrict__ maps, int world, int n_local, int box_rows, int N,
-                                                       int ti, int tj, long long s_begin, long long s_end, unsigned char* smem,
-                                                       uint64_t* full, uint64_t* empty, unsigned long long* __restrict__ inter) {
-  const int tid = threadIdx.x;
-  const long long n_st = s_end - s_begin;
-  if (tid >= ST_THREADS) {
-    if (tid == ST_THREADS) {
-      const int pieces = PT / box_rows;
-      for (long long s = 0; s < n_st; ++s) {
-        const int buf = (int)(s % NSTAGE);
-        if (s >= NSTAGE) mbar_wait(empty + buf, (unsigned)(((s / NSTAGE) - 1) & 1));
-        unsigned char* dst = smem + (size_t)buf * 2 * TMA_BOX_BYTES;
-        mbar_expect_tx(full + buf, DIAG ? TMA_BOX_BYTES : 2 * TMA_BOX_BYTES);
-        const int w0 = (int)((s_begin + s) * STAGE_WORDS);
-        for (int op = 0; op < (DIAG ? 1 : 2); ++op) {
-          const int tile = op == 0 ? ti : tj;
-          for (int p = 0; p < pieces; ++p) {
-            const int g0 = tile * PT + p * box_rows;                    // global index of the piece's first track
-            int owner = g0 / n_local;
-            if (owner > world - 1) owner = world - 1;                   // past the last track: out-of-range rows -> hardware zero fill
-            tma_load_2d(dst + (size_t)op * TMA_BOX_BYTES + (size_t)p * box_rows * STAGE_WORDS * 4, &maps->m[owner], w0,
-                        g0 - owner * n_local, full + buf);
-          }
-        }
-      }
-    }
-    return;
-  }
-  const int tx = tid & 15, ty = tid >> 4, lane = tid & 31;
-  Csa acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = Csa{0u, 0u, 0};
-  for (long long s = 0; s < n_st; ++s) {
-    const int bufi = (int)(s % NSTAGE);
-    mbar_wait(full + bufi, (unsigned)((s / NSTAGE) & 1));
-    const uint4* A = reinterpret_cast<const uint4*>(smem + (size_t)bufi * 2 * TMA_BOX_BYTES);
-    const uint4* B = DIAG ? A : A + TMA_BOX_BYTES / 16;
-#pragma unroll
-    for (int q = 0; q < KQ; ++q) {
-      uint4 a[4], b[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int ra = ty + 16 * r, rb = tx + 16 * r;
-        a[r] = A[ra * KQ + (q ^ (ra & 7))];
-        b[r] = B[rb * KQ + (q ^ (rb & 7))];
-      }
-#pragma unroll
-      for (int ri = 0; ri < 4; ++ri) {
-        if ((a[ri].x | a[ri].y | a[ri].z | a[ri].w) == 0u) continue;
-#pragma unroll
-        for (int rj = 0; rj < 4; ++rj) {
-          if (DIAG && rj < ri) continue;
-          csa_quad(acc[ri][rj], a[ri], b[rj]);
-        }
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty + bufi);
-  }
-#pragma unroll
-  for (int ri = 0; ri < 4; ++ri)
-#pragma unroll
-    for (int rj = 0; rj < 4; ++rj) {
-      if (DIAG && rj < ri) continue;
-      const int i = ti * PT + ty + 16 * ri, j = tj * PT + tx + 16 * rj;
-      if (i >= N || j >= N) continue;
-      if (DIAG && ri == rj && tx < ty) continue;
-      const unsigned long long v = (unsigned long long)csa_total(acc[ri][rj]);
-      if (v == 0) continue;
-      atomicAdd(inter + (long long)i * N + j, v);
-      if (i != j) atomicAdd(inter + (long long)j * N + i, v);
-    }
-}
-
 __global__ void __launch_bounds__(RING_THREADS, 2)
 pair_iou_st_ring_peer_kernel(const __grid_constant__ PeerMaps maps, int world, int n_local, int box_rows, int nt, int n_tiles, int splits,
                              long long stage_lo, long long stage_hi, unsigned long long* __restrict__ inter) {
   extern __shared__ __align__(1024) unsigned char smem_peer[];
   __shared__ uint64_t full[NSTAGE], empty[NSTAGE];
-  if (threadIdx.x == 0) {
-    for (int b = 0; b < NSTAGE; ++b) { mbar_init(full + b, 1); mbar_init(empty + b, ST_THREADS / 32); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  const RingSetup r = ring_setup(smem_peer, full, empty, nt, n_tiles, splits, 0, 1, stage_lo, stage_hi);
+  const int N = world * n_local, ti = r.ti, tj = r.tj;
+  const PeerMaps* pm = &maps;
+  auto load_operand = [=](unsigned char* dst, int w0, int tile, uint64_t* bar) {
+    const int pieces = PT / box_rows;
+    for (int p = 0; p < pieces; ++p) {
+      const int g0 = tile * PT + p * box_rows;                    // global index of the piece's first track
+      int owner = g0 / n_local;
+      if (owner > world - 1) owner = world - 1;                   // past the last track: out-of-range rows -> hardware zero fill
+      tma_load_2d(dst + (size_t)p * box_rows * STAGE_WORDS * 4, &pm->m[owner], w0, g0 - owner * n_local, bar);
+    }
+  };
+  if (ti == tj) {
+    st_tile_ring<true>([=](unsigned char* dst, int w0, uint64_t* bar) { load_operand(dst, w0, ti, bar); },
+                       N, ti, tj, r.s_begin, r.s_end, r.boxes, full, empty, inter);
+  } else {
+    st_tile_ring<false>([=](unsigned char* dst, int w0, uint64_t* bar) {
+      load_operand(dst, w0, ti, bar);
+      load_operand(dst + TMA_BOX_BYTES, w0, tj, bar);
+    }, N, ti, tj, r.s_begin, r.s_end, r.boxes, full, empty, inter);
   }
-  __syncthreads();
-  const int tile = blockIdx.x % n_tiles, split = blockIdx.x / n_tiles;
-  int ti, tj;
-  tile_from_index(tile, nt, ti, tj);
-  const long long stages = stage_hi - stage_lo;
-  const long long s_begin = stage_lo + stages * split / splits, s_end = stage_lo + stages * (split + 1) / splits;
-  unsigned char* boxes = smem_peer + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_peer) & 1023u)) & 1023u);
-  const int N = world * n_local;
-  if (ti == tj) st_tile_body_ring_peer<true>(&maps, world, n_local, box_rows, N, ti, tj, s_begin, s_end, boxes, full, empty, inter);
-  else st_tile_body_ring_peer<false>(&maps, world, n_local, box_rows, N, ti, tj, s_begin, s_end, boxes, full, empty, inter);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -520,7 +324,6 @@ static EncodeTiledFn tensor_map_encoder() {
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
       fn = reinterpret_cast<EncodeTiledFn>(p);
-    if (getenv("SOLA_NO_TMA")) fn = nullptr;
   }
   return fn;
 }
@@ -657,32 +460,10 @@ static int launch_pair_iou_st(const uint32_t* packed, int N, long long words_per
       SOLA_REQUIRE(splits * n_tiles < (1ll << 31), "pair_iou_st: grid too large");
       CUtensorMap map;
       if (make_track_map(packed, N, words_per_track, &map)) {
-        // TMA-staged tiles (UTMALDG): one elected thread per stage instead of 4 cp.async per thread
-        // default: warp-specialised ring (producer warp + empty/full mbarriers, no CTA barrier per stage): 3-4 % faster than the
-        // __syncthreads version below, which SOLA_K2_RING=0 selects (kept for A/B runs together with its PLAIN / OCC variants)
-        static const int ring_sel = [] { const char* e = getenv("SOLA_K2_RING"); return e ? atoi(e) : 1; }();
-        if (ring_sel) {
-          SOLA_CUDA(cudaFuncSetAttribute(pair_iou_st_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
-          pair_iou_st_ring_kernel<<<(unsigned)(splits * n_tiles), RING_THREADS, smem + 1024, stream>>>(
-              map, N, words_per_track, nt, n_tiles, (int)splits, part, n_parts, reinterpret_cast<unsigned long long*>(inter_out));
-        } else {
-        // SOLA_K2_PLAIN = 0 (default: pure carry-save) / 2 / 3 plain quads of 8: the POPC : LOP3 balance (experiments)
-        static const int plain_sel = [] { const char* e = getenv("SOLA_K2_PLAIN"); return e ? atoi(e) : 0; }();
-        auto launch = [&](auto kernel) -> int {
-          SOLA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
-          kernel<<<(unsigned)(splits * n_tiles), ST_THREADS, smem + 1024, stream>>>(
-              map, N, words_per_track, nt, n_tiles, (int)splits, part, n_parts, reinterpret_cast<unsigned long long*>(inter_out));
-          return SOLA_OK;
-        };
-        // SOLA_K2_OCC (experiments): 3 = register-capped build (80 regs, 3 CTAs per SM), 2 = 128 regs at 2 CTAs per SM;
-        // default: ptxas' own choice (96 regs, 2 CTAs per SM)
-        static const int occ_sel = [] { const char* e = getenv("SOLA_K2_OCC"); return e ? atoi(e) : 0; }();
-        const int lrc = plain_sel == 2 ? launch(pair_iou_st_tma_kernel<0x24>)
-                      : plain_sel == 3 ? launch(pair_iou_st_tma_kernel<0x92>)
-                      : occ_sel == 3 ? launch(pair_iou_st_tma_kernel<K2_PLAIN_DEFAULT, 3>)
-                      : occ_sel == 2 ? launch(pair_iou_st_tma_kernel<K2_PLAIN_DEFAULT, 2>) : launch(pair_iou_st_tma_kernel<K2_PLAIN_DEFAULT>);
-        if (lrc != SOLA_OK) return lrc;
-        }
+        // TMA-staged tiles (UTMALDG), warp-specialised ring
+        SOLA_CUDA(cudaFuncSetAttribute(pair_iou_st_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
+        pair_iou_st_ring_kernel<<<(unsigned)(splits * n_tiles), RING_THREADS, smem + 1024, stream>>>(
+            map, N, words_per_track, nt, n_tiles, (int)splits, part, n_parts, reinterpret_cast<unsigned long long*>(inter_out));
       } else {
         SOLA_CUDA(cudaFuncSetAttribute(pair_iou_st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         pair_iou_st_kernel<<<(unsigned)(splits * n_tiles), ST_THREADS, smem, stream>>>(
