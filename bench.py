@@ -1,17 +1,27 @@
 #!/usr/bin/env python
-"""bench.py — masklet-frames/s of the masklet-scoring hot path on BASELINE.json config 2
+"""bench.py — masklet-frames/s of the masklet-scoring hot path (dedup + J&F) on BASELINE.json config 2
 ("Grid-prompt track dedup: 64 synthetic SAM2 masklets x 80 frames at 720x1280 with stability score and miou_thresh 0.7").
 
 One step = one video's pass over the path, inputs already in HBM:
-    K1  binarise + bit-pack + stability counts over 64 x 80 fp32 logit planes      (dominant, HBM bound)
-    R1  bilinear resize to 540 x 960 + > 0.5 of all 5120 packed planes             (seg_utils.reshape_masklet)
-    R2  nearest resize + pack of the 64 prompt masks
-    G1  reference-order greedy filter: K2-gather IoU per tracked batch + host suppression
-    K2  64 x 64 spatio-temporal intersection matrix of the resized masklets + index-order greedy (compute_masklet_iou semantics)
-    one D2H of the stability counts -> float64 scores
+    K1+R1  binarise + bit-pack + stability counts over 64 x 80 fp32 logit planes, fused with the bilinear resize to 540 x 960 + > 0.5
+           (generate_tokens_grid.py:215-224, prompt_generator.py:169-186, seg_utils.reshape_masklet)            dominant, HBM bound
+    R2     nearest resize + pack of the 64 prompt masks
+    G1     reference-order greedy filter: K2-gather IoU per tracked batch + host suppression (generate_tokens_grid.py:266-278)
+    K2     64 x 64 spatio-temporal intersection matrix of the resized masklets + index-order greedy (compute_masklet_iou semantics)
+    M1     the J-type half the grid loop really runs: per-frame |track ∩ gt|, |track|, |gt| of every track against G = 3 GT masklets
+           -> frame-mean precision / recall / IoU labels (generate_tokens_grid.py:253-264, utils.compute_mask_metrics)
+    one D2H of the count tables -> float64 scores on the host (overlapped with the next step)
 `value` = masklet-frames processed by all ranks / max-over-ranks device time (weak scaling: one video per GPU per step, no
-data-path collective).  `e2e` = the same step with the logits and prompt masks starting in pinned HOST memory (H2D inside the
-timed region, results read back).  `--impl reference` times the oracle port of the reference's CPU path on the host cores.
+data-path collective).  `e2e` = the same step with the logits, prompt masks and GT masks starting in pinned HOST memory (H2D inside
+the timed region, results read back).
+A SECOND timed region measures the evaluation half of the metric on a BASELINE config-4-shaped sweep (MeViS-like: mixed 360p-1080p
+units of 30-120 frames, bit-packed, resident in HBM): ONE launch of the fused J & F kernel per sweep (region counts + boundary-match
+counts), one read-back, the reference's J / F formulas on the host, and — for N > 1 — the final NCCL sum of the accumulators.  It
+fills `jf_stage` and `roofline_jf`.  With N > 1 a config-5-shaped slice (32 tracks per GPU x 200 frames of 1080p-derived planes) is
+also pushed through the two exchange paths (peer-memory pull pipelined with K2, NCCL all-to-all) and checked against the single-rank
+matrix (`cfg5`).
+`--impl reference` times the oracle port of the reference's own CPU path for the config-2 step on the host cores: a FULL 64-track
+step, timed once (`--steps` is honoured as min(steps, 1); the step takes tens of seconds).
 """
 from __future__ import annotations
 
@@ -33,7 +43,8 @@ if ROOT not in sys.path:
 
 METRIC = "masklet-frames/s (dedup+J&F)"
 UNIT = "masklet-frames/s"
-CFG = dict(n_tracks=64, n_frames=80, H=720, W=1280, miou_thresh=0.7, n_max_tracks=64, batch_size=4, bin_size=4)
+CFG = dict(n_tracks=64, n_frames=80, H=720, W=1280, miou_thresh=0.7, n_max_tracks=64, batch_size=4, bin_size=4, n_gt=3)
+JF_SWEEP = dict(n_videos=12, exprs_per_video=4, t_range=(30, 120))      # per GPU; config-4-shaped (MeViS valid_u: mixed 360p-1080p)
 
 
 def parse():
@@ -47,11 +58,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--streams", type=int, default=1, choices=[1, 2], help="videos in flight on separate CUDA streams")
-    ap.add_argument("--tail-priority", action="store_true",
-                    help="run everything after the fused K1+R1 (R2, K2 gather, K2 N x N, read-backs) on a HIGH-priority side stream, so the "
-                         "INT-bound K2 of video k shares the SMs with the HBM-bound K1+R1 of video k+1")
     ap.add_argument("--no-fuse", action="store_true", help="run K1 and R1 as two kernels instead of the fused one")
+    ap.add_argument("--no-jf", action="store_true", help="skip the config-4 J&F sweep region")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the config-5 exchange slice (N > 1 only)")
+    ap.add_argument("--jf-reps", type=int, default=20)
     ap.add_argument("--st-native", action="store_true",
                     help="N x N spatio-temporal IoU on the native 720x1280 planes instead of the 540x960 resized masklets the "
                          "reference's filter works on (generate_tokens_grid.py:248-250)")
@@ -124,13 +134,11 @@ class ClockSampler:
 # the step (product path)
 # ---------------------------------------------------------------------------------------------------------------
 class Workload:
-    def __init__(self, device, seed, n_tracks, n_frames, n_streams=1, fused=True, st_native=False, tail_priority=False):
+    def __init__(self, device, seed, n_tracks, n_frames, fused=True, st_native=False):
         import sola_b200 as S
-        self.n_streams = n_streams
-        self.tail_stream = torch.cuda.Stream(device=device, priority=-1) if tail_priority else None
+        from sola_b200 import synth
         self.fused = fused
         self.st_native = st_native
-        from sola_b200 import synth
         self.S, self.device = S, device
         self.N, self.T, self.H, self.W = n_tracks, n_frames, CFG["H"], CFG["W"]
         self.logits, prompts = synth.dedup_candidates(self.N, self.T, self.H, self.W, seed=seed, device=device, bin_size=CFG["bin_size"])
@@ -140,63 +148,49 @@ class Workload:
         self.packed = S.PackedMasks.empty((self.N, self.T), self.H, self.W, device)                   # reused outputs
         self.counts = torch.empty((3, self.N * self.T), dtype=torch.int32, device=device)
         self.k1_events = []
-        oh, ow = S.packed.default_target_shape(self.H, self.W)
+        self.oh, self.ow = S.packed.default_target_shape(self.H, self.W)
+        # GT masklets of the video at the resized shape (what `gt_masklets` holds, generate_tokens_grid.py:112): G objects x T frames
+        self.gt_masks = torch.stack([synth.blob_masklet(self.T, self.oh, self.ow, seed * 31 + g, device=device, fill=0.12 + 0.05 * g)
+                                     for g in range(CFG["n_gt"])])                                    # (G, T, oh, ow) uint8
+        self.gt_planes = S.pack_masks(self.gt_masks)
         self.k1_bytes = self.N * self.T * (self.H * self.W * 4 + self.H * ((self.W + 31) // 32) * 4 + 12)          # logits in, planes + 3 counts out
         if fused:
-            self.k1_bytes += self.N * self.T * oh * ((ow + 31) // 32) * 4                                           # + resized planes out
+            self.k1_bytes += self.N * self.T * self.oh * ((self.ow + 31) // 32) * 4                                 # + resized planes out
 
     def make_jobs(self):
         from sola_b200 import dedup
         mk = lambda: dedup.VideoDedupJob(self.prompt_meta, self.T, device=self.device, mode="grid", st_on_resized=not self.st_native, bin_size=CFG["bin_size"],
                                          n_max_tracks=CFG["n_max_tracks"], batch_size=CFG["batch_size"], miou_thresh=CFG["miou_thresh"])
         self.jobs = [mk(), mk()]
-        # one stream per in-flight video: the HBM-bound K1 of video k+1 overlaps the ALU/XU-bound R1 + K2 of video k
-        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.jobs] if self.n_streams > 1 else [None, None]
-        two = self.n_streams > 1 or self.tail_stream is not None              # two videos in flight need two sets of output buffers
-        self.packed_slots = [self.packed, self.S.PackedMasks.empty((self.N, self.T), self.H, self.W, self.device)] if two else [self.packed, self.packed]
-        self.counts_slots = [self.counts, torch.empty_like(self.counts)] if two else [self.counts, self.counts]
+        for j in self.jobs:
+            j.set_gt_masklets(self.gt_planes)
 
     def enqueue(self, slot, logits=None, prompt_masks=None, record_k1=False):
-        """Device half of one step (no synchronisation): K1, R1, R2, K2-gather, K2 N x N, async read-back."""
+        """Device half of one step (no synchronisation): K1+R1, R2, K2-gather, K2 N x N, label counts, async read-back."""
         job = self.jobs[slot]
         logits = self.logits if logits is None else logits
         prompt_masks = self.prompt_masks_dev if prompt_masks is None else prompt_masks
-        if self.streams[slot] is not None:
-            with torch.cuda.stream(self.streams[slot]):
-                self._enqueue(job, slot, logits, prompt_masks, record_k1)
-        else:
-            self._enqueue(job, slot, logits, prompt_masks, record_k1)
-
-    def _enqueue(self, job, slot, logits, prompt_masks, record_k1):
-        packed_out, counts_out = self.packed_slots[slot], self.counts_slots[slot]
         S = self.S
         # the dominant kernel is the first launch of the step: bracket it with events on the launching stream
         if record_k1:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         if self.fused:
-            packed, counts, resized = S.binarize_pack_resize(logits, 0.0, 1.0, out=packed_out, counts_out=counts_out)      # K1 + R1
+            packed, counts, resized = S.binarize_pack_resize(logits, 0.0, 1.0, out=self.packed, counts_out=self.counts)      # K1 + R1
         else:
-            packed, counts = S.binarize_pack_stability(logits, 0.0, 1.0, out=packed_out, counts_out=counts_out)            # K1
+            packed, counts = S.binarize_pack_stability(logits, 0.0, 1.0, out=self.packed, counts_out=self.counts)            # K1
         if record_k1:
             e1.record()
             self.k1_events.append((e0, e1))
         if not self.fused:
             resized = S.resize_bilinear_bin(packed)                                                                        # R1
-        if self.tail_stream is not None:
-            done = torch.cuda.Event()
-            done.record()
-            with torch.cuda.stream(self.tail_stream):
-                self.tail_stream.wait_event(done)
-                job._enqueue_tail(packed, resized, counts, prompt_masks)
-            return
-        job._enqueue_tail(packed, resized, counts, prompt_masks)                                                           # R2, K2 gather, K2 N x N, read-backs
+        job._enqueue_tail(packed, resized, counts, prompt_masks)                                         # R2, K2 gather, K2 N x N, labels, read-backs
 
     def finish(self, slot):
-        """Host half: wait for that step's read-back, replay both greedy filters, stability scores."""
+        """Host half: wait for that step's read-back, replay both greedy loops, stability scores, label metrics."""
         r = self.jobs[slot].finish()
         return {"tracked": r["tracked"], "filtered": r["filtered"], "kept_st": r["kept_spatiotemporal"], "stability": r["stability"],
-                "inter": r["inter"]}
+                "inter": r["inter"], "labels": r.get("labels")}
 
     def step(self, logits=None, prompt_masks=None):
         self.enqueue(0, logits, prompt_masks)
@@ -226,117 +220,262 @@ def checks(w: Workload, out) -> dict:
     if w.st_native:
         assert np.array_equal(c[1].sum(1, dtype=np.int64), area), "diag(inter) != sum of K1 areas (checksum of checksums)"
     else:
-        _, r_area = w.S.resize_bilinear_bin(w.packed, want_area=True)                  # untimed: R1's own per-frame areas
+        rz, r_area = w.S.resize_bilinear_bin(w.packed, want_area=True)                 # untimed: R1's own per-frame areas
         r_area = r_area.view(w.N, w.T).cpu().numpy().sum(1, dtype=np.int64)
         assert np.array_equal(r_area, area), "diag(inter) != sum of R1 areas (checksum of checksums)"
     assert (c[0] <= c[1]).all() and (c[1] <= c[2]).all(), "stability counts not nested"
     assert (inter <= np.minimum(area[:, None], area[None, :])).all()
-    # sub-sample vs the oracle: 2 tracks x 3 frames of planes + their pair intersection
+    # sub-sample vs the oracle: 2 tracks x 3 frames of planes, their stability scores, and the label metrics of track 0 vs GT 0
     sub = w.logits[:2, :3].float().cpu()
     planes = w.packed.words[:2, :3].cpu().numpy().view(np.uint32)
     assert np.array_equal(planes, O.pack_bits(sub.numpy() > 0)), "K1 planes differ from the oracle on the sub-sample"
     s = O.get_stability_score(sub.numpy())
     assert np.array_equal(np.nan_to_num(s, nan=-1), np.nan_to_num(out["stability"][:2, :3], nan=-1)), "stability differs"
-    return {"tracked": len(out["tracked"]), "filtered": len(out["filtered"]), "kept_spatiotemporal": len(out["kept_st"])}
+    lab = out["labels"]
+    rz0 = w.S.unpack_masks(w.S.resize_bilinear_bin(w.packed[0]), torch.float32).cpu()
+    p_, r_, i_ = O.compute_mask_metrics(rz0, w.gt_masks[0].float().cpu())
+    assert (float(p_), float(r_), float(i_)) == (float(lab["precision"][0, 0]), float(lab["recall"][0, 0]), float(lab["iou"][0, 0])), \
+        "label metrics differ from the oracle's compute_mask_metrics"
+    return {"tracked": len(out["tracked"]), "filtered": len(out["filtered"]), "kept_spatiotemporal": len(out["kept_st"]),
+            "labels": f"{lab['iou'].shape[0]} tracks x {lab['iou'].shape[1]} GT objects, mean IoU {float(lab['iou'].mean()):.4f}"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# CPU arm (oracle port of the reference's own CPU path), bounded sample scaled to the full step
+# CPU arm: the oracle port of the reference's own CPU path, a FULL config-2 step timed once
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference_step(logits_cpu: torch.Tensor, prompts, n_pairs_st: int):
-    """The reference's operations on a sample: per-track linear stages, greedy IoU pairs, spatio-temporal pairs.
-    Returns seconds (t_linear_per_track, t_gather_pair, t_st_pair).  Works on CPU tensors (the CPU arm) and on CUDA tensors
-    (the reference's own GPU path: generic ATen launches with a .item() sync per scalar)."""
+class _Clock:
+    def __init__(self):
+        self.t = {}
+
+    def timed(self, key, fn):
+        def wrapped(*a, **k):
+            t0 = time.perf_counter()
+            r = fn(*a, **k)
+            self.t[key] = self.t.get(key, 0.0) + time.perf_counter() - t0
+            return r
+        return wrapped
+
+
+def cpu_reference_step(n_tracks, n_frames, seed=1234 + 2, st_pair_sample=6, gen_device=None):
+    """The reference's grid loop (generate_tokens_grid.py:133-292 via oracle/greedy_oracle.py) on synthetic SAM2 logits, with every
+    dense operation the loop runs per tracked batch: per-frame binarise + cat (:215-224), stability score per plane
+    (prompt_generator.py:169-186; named by BASELINE config 2), reshape_masklet (:248-250), the label metrics against every GT object
+    (:253-264) and the greedy suppression pairs (:266-278: nearest resize + compute_mask_iou).  Input generation is NOT timed.
+    Returns (seconds per stage, bookkeeping)."""
+    from oracle import greedy_oracle as GO
     from oracle import maskpath_oracle as O
-    S_, T = logits_cpu.shape[:2]
-    on_gpu = logits_cpu.is_cuda
-    sync = torch.cuda.synchronize if on_gpu else (lambda: None)
-    sync()
-    t0 = time.perf_counter()
-    masklets, resized = [], []
-    for i in range(S_):
-        frames = [O.binarize(logits_cpu[i, t][None]) for t in range(T)]                  # generate_tokens_grid.py:219 per frame
-        m = torch.cat(frames, 0)                                                         # :224
-        masklets.append(m)
-        _ = [O.get_stability_score(logits_cpu[i, t].cpu().numpy()) for t in range(T)]    # prompt_generator.py:169 (numpy, per plane)
-        resized.append(O.reshape_masklet(m))                                             # seg_utils.py:145
-    sync()
-    t_lin = (time.perf_counter() - t0) / S_
-    t0 = time.perf_counter()
-    n_g = 0
-    for i in range(S_):
-        for p in prompts[: 2 * S_]:
-            pm = O.resize_prompt_nearest(p["segmentation"], resized[i].shape[1], resized[i].shape[2])       # :271-272
-            if on_gpu:
-                pm = pm.to(logits_cpu.device)              # the reference does this H2D inside the loop (:271)
-            O.compute_mask_iou(resized[i][p["frame_idx"]], pm)                                                # :273
-            n_g += 1
-    t_g = (time.perf_counter() - t0) / max(n_g, 1)
-    t0 = time.perf_counter()
-    n_st = 0
-    for i in range(S_):
-        for j in range(i + 1, S_):
-            if n_st >= n_pairs_st:
-                break
-            O.compute_masklet_iou(resized[i], resized[j], resized[i].device)   # seg_utils.py:110 on the resized masklets (all that exist after grid :248-250)
-            n_st += 1
-    t_st = (time.perf_counter() - t0) / max(n_st, 1)
-    return t_lin, t_g, t_st
-
-
-def cpu_arm(n_tracks, n_frames, steps, warmup, sample_tracks=4, device="cpu"):
     from sola_b200 import synth
-    logits, prompts = synth.dedup_candidates(sample_tracks, n_frames, CFG["H"], CFG["W"], seed=1234 + 2, device="cpu", bin_size=CFG["bin_size"])
-    if device != "cpu":
-        logits = logits.to(device)
-    n_pairs = sample_tracks * (sample_tracks - 1) // 2
-    times = []
-    for it in range(warmup + steps):
-        t = cpu_reference_step(logits, prompts, n_pairs)
-        if it >= warmup:
-            times.append(t)
-    t_lin, t_g, t_st = (float(np.mean([x[k] for x in times])) for k in range(3))
-    N = n_tracks
-    # full step on the CPU: N linear stages, ~N*N/2 greedy pairs (every tracked masklet vs the remaining prompts), N(N-1)/2 volume pairs
-    full = N * t_lin + (N * (N - 1) // 2) * t_g + (N * (N - 1) // 2) * t_st
-    value = N * n_frames / full
-    sample = (f"{sample_tracks} tracks x {n_frames} frames x {CFG['H']}x{CFG['W']} through binarise+cat+stability+reshape_masklet "
-              f"({t_lin * 1e3:.0f} ms/track), {2 * sample_tracks * sample_tracks} greedy mask-IoU pairs ({t_g * 1e6:.0f} us/pair), "
-              f"{n_pairs} compute_masklet_iou pairs ({t_st * 1e3:.0f} ms/pair); scaled to {N} tracks: "
-              f"{N}*t_track + {N * (N - 1) // 2}*(t_gather + t_masklet_pair) = {full:.1f} s/step")
-    return value, full, sample
+    H, W = CFG["H"], CFG["W"]
+    dev = gen_device if gen_device is not None else "cpu"
+    logits, prompts = synth.dedup_candidates(n_tracks, n_frames, H, W, seed=seed, device=dev, bin_size=CFG["bin_size"])
+    if logits.is_cuda:                                           # synthetic inputs may be GENERATED on the GPU (faster); the timed work is all CPU
+        host = torch.empty(logits.shape, dtype=logits.dtype)
+        for i in range(0, n_tracks, 8):
+            host[i:i + 8] = logits[i:i + 8].cpu()
+        logits = host
+        torch.cuda.empty_cache()
+    oh, ow = O.default_target_shape(H, W)
+    gts = [synth.blob_masklet(n_frames, oh, ow, seed * 31 + g, device="cpu", fill=0.12 + 0.05 * g).float() for g in range(CFG["n_gt"])]
+    clk = _Clock()
+
+    def binarise_and_stability(frame_idx, batch):
+        out = {}
+        for p in batch:
+            i = p["prompt_id"]
+            frames = [O.binarize(logits[i, t][None]) for t in range(n_frames)]                 # :219 per frame
+            out[i] = torch.cat(frames, 0)                                                      # :224
+            _ = [O.get_stability_score(logits[i, t].numpy()) for t in range(n_frames)]         # prompt_generator.py:169 per plane
+        return out
+
+    def reshape_and_label(m):
+        r = clk.timed("reshape_masklet", O.reshape_masklet)(m)
+        for g in gts:                                                                          # :256-264
+            clk.timed("label_metrics", O.compute_mask_metrics)(r, g)
+        return r
+
+    class Impl:
+        compute_mask_iou = staticmethod(clk.timed("greedy_pairs", O.compute_mask_iou))
+        reshape_masklet = staticmethod(reshape_and_label)
+
+    t0 = time.perf_counter()
+    res = GO.grid_greedy([dict(p) for p in prompts], n_frames, clk.timed("binarise_cat_stability", binarise_and_stability),
+                         bin_size=CFG["bin_size"], n_max_tracks=CFG["n_max_tracks"], batch_size=CFG["batch_size"], miou_thresh=CFG["miou_thresh"], impl=Impl)
+    t_step = time.perf_counter() - t0
+    # the dead-code volume IoU (seg_utils.compute_masklet_iou has no caller in the reference): timed on a few pairs, reported apart
+    a = O.reshape_masklet((logits[0] > 0).float())
+    b = O.reshape_masklet((logits[1] > 0).float())
+    t0 = time.perf_counter()
+    for _ in range(st_pair_sample):
+        O.compute_masklet_iou(a, b, "cpu")
+    t_pair = (time.perf_counter() - t0) / st_pair_sample
+    stages = dict(clk.t)
+    stages["greedy_other (nearest resize, control flow)"] = max(0.0, t_step - sum(clk.t.values()))
+    return t_step, stages, t_pair, res
 
 
-def jf_stage(device):
-    """The J&F half of the metric (BASELINE configs 1 / 4), untimed with respect to the step above and informative only: the drop-in
-    Evaluator.compute_J + compute_F call on config 1 (30 x 480 x 854 fp32 masklets resident on the device, one read-back per call),
-    the K3 count kernel on a 320-frame 720p batch, and the boundary-F extension."""
+def reference_line(args, n_tracks, n_frames, workload):
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    cores = torch.get_num_threads()
+    gen = torch.device("cuda", 0) if torch.cuda.is_available() else None
+    # warm the thread pool / allocator on a 2-track slice (untimed), then ONE full step
+    cpu_reference_step(2, min(n_frames, 8), gen_device=gen)
+    t_step, stages, t_pair, res = cpu_reference_step(n_tracks, n_frames, gen_device=gen)
+    n_pairs = n_tracks * (n_tracks - 1) // 2
+    value = n_tracks * n_frames / t_step
+    with_pairs = n_tracks * n_frames / (t_step + n_pairs * t_pair)
+    sample = (f"FULL step, timed once: {n_tracks} tracks x {n_frames} frames x {CFG['H']}x{CFG['W']} through the reference grid loop "
+              f"({len(res['tracked'])} tracked, {len(res['filtered'])} filtered) = {t_step:.1f} s; stages (s): "
+              + ", ".join(f"{k} {v:.2f}" for k, v in stages.items()))
+    return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": 1,
+            "warmup": 0, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload,
+                       "note": "oracle port of the reference's CPU path (the reference is Python; /root/reference does not exist on the GPU box), "
+                               "torch-CPU / numpy ops on all host threads; ONE full step is timed (--steps is honoured as min(steps, 1), --warmup "
+                               "as an untimed 2-track run) because a step takes tens of seconds; one rank regardless of --gpus. The headline "
+                               "excludes the N x N compute_masklet_iou pairs, which are dead code in the reference (SURVEY.md §0); "
+                               "`with_dead_code_st_pairs` adds them (per-pair time measured on a sample)",
+                       "requested_steps": args.steps, "requested_warmup": args.warmup},
+            "stage_s": stages,
+            "with_dead_code_st_pairs": {"value": with_pairs, "unit": UNIT, "pairs": n_pairs, "s_per_pair": t_pair,
+                                        "extrapolated": True},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def cpu_baseline_sample(n_tracks_sample, n_frames):
+    """Bounded sample for the product run's `cpu_baseline` leg: the same reference step on the first tracks only (~10-20 s)."""
+    t_step, stages, t_pair, res = cpu_reference_step(n_tracks_sample, n_frames, gen_device=torch.device("cuda", torch.cuda.current_device()))
+    value = n_tracks_sample * n_frames / t_step
+    sample = (f"{n_tracks_sample}-track sample of the config-2 step (same generator, same loop) x {n_frames} frames x {CFG['H']}x{CFG['W']}: "
+              f"{t_step:.1f} s; stages (s): " + ", ".join(f"{k} {v:.2f}" for k, v in stages.items())
+              + "; the per-track stages dominate, so masklet-frames/s is size-independent to first order")
+    return value, sample
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# second timed region: config-4-shaped J&F sweep through the fused kernel
+# ---------------------------------------------------------------------------------------------------------------
+def jf_region(device, rank, world, reps, peak):
+    import torch.distributed as dist
     import sola_b200 as S
-    from sola_b200 import evaluator, synth
+    from sola_b200 import evaluator, packed as P, sharding, synth
+    units = synth.mevis_like_sweep(JF_SWEEP["n_videos"], JF_SWEEP["exprs_per_video"], 1234 + 4 + 1000 * rank, device,
+                                   t_range=JF_SWEEP["t_range"], pack=S.pack_masks)
+    pairs = [(p, g) for _, _, p, g in units]
+    plan = P.JFSweepPlan(pairs, with_boundary=True)
+    buf = torch.empty((7, plan.total_frames), dtype=torch.int32, device=device)
+    host = torch.empty((7, plan.total_frames), dtype=torch.int32).pin_memory()
 
-    def timed(fn, reps):
-        fn()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+    def sweep_once():
+        """ONE launch for the whole sweep, one read-back, the reference's formulas per unit on the host, the integer audit."""
+        plan.run(buf)
+        host.copy_(buf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        c = host.numpy()
+        Js, Fs, Fbs = [], [], []
+        tot = np.zeros(3, np.int64)
+        for k in range(plan.n_units):
+            u = c[:, plan.offsets[k]: plan.offsets[k] + plan.frames[k]]
+            Js.append(float(evaluator.J_from_counts(u[0], u[1], u[2])))
+            Fs.append(float(evaluator.F_from_counts(u[0], u[1], u[2])))
+            Fbs.append(evaluator.F_boundary_from_counts(u[3], u[4], u[5], u[6]))
+            tot += u[:3].sum(axis=1, dtype=np.int64)
+        return Js, Fs, Fbs, tot
+
+    for _ in range(3):
+        Js, Fs, Fbs, tot = sweep_once()
+    # parity inside the run: one unit against the oracles (untimed)
+    from oracle import boundary_oracle as BO
+    from oracle import maskpath_oracle as O
+    k = min(range(plan.n_units), key=lambda i: pairs[i][0].words.numel())
+    pu, gu = (S.unpack_masks(x, torch.uint8).cpu().numpy() for x in pairs[k])
+    assert Js[k] == float(O.J_from_counts(*O.jf_counts_exact(pu, gu))) and abs(Fbs[k] - BO.boundary_f_masklet(pu, gu)) < 1e-12, \
+        "fused J&F kernel differs from the oracles on the checked unit"
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    # (a) kernel only, CUDA events on the launching stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        plan.run(buf)
+    e1.record()
+    torch.cuda.synchronize()
+    k_ms = e0.elapsed_time(e1) / reps
+    # (b) the whole sweep incl. read-back, host formulas and (N > 1) the final NCCL sum of the accumulators
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_sw = max(3, reps // 4)
+    for _ in range(n_sw):
+        Js, Fs, Fbs, tot = sweep_once()
+        red = sharding.allreduce_jf(sum(Js), sum(Fs), sum(0.5 * (a + b) for a, b in zip(Js, Fs)), len(Js), tot, device=device)
+    torch.cuda.synchronize()
+    dt = torch.tensor([(time.perf_counter() - t0) / n_sw, k_ms * 1e-3, float(plan.total_frames)], dtype=torch.float64, device=device)
+    frames = dt[2:].clone()
+    if world > 1:
+        dist.all_reduce(dt[:2], op=dist.ReduceOp.MAX)
+        dist.all_reduce(frames, op=dist.ReduceOp.SUM)
+    sweep_s, kern_s, total_frames = float(dt[0]), float(dt[1]), float(frames[0])
+    ach = plan.algorithmic_bytes / (k_ms * 1e-3) / 1e9
+    stage = {"workload": f"config4-shaped J&F sweep: {plan.n_units} (video, expression) units per GPU, {plan.total_frames} frame pairs, "
+                         f"mixed 360p-1080p, {JF_SWEEP['t_range'][0]}-{JF_SWEEP['t_range'][1]} frames, bit-packed in HBM; J + F(Dice) + F(boundary)",
+             "masklet_frames_per_s": total_frames / sweep_s, "kernel_only_masklet_frames_per_s": total_frames / kern_s,
+             "ms_per_sweep": sweep_s * 1e3, "kernel_ms": kern_s * 1e3, "launches_per_sweep": 1, "n_gpus": world,
+             "mean_J": red["mean_J"], "mean_F": red["mean_F"], "mean_F_boundary": float(np.mean(Fbs)),
+             "int_totals": [int(x) for x in red["int_totals"]], "timed": "CUDA events (kernel) / host clock around launch + read-back + host formulas"
+             + (" + NCCL all-reduce" if world > 1 else ""), "parity": "one unit checked against oracle.J_from_counts / boundary_oracle inside the run"}
+    roof = {"bound": "hbm", "kernel": "jf_fused_kernel (J + F + boundary-F: TMA-staged tiles, boundary maps + sparse disk dilation in smem)",
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "bytes_per_launch": int(plan.algorithmic_bytes),
+            "ms_per_launch": k_ms, "work_items": int(plan.n_items),
+            "note": "algorithmic bytes = both bit-packed planes of every frame pair read once; the kernel is issue-bound on the boundary "
+                    "phases (profiles/), so the HBM fraction is the honest distance to its floor"}
+    return stage, roof
+
+
+def cfg5_region(device, rank, world):
+    """BASELINE config 5 slice (N > 1): 32 tracks per GPU x 200 frames of 1080p-derived 540x960 planes; the N x N matrix through the
+    peer-memory pull pipelined with K2 and through the NCCL all-to-all, both checked against the single-rank matrix on rank 0."""
+    import torch.distributed as dist
+    import sola_b200 as S
+    from sola_b200 import packed as P, sharding, synth
+    n_local, T, H, W = 32, 200, 540, 960
+    peers = sharding.PeerPlanes(n_local, T, H, W, device)
+    for i in range(n_local):
+        gidx = rank * n_local + i
+        m = synth.blob_masklet(T, H, W, 500 + gidx % max(1, (n_local * world) // 3), device=device, fill=0.10 + 0.02 * (gidx % 5))
+        peers.local.words[i] = S.pack_masks(m).words
+    torch.cuda.synchronize()
+    dist.barrier()
+
+    def timed(fn, reps=3):
+        best, out = None, None
         for _ in range(reps):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / reps
-
-    p1, g1 = synth.jf_pair(30, 480, 854, seed=1235, device=device)
-    p1f, g1f = p1.float(), g1.float()
-    ms1 = timed(lambda: evaluator.compute_JF(p1f, g1f), 50)
-    T = 320
-    a = (synth.smooth_logits(T, 720, 1280, 5, device=device, cell=120) > 0).float()
-    b = (synth.smooth_logits(T, 720, 1280, 6, device=device, cell=120) > 0).float()
-    ms3 = timed(lambda: S.frame_counts(a, b), 10)
-    pa, pb = S.pack_masks(a), S.pack_masks(b)
-    msb = timed(lambda: S.boundary_counts(pa, pb), 3)
-    return {"config1_compute_J_and_F_call": {"ms": ms1, "masklet_frames_per_s": 30 / ms1 * 1e3, "shape": "30 x 480 x 854 fp32, incl. read-back"},
-            "K3_counts_fp32_720p": {"GBps": 2 * a.numel() * 4 / ms3 / 1e6, "masklet_frames_per_s": T / ms3 * 1e3},
-            "boundary_F_720p": {"masklet_frames_per_s": T / msb * 1e3}}
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = fn()
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = float(t) if best is None else min(best, float(t))
+        return best, out
+    pull_ms, m_pull = timed(lambda: peers.pairwise_inter_matrix("pull"))
+    a2a_ms, m_a2a = timed(lambda: sharding.pairwise_inter_matrix_sharded(peers.local, split="words"))
+    gathered = torch.empty((n_local * world, T, H, peers.local.Wp), dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(gathered, peers.local.words.contiguous())
+    identical = None
+    if rank == 0:
+        alone = S.pairwise_inter_matrix(S.PackedMasks(gathered, H, W))
+        identical = bool(torch.equal(alone, m_pull) and torch.equal(alone, m_a2a))
+    words = T * H * peers.local.Wp
+    remote_bytes = (world - 1) * n_local * (words // world) * 4            # what one rank pulls over NVLink
+    return {"workload": f"config5-shaped slice: {n_local * world} tracks x {T} frames x {H}x{W} planes, {n_local} tracks per GPU",
+            "peer_pull_pipelined_ms": pull_ms, "nccl_all_to_all_ms": a2a_ms, "identical_to_single_rank": identical,
+            "nvlink_GBps_per_rank_pull": remote_bytes / (pull_ms * 1e-3) / 1e9,
+            "note": "exchange + K2 over this rank's word slice + all-reduce of the int64 matrix, max over ranks, best of 3"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -346,23 +485,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_tracks, n_frames = args.tracks, args.frames
-    workload = f"config2: grid-prompt track dedup, {n_tracks} masklets x {n_frames} frames x {CFG['H']}x{CFG['W']} fp32 logits, " \
-               f"stability score, miou_thresh {CFG['miou_thresh']} (one video per GPU per step)"
+    workload = f"config2: grid-prompt track dedup + label metrics, {n_tracks} masklets x {n_frames} frames x {CFG['H']}x{CFG['W']} fp32 logits, " \
+               f"stability score, miou_thresh {CFG['miou_thresh']}, {CFG['n_gt']} GT masklets (one video per GPU per step)"
 
     if args.impl == "reference":
         if rank != 0:
             return
-        torch.set_num_threads(max(1, os.cpu_count() or 1))
-        value, full, sample = cpu_arm(n_tracks, n_frames, max(1, args.steps), max(0, args.warmup))
-        cores = torch.get_num_threads()
-        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": full * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "note": "oracle port of the reference's CPU path (the reference is Python; /root/reference does "
-                           "not exist on the GPU box), torch-CPU ops with all host threads; one rank regardless of --gpus"},
-                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(reference_line(args, n_tracks, n_frames, workload)))
         return
 
     import torch.distributed as dist
@@ -379,7 +508,7 @@ def main():
     # its cpu_baseline leg must see the whole host)
     cpus = sharding.bind_to_gpu_cpus(local_rank) if (world > 1 and not os.environ.get("SOLA_BENCH_NO_AFFINITY")) else []
 
-    w = Workload(device, seed=1234 + 2 + 1000 * rank, n_tracks=n_tracks, n_frames=n_frames, n_streams=args.streams, fused=not args.no_fuse, st_native=args.st_native, tail_priority=args.tail_priority)
+    w = Workload(device, seed=1234 + 2 + 1000 * rank, n_tracks=n_tracks, n_frames=n_frames, fused=not args.no_fuse, st_native=args.st_native)
     w.make_jobs()
     torch.cuda.synchronize()
 
@@ -405,7 +534,6 @@ def main():
     t_wall1 = time.perf_counter()
     torch.cuda.nvtx.range_pop()
     time.sleep(0.12)                         # let the last in-flight sample arrive
-    clk.stop()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = S.launch_count() - launches0
     k1_ms = float(np.mean([a.elapsed_time(b) for a, b in w.k1_events]))
@@ -416,8 +544,9 @@ def main():
     max_ms = float(t.item())
     units = world * n_tracks * n_frames * args.steps
     value = units / (max_ms * 1e-3)
+    clocks = clk.summary(t_wall0, t_wall1)
 
-    # ---- e2e: logits + prompt masks start in pinned host memory; H2D in the timed region; results read back -------
+    # ---- e2e: logits + prompt masks + GT masks start in pinned host memory; H2D in the timed region; results read back -------
     e2e = None
     if not args.no_e2e:
         try:
@@ -436,19 +565,25 @@ def main():
                 h.copy_(w.logits[s:s + chunk])
                 host_chunks.append(h)
             host_prompts = torch.from_numpy(w.prompt_masks_host).pin_memory()
+            host_gt = w.gt_masks.cpu().pin_memory()
             dev_logits = torch.empty_like(w.logits)
             copy_stream = torch.cuda.Stream(device=device)
+            h2d_ms = []
 
             def e2e_step():
                 # chunked H2D on a copy stream; K1 of chunk c runs while chunk c+1 is still crossing PCIe
                 evs = []
                 with torch.cuda.stream(copy_stream):
+                    c0 = torch.cuda.Event(enable_timing=True)
+                    c0.record(copy_stream)
                     for c, h in enumerate(host_chunks):
                         dev_logits[c * chunk: c * chunk + h.shape[0]].copy_(h, non_blocking=True)
-                        e = torch.cuda.Event()
+                        e = torch.cuda.Event(enable_timing=(c == len(host_chunks) - 1))
                         e.record(copy_stream)
                         evs.append(e)
+                    h2d_ms.append((c0, evs[-1]))
                     pm = host_prompts.to(device, non_blocking=True)
+                    gt = host_gt.to(device, non_blocking=True)
                     e = torch.cuda.Event()
                     e.record(copy_stream)
                     evs.append(e)
@@ -459,12 +594,14 @@ def main():
                     _, cc = S.binarize_pack_stability(dev_logits[sl], 0.0, 1.0, out=w.packed[sl])       # K1 on the chunk that just landed
                     cview[:, sl] = cc
                 torch.cuda.current_stream().wait_event(evs[-1])
-                w.jobs[0].enqueue_after_k1(w.packed, w.counts.view(3, n_tracks, n_frames), pm)          # R1, R2, K2-gather, K2, read-backs
+                w.jobs[0].set_gt_masklets(S.pack_masks(gt))                                              # GT masks packed on the device
+                w.jobs[0].enqueue_after_k1(w.packed, w.counts.view(3, n_tracks, n_frames), pm)          # R1, R2, K2-gather, K2, labels, read-backs
                 return w.finish(0)
 
             e2e_step()
             barrier()
             n_e2e = max(1, min(args.e2e_steps, args.steps))
+            h2d_ms.clear()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             for _ in range(n_e2e):
@@ -472,24 +609,49 @@ def main():
             b.record()
             barrier()
             te = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=device)
+            # per-rank H2D bandwidth of the logits (explains the N > 1 e2e numbers: all ranks stream from one host's memory)
+            bw = torch.tensor([w.logits.numel() * 4 / (np.mean([x.elapsed_time(y) for x, y in h2d_ms]) * 1e-3) / 1e9], dtype=torch.float64, device=device)
+            bw_all = [torch.zeros_like(bw) for _ in range(world)] if world > 1 else [bw]
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            h2d = w.logits.numel() * 4 + host_prompts.numel()
-            d2h = int(3 * n_tracks * n_frames * 4 + n_tracks * n_tracks * 8 + 3 * n_tracks * n_tracks * 4)
+                dist.all_gather(bw_all, bw)
+            h2d = w.logits.numel() * 4 + host_prompts.numel() + host_gt.numel()
+            G = CFG["n_gt"]
+            d2h = int(3 * n_tracks * n_frames * 4 + n_tracks * n_tracks * 8 + 3 * n_tracks * n_tracks * 4
+                      + (n_tracks * G * n_frames + n_tracks * n_frames + G * n_frames) * 4)
             e2e = {"value": world * n_tracks * n_frames * n_e2e / (float(te.item()) * 1e-3), "unit": UNIT,
                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h, "steps": n_e2e, "host_cpus_bound": len(cpus),
-                   "note": "pinned host fp32 logits + uint8 prompt masks copied H2D every step (chunked, overlapped with K1); "
-                           "stability counts, IoU count matrices and the N x N intersection matrix read back"}
+                   "h2d_GBps_per_rank": [round(float(x), 1) for x in bw_all],
+                   "note": "pinned host fp32 logits + uint8 prompt masks + uint8 GT masks copied H2D every step (chunked, overlapped with K1); "
+                           "stability counts, IoU count matrices, the N x N intersection matrix and the label count tables read back"}
+            for j in w.jobs:
+                j.set_gt_masklets(w.gt_planes)
             del host_chunks, dev_logits
         except Exception as ex:  # e.g. pinned allocation refused on a small host
             e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(ex)[:200]}
+
+    peak, peak_src = peaks()
+    jf_stage = roofline_jf = cfg5 = None
+    launches_jf = 0
+    if not args.no_jf:
+        try:
+            l0 = S.launch_count()
+            jf_stage, roofline_jf = jf_region(device, rank, world, args.jf_reps, peak)
+            launches_jf = S.launch_count() - l0
+        except Exception as ex:
+            jf_stage = {"error": repr(ex)[:300]}
+    if world > 1 and not args.no_cfg5:
+        try:
+            cfg5 = cfg5_region(device, rank, world)
+        except Exception as ex:
+            cfg5 = {"error": repr(ex)[:300]}
+    clk.stop()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = peaks()
     fused_flag = w.fused
     achieved = w.k1_bytes / (k1_ms * 1e-3) / 1e9
     line = {
@@ -499,10 +661,11 @@ def main():
         "config": {"workload": workload, "l2_policy": "inputs larger than L2 (18.9 GB fp32 logits per step vs 126 MB L2)",
                    "kept_sets": info, "parallelism": f"video-sharded x{world}, no data-path collective",
                    "n_x_n_planes": "native 720x1280" if args.st_native else "540x960 resized masklets (what the reference filter compares)"},
-        "clocks": clk.summary(t_wall0, t_wall1),
+        "clocks": clocks,
         "stage_ms": {"dominant (K1+R1 fused)" if w.fused else "dominant (K1)": k1_ms, "K2 N x N (int pipe, carry-save, TMA-staged)": k2_ms,
-                     "everything else incl. gaps": max_ms / args.steps - k1_ms - k2_ms},
+                     "everything else incl. label counts and gaps": max_ms / args.steps - k1_ms - k2_ms},
         "gpu_launches": int(launches),
+        "gpu_launches_jf_region": int(launches_jf),
         "e2e": e2e,
         "roofline": {"bound": "hbm", "kernel": ("fused_pack_resize_kernel<float> (K1+R1: binarise+pack+stability+resize)" if w.fused
                                                 else "pack_flat_kernel<float, THRESH3> (K1 binarise+pack+stability)"),
@@ -510,12 +673,19 @@ def main():
                      "bytes_per_launch": w.k1_bytes, "ms_per_launch": k1_ms, "share_of_step": k1_ms / (max_ms / args.steps),
                      "traffic": None},
     }
+    if jf_stage is not None:
+        line["jf_stage"] = jf_stage
+    if roofline_jf is not None:
+        roofline_jf["peak_source"] = peak_src
+        line["roofline_jf"] = roofline_jf
+    if cfg5 is not None:
+        line["cfg5"] = cfg5
     try:
         # secondary roofline: K2 is integer-pipe work.  Denominator = alu pipe at 64 lanes/clk/SM (B300_MICROARCH.md; LOP3 measured 64-84
         # by tools/microbench_int.cu) x 148 SMs x the SM clock sampled during the timed region / 2.5 LOP3 per pair-word (4 AND + 6
-        # compressor LOP3 per 4 words).  Pair-words are counted densely; the kernel skips all-zero operand quads, which is why this
-        # fraction on the object-like bench masklets (~0.8) is above the dense-data one (~0.6, profiles/r1_k2_variants.jsonl).
-        oh_, ow_ = (CFG["H"], CFG["W"]) if args.st_native else S.packed.default_target_shape(CFG["H"], CFG["W"])
+        # compressor LOP3 per 4 words).  `frac` counts pair-words DENSELY; the kernel skips all-zero operand quads, so on the object-like
+        # bench masklets it is an upper bound on pipe utilisation — `executed_frac_of_dense` says how much of the dense work was run.
+        oh_, ow_ = (CFG["H"], CFG["W"]) if args.st_native else (w.oh, w.ow)
         words_ = n_frames * oh_ * ((ow_ + 31) // 32)
         pair_words = (n_tracks * (n_tracks + 1) // 2) * words_
         sm_mhz = (line["clocks"] or {}).get("sm_mhz") or 1965.0
@@ -523,34 +693,29 @@ def main():
             raise ValueError("no K2 timing events")
         peak_k2 = 148 * 64 * sm_mhz * 1e6 / 2.5
         ach_k2 = pair_words / (k2_ms * 1e-3)
+        planes_ = (w.packed if args.st_native else S.resize_bilinear_bin(w.packed)).words.view(n_tracks, -1, 4)
+        nz_quads = (planes_ != 0).any(dim=-1).float().mean().item()            # share of (row, k-quad) operands that are not skipped
         line["roofline_k2"] = {"bound": "int-alu", "kernel": "pair_iou_st_ring_kernel (K2 N x N AND-popcount, carry-save)",
                                "achieved": ach_k2 / 1e12, "peak": peak_k2 / 1e12, "unit": "T pair-words/s", "frac": ach_k2 / peak_k2,
+                               "executed_frac_of_dense": nz_quads, "frac_on_executed_pair_words": ach_k2 * nz_quads / peak_k2,
                                "peak_source": "148 SMs x 64 alu lanes/clk x sampled SM clock / 2.5 LOP3 per pair-word",
                                "pair_words_per_launch": int(pair_words), "ms_per_launch": k2_ms}
     except Exception as ex:
         line["roofline_k2"] = {"error": repr(ex)[:200]}
-    if world == 1:
-        try:
-            line["jf_stage"] = jf_stage(device)
-        except Exception as ex:
-            line["jf_stage"] = {"error": repr(ex)[:200]}
     if not args.no_cpu_baseline and world == 1:
-        v, full, sample = cpu_arm(n_tracks, n_frames, 1, 1)
+        del w
+        torch.cuda.empty_cache()
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        v, sample = cpu_baseline_sample(min(16, n_tracks), n_frames)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
-        # second, informative baseline: the same reference operations on CUDA tensors — generic ATen kernels plus
-        # one .item() sync per scalar, which is how the reference actually runs this path on a GPU
-        try:
-            del w                                   # release the bench buffers so ATen's temporaries do not fight the allocator
-            torch.cuda.empty_cache()
-            v2, full2, sample2 = cpu_arm(n_tracks, n_frames, 2, 2, device=device)
-            line["gpu_aten_baseline"] = {"value": v2, "unit": UNIT, "kind": "port on CUDA tensors (ATen)", "sample": sample2}
-        except Exception as ex:
-            line["gpu_aten_baseline"] = {"value": None, "error": repr(ex)[:200]}
     traffic_path = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")       # from the committed `ncu --set full` capture
     if os.path.isfile(traffic_path) and (n_tracks, n_frames) == (CFG["n_tracks"], CFG["n_frames"]):
         with open(traffic_path) as f:
+            tj = json.load(f)
             key = "fused_pack_resize_kernel<float>" if fused_flag else "pack_flat_kernel<float, THRESH3>"
-            line["roofline"]["traffic"] = json.load(f).get(key, {}).get("dram_bytes_per_launch")
+            line["roofline"]["traffic"] = tj.get(key, {}).get("dram_bytes_per_launch")
+            if "roofline_jf" in line:
+                line["roofline_jf"]["traffic"] = tj.get("jf_fused_kernel", {}).get("dram_bytes_per_launch")
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

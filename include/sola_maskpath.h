@@ -183,12 +183,15 @@ typedef struct sola_jf_unit {
   int band_rows, n_bands; /* [filled by sola_jf_sweep_plan] */
   int reserved0, reserved1;
 } sola_jf_unit;           /* 64 bytes */
+typedef struct sola_jf_plan {
+  long long n_items, total_frames;      /* work items (frame x row band) and output columns of the sweep */
+  int raw_cap, bm_cap, mask_steps;      /* shared-memory layout of the launch */
+  int reserved;
+} sola_jf_plan;           /* 32 bytes */
 /* host-only: plans the row-band split of every unit (HOST array, updated in place) and the launch's shared-memory layout */
-int sola_jf_sweep_plan(sola_jf_unit* units_host, int n_units, long long* n_items_out, long long* total_frames_out,
-                       int* raw_cap_out, int* bm_cap_out);
-/* units_dev: the planned table copied to the device; the other scalars are the plan's outputs */
-int sola_jf_sweep(const sola_jf_unit* units_dev, int n_units, long long n_items, long long total_frames, int raw_cap, int bm_cap,
-                  int* counts_out, sola_stream_t stream);
+int sola_jf_sweep_plan(sola_jf_unit* units_host, int n_units, sola_jf_plan* plan_out);
+/* units_dev: the planned table copied to the device; plan: HOST pointer to what sola_jf_sweep_plan returned */
+int sola_jf_sweep(const sola_jf_unit* units_dev, int n_units, const sola_jf_plan* plan, int* counts_out, sola_stream_t stream);
 /* one unit, no table: pred, gt (n_frames, H, Wp) -> counts_out int32 (7, n_frames) */
 int sola_jf_boundary_packed(const uint32_t* pred, const uint32_t* gt, long long n_frames, int H, int W, int radius,
                             int* counts_out, sola_stream_t stream);

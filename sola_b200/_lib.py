@@ -50,8 +50,8 @@ SIGNATURES = {
     "sola_bit_transpose": [_P, _LL, _I, _I, _P, _P],
     "sola_rle_decode_runs": [_P, _P, _P, _LL, _LL, _I, _I, _P, _P, _P],
     "sola_rle_encode_transitions": [_P, _LL, _I, _I, _P, _I, _P, _P, _P],
-    "sola_jf_sweep_plan": [_P, _I, _P, _P, _P, _P],
-    "sola_jf_sweep": [_P, _I, _LL, _LL, _I, _I, _P, _P],
+    "sola_jf_sweep_plan": [_P, _I, _P],
+    "sola_jf_sweep": [_P, _I, _P, _P, _P],
     "sola_jf_boundary_packed": [_P, _P, _LL, _I, _I, _I, _P, _P],
 }
 _RESTYPES = {

@@ -40,6 +40,10 @@ constexpr int JF_MAX_WP = 256;                 // one walker per word column: W 
 constexpr int JF_QUEUE = 96;                   // < 32 left over + at most 64 pushed per scan step
 constexpr int JF_PRE_R = 2;                    // radius of the early-exit pre-test
 
+// row pitch of the boundary maps: the Wp words of a row + one zero word each side, made odd so that vertically adjacent items of
+// phase 2 fall into different banks
+__host__ __device__ constexpr int jf_pitch(int Wp) { return (Wp + 2) | 1; }
+
 struct JfGeo {
   const uint32_t* pred;
   const uint32_t* gt;
@@ -185,11 +189,11 @@ __device__ __forceinline__ uint32_t dilate_word(const uint32_t* __restrict__ src
 // disk, so a pixel it matches IS matched) settles the words whose pixels all have a partner within 2 px — nearly all of them when
 // pred ≈ gt; only the rest go to queue 2 and pay for the full (2r+1)-row dilation, again 32 at a time.
 template <int RAD>
-__device__ __forceinline__ void jf_phase2(const uint32_t* __restrict__ bmF, const uint32_t* __restrict__ bmG, int BP, int Wp, int r, int n_own,
+__device__ __forceinline__ void jf_phase2(const uint32_t* __restrict__ bmF, const uint32_t* __restrict__ bmG, int BP, int r, int n_steps,
+                                          int my_o0 /* this lane's boundary-map offset at step 0 */, const uint2* __restrict__ masks,
                                           const unsigned char* __restrict__ vtab, uint32_t* __restrict__ q1, uint32_t* __restrict__ q2,
-                                          int lane, int warp, int& fm, int& gm) {
+                                          int lane, int& fm, int& gm) {
   constexpr bool PRE = (RAD == 0) || (RAD > JF_PRE_R);        // run-time radii <= 2 take the pre-test too: harmless, it is exact
-  const unsigned magic = (unsigned)((0x100000000ull + (unsigned)Wp - 1) / (unsigned)Wp);   // idx / Wp == umulhi(idx, magic) for idx * Wp < 2^32
   const unsigned lt = (1u << lane) - 1u;
   int n1 = 0, n2 = 0;
   auto full_pass = [&](bool active) {
@@ -225,18 +229,17 @@ __device__ __forceinline__ void jf_phase2(const uint32_t* __restrict__ bmF, cons
     __syncwarp();
     if (n2 >= 32) { n2 -= 32; full_pass(true); }
   };
-  for (int base = warp * 32; base < n_own; base += JF_THREADS) {
-    const int idx = base + lane;
-    const bool valid = idx < n_own;
-    const int row = (int)__umulhi((unsigned)idx, magic), col = idx - row * Wp;
-    const int o = (r + row) * BP + col + 1;
-    const uint32_t bf = valid ? bmF[o] : 0u, bg = valid ? bmG[o] : 0u;
-    const unsigned mF = __ballot_sync(FULL, bf != 0u), mG = __ballot_sync(FULL, bg != 0u);
-    if ((mF | mG) == 0u) continue;
-    if (bf) q1[n1 + __popc(mF & lt)] = (uint32_t)o;
-    n1 += __popc(mF);
-    if (bg) q1[n1 + __popc(mG & lt)] = (uint32_t)o | 0x80000000u;
-    n1 += __popc(mG);
+  // the warp walks the steps of ITS OWN walkers again: masks[k] = which lanes produced a non-zero owned boundary word at step k.
+  // Consecutive steps are consecutive rows of the same columns, so a batch of 32 items is a compact patch of the contour and its
+  // shared loads spread over the banks (the row pitch BP is odd).
+  for (int k = 0; k < n_steps; ++k) {
+    const uint2 m = masks[k];
+    if ((m.x | m.y) == 0u) continue;
+    const uint32_t o = (uint32_t)(my_o0 + k * BP);
+    if ((m.x >> lane) & 1u) q1[n1 + __popc(m.x & lt)] = o;
+    n1 += __popc(m.x);
+    if ((m.y >> lane) & 1u) q1[n1 + __popc(m.y & lt)] = o | 0x80000000u;
+    n1 += __popc(m.y);
     __syncwarp();
     while (n1 >= 32) { n1 -= 32; pre_pass(true); }
   }
@@ -244,43 +247,15 @@ __device__ __forceinline__ void jf_phase2(const uint32_t* __restrict__ bmF, cons
   if (n2 > 0) { const int n = n2; n2 = 0; full_pass(lane < n); }
 }
 
-// ---- phase 1 helpers: one walker step ------------------------------------------------------------------------------------------------
-struct WalkRow { uint32_t s, e; };        // a row's word and its east-shifted copy
-
-template <bool OWNED>
-__device__ __forceinline__ void jf_walk_rows(int n_rows, const uint32_t*& rp, const uint32_t*& rq, uint32_t*& bf, uint32_t*& bg, int Wp, int BP,
-                                             bool east, uint32_t lastbit, WalkRow& p, WalkRow& q, int& n_i, int& n_p, int& n_g, int& n_bf,
-                                             int& n_bg) {
-  // rows that have a row below them: b = (s ^ e) | (s ^ south) | (s ^ south-east); last column: s ^ south only
-#pragma unroll 2
-  for (int k = 0; k < n_rows; ++k) {
-    rp += Wp; rq += Wp;
-    const uint32_t p1 = rp[0], q1 = rq[0];
-    const uint32_t pn = east ? rp[1] : 0u, qn = east ? rq[1] : 0u;
-    const uint32_t pe1 = __funnelshift_r(p1, pn, 1), qe1 = __funnelshift_r(q1, qn, 1);
-    const uint32_t ps = p.s ^ p1, qs = q.s ^ q1;
-    uint32_t bp = (p.s ^ p.e) | ps | (p.s ^ pe1);
-    uint32_t bq = (q.s ^ q.e) | qs | (q.s ^ qe1);
-    bp = (bp & ~lastbit) | (ps & lastbit);
-    bq = (bq & ~lastbit) | (qs & lastbit);
-    if (OWNED) {
-      n_p += __popc(p.s); n_g += __popc(q.s); n_i += __popc(p.s & q.s);
-      n_bf += __popc(bp); n_bg += __popc(bq);
-    }
-    *bf = bp; *bg = bq;
-    bf += BP; bg += BP;
-    p.s = p1; p.e = pe1; q.s = q1; q.e = qe1;
-  }
-}
-
 __global__ void __launch_bounds__(JF_THREADS, 2)
 jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_jf_unit single, long long n_items, int raw_cap,
-                int bm_cap, int* __restrict__ counts, long long total_frames) {
+                int bm_cap, int mask_steps, int* __restrict__ counts, long long total_frames) {
   extern __shared__ __align__(16) uint32_t jf_smem[];
   uint32_t* rawP = jf_smem;
   uint32_t* rawG = rawP + raw_cap;
   uint32_t* bmF = rawG + raw_cap;
   uint32_t* bmG = bmF + bm_cap;
+  uint2* masks = reinterpret_cast<uint2*>(bmG + bm_cap);          // [JF_WARPS][mask_steps]: phase 1's ballots = phase 2's work list
   __shared__ uint64_t bar;
   __shared__ uint32_t queue1[JF_WARPS][JF_QUEUE], queue2[JF_WARPS][64];
   __shared__ int red[7][JF_WARPS];
@@ -304,7 +279,7 @@ jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_
     const long long next = item + gridDim.x;
     const bool has_next = next < n_items;
     if (has_next) jf_decode(units, n_units, single, next, gn);
-    const int Wp = g.Wp, BP = Wp + 2, r = g.r < 0 ? 0 : g.r;
+    const int Wp = g.Wp, BP = jf_pitch(Wp), r = g.r < 0 ? 0 : g.r;
     const int off = (int)(g.g0 & 3ll);
     if (g.r >= 0) {
       if (r != r_cached && tid <= r) vtab[tid] = (unsigned char)jf_isqrt(r * r - tid * tid);     // disk table for run-time radii
@@ -319,6 +294,7 @@ jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_
     parity ^= 1u;
 
     int n_i = 0, n_p = 0, n_g = 0, n_bf = 0, n_bg = 0, fm = 0, gm = 0;
+    int n_steps = 0, my_o0 = 0;
     if (g.r < 0) {
       // region counts only: flat pass over the owned words
       const int n_words = (g.y1 - g.y0) * Wp;
@@ -328,58 +304,73 @@ jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_
       }
     } else {
       // ---- phase 1: column walkers build both boundary maps ------------------------------------------------------------------
+      // Warp-uniform loop over the walker steps, per-lane predicates instead of per-lane trip counts: every step ends in two ballots
+      // ("which lanes produced a non-zero boundary word in a row the band owns"), the work list of phase 2.
       const int c = tid % Wp, s = tid / Wp;
       const int n_sub = min(JF_THREADS / Wp, g.NB);
-      if (s < n_sub) {
-        const int j0 = (int)((long long)s * g.NB / n_sub), j1 = (int)((long long)(s + 1) * g.NB / n_sub);
-        const int ya = g.y0 - r + j0, yb = g.y0 - r + j1;            // this walker's frame rows [ya, yb)
-        const uint32_t lastbit = (c == Wp - 1) ? (1u << ((g.W - 1) & 31)) : 0u;
-        const bool east = c + 1 < Wp;
-        uint32_t* bf = bmF + j0 * BP + c + 1;
-        uint32_t* bg = bmG + j0 * BP + c + 1;
-        int y = ya;
-        for (; y < min(yb, 0); ++y) { *bf = 0u; *bg = 0u; bf += BP; bg += BP; }           // rows above the frame
-        if (y < yb && y < g.H) {
-          const uint32_t* rp = rawP + off + (y - g.ra) * Wp + c;
-          const uint32_t* rq = rawG + off + (y - g.ra) * Wp + c;
-          WalkRow p, q;
-          p.s = rp[0]; q.s = rq[0];
-          p.e = __funnelshift_r(p.s, east ? rp[1] : 0u, 1);
-          q.e = __funnelshift_r(q.s, east ? rq[1] : 0u, 1);
-          const int y_south = min(yb, g.H - 1);                      // rows [y, y_south) have a row below them
-          // halo rows before the owned range, the owned rows, halo rows after: the popcounts exist only in the middle loop
-          const int a1 = min(max(g.y0, y), y_south), a2 = min(max(g.y1, y), y_south);
-          jf_walk_rows<false>(a1 - y, rp, rq, bf, bg, Wp, BP, east, lastbit, p, q, n_i, n_p, n_g, n_bf, n_bg);
-          jf_walk_rows<true>(a2 - a1, rp, rq, bf, bg, Wp, BP, east, lastbit, p, q, n_i, n_p, n_g, n_bf, n_bg);
-          jf_walk_rows<false>(y_south - a2, rp, rq, bf, bg, Wp, BP, east, lastbit, p, q, n_i, n_p, n_g, n_bf, n_bg);
-          y = max(y, y_south);
-          if (y < yb && y == g.H - 1) {                              // last row of the frame: seg ^ east, corner forced to 0
-            const uint32_t bp = (p.s ^ p.e) & ~lastbit, bq = (q.s ^ q.e) & ~lastbit;
-            if (y >= g.y0 && y < g.y1) {
-              n_p += __popc(p.s); n_g += __popc(q.s); n_i += __popc(p.s & q.s);
-              n_bf += __popc(bp); n_bg += __popc(bq);
-            }
-            *bf = bp; *bg = bq; bf += BP; bg += BP;
-            ++y;
-          }
+      n_steps = (g.NB + n_sub - 1) / n_sub;
+      const bool walker = s < n_sub;
+      const int j0 = walker ? (int)((long long)s * g.NB / n_sub) : 0, j1 = walker ? (int)((long long)(s + 1) * g.NB / n_sub) : 0;
+      const int ya = g.y0 - r + j0;                                  // frame row of this walker's step 0
+      const uint32_t lastbit = (c == Wp - 1) ? (1u << ((g.W - 1) & 31)) : 0u;
+      const bool east = c + 1 < Wp;
+      my_o0 = j0 * BP + c + 1;
+      const uint32_t* rp = rawP + off + (ya - g.ra) * Wp + c;        // row y of the raw tile = rp[(y - ya) * Wp]; dereferenced in-frame only
+      const uint32_t* rq = rawG + off + (ya - g.ra) * Wp + c;
+      uint32_t p0 = 0u, pe0 = 0u, q0 = 0u, qe0 = 0u;
+      {
+        const int y = max(ya, 0);                                    // first in-frame row of the walk (if any): prime the registers
+        if (walker && y < g.H && y < ya + (j1 - j0)) {
+          const int d = (y - ya) * Wp;
+          p0 = rp[d]; q0 = rq[d];
+          pe0 = __funnelshift_r(p0, east ? rp[d + 1] : 0u, 1);
+          qe0 = __funnelshift_r(q0, east ? rq[d + 1] : 0u, 1);
         }
-        for (; y < yb; ++y) { *bf = 0u; *bg = 0u; bf += BP; bg += BP; }                  // rows below the frame
+      }
+      uint2* mk = masks + warp * mask_steps;
+#pragma unroll 2
+      for (int k = 0; k < n_steps; ++k) {
+        const int y = ya + k;
+        const bool active = walker && k < j1 - j0;
+        const bool in_frame = active && y >= 0 && y < g.H;
+        const bool south = in_frame && y + 1 < g.H;
+        const bool owned = in_frame && y >= g.y0 && y < g.y1;
+        uint32_t p1 = 0u, q1w = 0u, pe1 = 0u, qe1 = 0u;
+        if (south) {
+          const int d = (k + 1) * Wp;
+          p1 = rp[d]; q1w = rq[d];
+          pe1 = __funnelshift_r(p1, east ? rp[d + 1] : 0u, 1);
+          qe1 = __funnelshift_r(q1w, east ? rq[d + 1] : 0u, 1);
+        }
+        const uint32_t ps = p0 ^ p1, qs = q0 ^ q1w;
+        // rows with a row below: (s ^ e) | (s ^ south) | (s ^ south-east), last column: s ^ south only; last row: s ^ e, corner 0
+        uint32_t bp = south ? ((((p0 ^ pe0) | ps | (p0 ^ pe1)) & ~lastbit) | (ps & lastbit)) : ((p0 ^ pe0) & ~lastbit);
+        uint32_t bq = south ? ((((q0 ^ qe0) | qs | (q0 ^ qe1)) & ~lastbit) | (qs & lastbit)) : ((q0 ^ qe0) & ~lastbit);
+        if (!in_frame) { bp = 0u; bq = 0u; }
+        if (owned) {
+          n_p += __popc(p0); n_g += __popc(q0); n_i += __popc(p0 & q0);
+          n_bf += __popc(bp); n_bg += __popc(bq);
+        }
+        if (active) { bmF[my_o0 + k * BP] = bp; bmG[my_o0 + k * BP] = bq; }
+        const unsigned mF = __ballot_sync(FULL, owned && bp != 0u), mG = __ballot_sync(FULL, owned && bq != 0u);
+        if (lane == 0) mk[k] = make_uint2(mF, mG);
+        if (south) { p0 = p1; pe0 = pe1; q0 = q1w; qe0 = qe1; }
       }
     }
     __syncthreads();                                        // boundary maps complete; the raw tile is dead
     if (has_next) jf_issue_load(gn, rawP, rawG, &bar, tid);  // next tile streams in while this one is matched
 
     if (g.r >= 0) {
-      const int n_own = (g.y1 - g.y0) * Wp;
       uint32_t* q1 = queue1[warp];
       uint32_t* q2 = queue2[warp];
+      const uint2* mk = masks + warp * mask_steps;
       switch (r) {
-        case 6: jf_phase2<6>(bmF, bmG, BP, Wp, r, n_own, vtab, q1, q2, lane, warp, fm, gm); break;       // 360 x 640
-        case 8: jf_phase2<8>(bmF, bmG, BP, Wp, r, n_own, vtab, q1, q2, lane, warp, fm, gm); break;       // 480 x 854
-        case 9: jf_phase2<9>(bmF, bmG, BP, Wp, r, n_own, vtab, q1, q2, lane, warp, fm, gm); break;       // 540 x 960
-        case 12: jf_phase2<12>(bmF, bmG, BP, Wp, r, n_own, vtab, q1, q2, lane, warp, fm, gm); break;     // 720 x 1280
-        case 18: jf_phase2<18>(bmF, bmG, BP, Wp, r, n_own, vtab, q1, q2, lane, warp, fm, gm); break;     // 1080 x 1920
-        default: jf_phase2<0>(bmF, bmG, BP, Wp, r, n_own, vtab, q1, q2, lane, warp, fm, gm); break;
+        case 6: jf_phase2<6>(bmF, bmG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;       // 360 x 640
+        case 8: jf_phase2<8>(bmF, bmG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;       // 480 x 854
+        case 9: jf_phase2<9>(bmF, bmG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;       // 540 x 960
+        case 12: jf_phase2<12>(bmF, bmG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;     // 720 x 1280
+        case 18: jf_phase2<18>(bmF, bmG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;     // 1080 x 1920
+        default: jf_phase2<0>(bmF, bmG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;
       }
     }
 
@@ -400,15 +391,18 @@ jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_
 }
 
 // ---- host side: row-band plan ------------------------------------------------------------------------------------------------
-struct JfPlan { long long n_items, total_frames; int raw_cap, bm_cap; size_t smem; };
-
-static size_t jf_unit_smem(int Wp, int r, int rows, bool boundary, int* raw_cap, int* bm_cap) {
+static size_t jf_unit_smem(int Wp, int r, int rows, bool boundary, int* raw_cap, int* bm_cap, int* steps) {
   const int rr = boundary ? r : 0;
   const int rc = (((rows + (boundary ? 2 * rr + 1 : 0)) * Wp + 8) + 3) & ~3;
-  const int bc = boundary ? (rows + 2 * rr) * (Wp + 2) : 0;
+  const int NB = rows + 2 * rr;
+  const int bc = boundary ? ((NB * jf_pitch(Wp) + 1) & ~1) : 0;             // even: the uint2 mask table behind it stays 8-byte aligned
+  int n_sub = JF_THREADS / Wp;
+  if (n_sub > NB) n_sub = NB;
+  const int st = boundary ? (NB + n_sub - 1) / n_sub : 0;
   if (raw_cap) *raw_cap = rc;
   if (bm_cap) *bm_cap = bc;
-  return (size_t)(2 * rc + 2 * bc) * sizeof(uint32_t);
+  if (steps) *steps = st;
+  return (size_t)(2 * rc + 2 * bc + 2 * JF_WARPS * st) * sizeof(uint32_t);
 }
 
 // Largest band height whose tile fits `budget` bytes; 0 if not even one row fits.
@@ -416,7 +410,7 @@ static int jf_max_band_rows(int H, int Wp, int r, bool boundary, size_t budget) 
   int lo = 0, hi = H;
   while (lo < hi) {
     const int mid = (lo + hi + 1) / 2;
-    if (jf_unit_smem(Wp, r, mid, boundary, nullptr, nullptr) <= budget) lo = mid; else hi = mid - 1;
+    if (jf_unit_smem(Wp, r, mid, boundary, nullptr, nullptr, nullptr) <= budget) lo = mid; else hi = mid - 1;
   }
   return lo;
 }
@@ -424,13 +418,20 @@ static int jf_max_band_rows(int H, int Wp, int r, bool boundary, size_t budget) 
 constexpr size_t JF_BUDGET_2CTA = 100 * 1024;     // two resident CTAs per SM: one loads / walks while the other dilates
 constexpr size_t JF_BUDGET_1CTA = 200 * 1024;     // tall halos (1080p: r = 18): fewer, taller bands beat occupancy
 
-static int jf_plan(sola_jf_unit* units, int n_units, JfPlan* plan) {
+extern "C" {
+typedef struct sola_jf_plan {
+  long long n_items, total_frames;
+  int raw_cap, bm_cap, mask_steps, reserved;
+} sola_jf_plan;
+}
+
+static int jf_plan(sola_jf_unit* units, int n_units, sola_jf_plan* plan) {
   // one budget for the whole launch: the small one unless some unit would then spend > 30 % of its rows on halo
   size_t budget = JF_BUDGET_2CTA;
   for (int pass = 0; pass < 2; ++pass) {
     bool retry = false;
     long long items = 0, frames = 0;
-    int raw_cap = 4, bm_cap = 0;
+    int raw_cap = 4, bm_cap = 0, steps = 0;
     for (int i = 0; i < n_units; ++i) {
       sola_jf_unit& u = units[i];
       SOLA_REQUIRE(u.T >= 0 && u.H > 0 && u.W > 0, "jf_sweep: unit %d has a bad shape T=%d H=%d W=%d", i, u.T, u.H, u.W);
@@ -455,34 +456,37 @@ static int jf_plan(sola_jf_unit* units, int n_units, JfPlan* plan) {
       u.out_off = frames;
       items += (long long)u.T * u.n_bands;
       frames += u.T;
-      int rc, bc;
-      jf_unit_smem(Wp, u.radius, u.band_rows, boundary, &rc, &bc);
+      int rc, bc, st;
+      jf_unit_smem(Wp, u.radius, u.band_rows, boundary, &rc, &bc, &st);
       if (rc > raw_cap) raw_cap = rc;
       if (bc > bm_cap) bm_cap = bc;
+      if (st > steps) steps = st;
     }
     if (retry) { budget = JF_BUDGET_1CTA; continue; }
-    plan->n_items = items; plan->total_frames = frames; plan->raw_cap = raw_cap; plan->bm_cap = bm_cap;
-    plan->smem = (size_t)(2 * raw_cap + 2 * bm_cap) * sizeof(uint32_t);
+    plan->n_items = items; plan->total_frames = frames; plan->raw_cap = raw_cap; plan->bm_cap = bm_cap; plan->mask_steps = steps;
+    plan->reserved = 0;
     return SOLA_OK;
   }
   return SOLA_ERR_UNSUPPORTED;
 }
 
-static int jf_launch(const sola_jf_unit* units_dev, int n_units, const sola_jf_unit& single, long long n_items, long long total_frames,
-                     int raw_cap, int bm_cap, int* counts_out, cudaStream_t stream) {
-  if (total_frames <= 0) return SOLA_OK;
+static int jf_launch(const sola_jf_unit* units_dev, int n_units, const sola_jf_unit& single, const sola_jf_plan& p, int* counts_out,
+                     cudaStream_t stream) {
+  if (p.total_frames <= 0) return SOLA_OK;
   SOLA_REQUIRE(counts_out, "jf_sweep: null output");
-  SOLA_CUDA(cudaMemsetAsync(counts_out, 0, sizeof(int) * 7 * (size_t)total_frames, stream));
-  if (n_items <= 0) return SOLA_OK;
-  const size_t smem = (size_t)(2 * raw_cap + 2 * bm_cap) * sizeof(uint32_t);
-  SOLA_REQUIRE(raw_cap % 4 == 0 && smem <= 220 * 1024, "jf_sweep: bad shared-memory plan (raw_cap %d, bm_cap %d)", raw_cap, bm_cap);
+  SOLA_CUDA(cudaMemsetAsync(counts_out, 0, sizeof(int) * 7 * (size_t)p.total_frames, stream));
+  if (p.n_items <= 0) return SOLA_OK;
+  const size_t smem = (size_t)(2 * p.raw_cap + 2 * p.bm_cap + 2 * JF_WARPS * p.mask_steps) * sizeof(uint32_t);
+  SOLA_REQUIRE(p.raw_cap > 0 && p.raw_cap % 4 == 0 && p.bm_cap >= 0 && p.bm_cap % 2 == 0 && p.mask_steps >= 0 && smem <= 220 * 1024,
+               "jf_sweep: bad shared-memory plan (raw_cap %d, bm_cap %d, mask_steps %d)", p.raw_cap, p.bm_cap, p.mask_steps);
   SOLA_CUDA(cudaFuncSetAttribute(jf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jf_fused_kernel, JF_THREADS, smem);
   if (occ < 1) occ = 1;
   long long grid = (long long)num_sms() * occ;
-  if (grid > n_items) grid = n_items;
-  jf_fused_kernel<<<(unsigned)grid, JF_THREADS, smem, stream>>>(units_dev, n_units, single, n_items, raw_cap, bm_cap, counts_out, total_frames);
+  if (grid > p.n_items) grid = p.n_items;
+  jf_fused_kernel<<<(unsigned)grid, JF_THREADS, smem, stream>>>(units_dev, n_units, single, p.n_items, p.raw_cap, p.bm_cap, p.mask_steps,
+                                                                counts_out, p.total_frames);
   return check_launch("jf_fused kernel");
 }
 
@@ -493,29 +497,27 @@ using namespace sola;
 extern "C" {
 
 // Host-only: fills band_rows / n_bands / item0 / out_off of every unit (frames are numbered in unit order) and reports the launch plan.
-int sola_jf_sweep_plan(sola_jf_unit* units_host, int n_units, long long* n_items_out, long long* total_frames_out, int* raw_cap_out,
-                       int* bm_cap_out) {
+int sola_jf_sweep_plan(sola_jf_unit* units_host, int n_units, sola_jf_plan* plan_out) {
   SOLA_REQUIRE(n_units >= 0 && (n_units == 0 || units_host), "jf_sweep_plan: bad arguments");
-  SOLA_REQUIRE(n_items_out && total_frames_out && raw_cap_out && bm_cap_out, "jf_sweep_plan: null output");
-  JfPlan p{0, 0, 4, 0, 0};
+  SOLA_REQUIRE(plan_out, "jf_sweep_plan: null output");
+  sola_jf_plan p{0, 0, 4, 0, 0, 0};
   if (n_units > 0) {
     const int rc = jf_plan(units_host, n_units, &p);
     if (rc != SOLA_OK) return rc;
   }
-  *n_items_out = p.n_items; *total_frames_out = p.total_frames; *raw_cap_out = p.raw_cap; *bm_cap_out = p.bm_cap;
+  *plan_out = p;
   return SOLA_OK;
 }
 
 // counts_out int32 (7, total_frames): rows = inter, |pred|, |gt|, |b(pred)|, |b(gt)|, fg_match, gt_match (rows 3..6 stay 0 for units
-// planned with radius < 0).  units_dev = the planned table copied to the device.
-int sola_jf_sweep(const sola_jf_unit* units_dev, int n_units, long long n_items, long long total_frames, int raw_cap, int bm_cap,
-                  int* counts_out, cudaStream_t stream) {
-  SOLA_REQUIRE(n_units >= 0 && n_items >= 0 && total_frames >= 0, "jf_sweep: bad arguments");
-  if (n_units == 0 || total_frames == 0) return SOLA_OK;
+// planned with radius < 0).  units_dev = the planned table copied to the device; plan = what sola_jf_sweep_plan returned (HOST pointer).
+int sola_jf_sweep(const sola_jf_unit* units_dev, int n_units, const sola_jf_plan* plan, int* counts_out, cudaStream_t stream) {
+  SOLA_REQUIRE(n_units >= 0 && plan && plan->n_items >= 0 && plan->total_frames >= 0, "jf_sweep: bad arguments");
+  if (n_units == 0 || plan->total_frames == 0) return SOLA_OK;
   SOLA_REQUIRE(units_dev, "jf_sweep: null unit table");
   sola_jf_unit none;
   memset(&none, 0, sizeof(none));
-  return jf_launch(units_dev, n_units, none, n_items, total_frames, raw_cap, bm_cap, counts_out, stream);
+  return jf_launch(units_dev, n_units, none, *plan, counts_out, stream);
 }
 
 // One unit, no table: pred, gt (n_frames, H, Wp) -> counts_out int32 (7, n_frames).  radius < 0: region counts only.
@@ -527,10 +529,10 @@ int sola_jf_boundary_packed(const uint32_t* pred, const uint32_t* gt, long long 
   sola_jf_unit u;
   memset(&u, 0, sizeof(u));
   u.pred = pred; u.gt = gt; u.T = (int)n_frames; u.H = H; u.W = W; u.radius = radius;
-  JfPlan p{0, 0, 4, 0, 0};
+  sola_jf_plan p{0, 0, 4, 0, 0, 0};
   const int rc = jf_plan(&u, 1, &p);
   if (rc != SOLA_OK) return rc;
-  return jf_launch(nullptr, 1, u, p.n_items, p.total_frames, p.raw_cap, p.bm_cap, counts_out, stream);
+  return jf_launch(nullptr, 1, u, p, counts_out, stream);
 }
 
 }  // extern "C"

@@ -272,7 +272,9 @@ class VideoDedupJob:
         self.frame_idx_dev = P.to_device(self.frame_idx, device=self.device)
         self.event = torch.cuda.Event()
         self._host = None
+        self._host_labels = None
         self.packed = self.counts = self.resized = None
+        self.gt_planes: Optional[P.PackedMasks] = None      # (G, T, h, wp) GT masklets at the resized shape -> label metrics in the step
 
     def _pinned(self, n_tracks: int, n_prompts: int, T: int):
         shapes = ((3, n_tracks, n_prompts), (n_tracks, n_tracks), (3, n_tracks, T))
@@ -281,6 +283,12 @@ class VideoDedupJob:
                           torch.empty((n_tracks, n_tracks), dtype=torch.int64).pin_memory(),
                           torch.empty((3, n_tracks, T), dtype=torch.int32).pin_memory())
         return self._host
+
+    def set_gt_masklets(self, gt_planes: Optional[P.PackedMasks]) -> None:
+        """GT masklets of the video, (G, T, h, wp) packed at the resized shape (what `gt_masklets` holds at generate_tokens_grid.py:112).
+        When set, every step also produces the training labels of generate_tokens_grid.py:253-264: frame-mean precision / recall / IoU of
+        every track against every GT object (utils.compute_mask_metrics), from ONE batched count launch on the resized planes."""
+        self.gt_planes = gt_planes
 
     def enqueue(self, logits: torch.Tensor, prompt_masks: torch.Tensor, *, mask_threshold: float = 0.0, threshold_offset: float = 1.0,
                 packed_out: Optional[P.PackedMasks] = None, counts_out: Optional[torch.Tensor] = None, target_shape=None):
@@ -316,6 +324,15 @@ class VideoDedupJob:
         hg.copy_(g, non_blocking=True)
         hi.copy_(inter, non_blocking=True)
         hc.copy_(counts.reshape(3, N, T), non_blocking=True)
+        if self.gt_planes is not None:
+            # label metrics (generate_tokens_grid.py:253-264): per-frame |track ∩ gt|, |track|, |gt| for all N x G x T frame pairs
+            G = int(self.gt_planes.words.shape[0])
+            li, la, lb = P.frame_counts_packed(self.resized, self.gt_planes)
+            shapes = ((N, G, T), (N, T), (G, T))
+            if self._host_labels is None or tuple(tuple(t.shape) for t in self._host_labels) != shapes:
+                self._host_labels = tuple(torch.empty(sh, dtype=torch.int32).pin_memory() for sh in shapes)
+            for h, d in zip(self._host_labels, (li, la, lb)):
+                h.copy_(d, non_blocking=True)
         self.event.record(torch.cuda.current_stream(self.device))
         self.counts = counts
 
@@ -343,4 +360,23 @@ class VideoDedupJob:
             stability = hc[0] / hc[2]
         res.update({"kept_spatiotemporal": np.nonzero(alive)[0].tolist(), "suppressed_by_spatiotemporal": by,
                     "inter": hi.copy(), "stability": stability, "iou_gather": M})
+        if self.gt_planes is not None and self._host_labels is not None:
+            res["labels"] = label_metrics_from_counts(*(t.numpy() for t in self._host_labels))
         return res
+
+
+def label_metrics_from_counts(inter: np.ndarray, area_p: np.ndarray, area_g: np.ndarray) -> dict:
+    """inter (N, G, T), area_p (N, T), area_g (G, T) -> {'precision', 'recall', 'iou'}: fp32 (N, G) arrays holding what
+    utils.compute_mask_metrics(...)[k].squeeze().item() returns for every (track, GT object) (utils.py:132-174): per-frame float64
+    ratios with the four empty-case rules, stored as fp32, then an fp32 mean over the T frames."""
+    inter = inter.astype(np.int64)
+    n_p = area_p.astype(np.int64)[:, None, :]
+    n_g = area_g.astype(np.int64)[None, :, :]
+    union = n_p + n_g - inter
+    with np.errstate(divide="ignore", invalid="ignore"):
+        iou = np.where(union == 0, 1.0, inter / union)
+        prec = np.where(n_p == 0, 1.0, np.where(n_g == 0, 0.0, inter / n_p))
+        rec = np.where(n_p == 0, np.where(n_g == 0, 1.0, 0.0), np.where(n_g == 0, 1.0, inter / n_g))
+    # torch's fp32 .mean() over a contiguous (T,) tensor; reproduce it with torch so the rounding is the reference's
+    as_mean = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).float().mean(dim=-1).numpy()
+    return {"precision": as_mean(prec), "recall": as_mean(rec), "iou": as_mean(iou)}

@@ -521,7 +521,13 @@ class JfUnit(_C.Structure):
                 ("band_rows", _C.c_int), ("n_bands", _C.c_int), ("reserved0", _C.c_int), ("reserved1", _C.c_int)]
 
 
-assert _C.sizeof(JfUnit) == 64
+class JfPlan(_C.Structure):
+    """ctypes mirror of `sola_jf_plan`: 32 bytes."""
+    _fields_ = [("n_items", _C.c_longlong), ("total_frames", _C.c_longlong), ("raw_cap", _C.c_int), ("bm_cap", _C.c_int),
+                ("mask_steps", _C.c_int), ("reserved", _C.c_int)]
+
+
+assert _C.sizeof(JfUnit) == 64 and _C.sizeof(JfPlan) == 32
 
 
 class JFSweepPlan:
@@ -551,9 +557,10 @@ class JFSweepPlan:
             u.T, u.H, u.W = p.n_frames, p.H, p.W
             u.radius = bound_pix_for(p.H, p.W, bound_th) if with_boundary else -1
         self.n_units = n
-        n_items, total, raw_cap, bm_cap = _C.c_longlong(0), _C.c_longlong(0), _C.c_int(0), _C.c_int(0)
-        _lib.call("sola_jf_sweep_plan", _C.cast(arr, _C.c_void_p), n, _C.byref(n_items), _C.byref(total), _C.byref(raw_cap), _C.byref(bm_cap))
-        self.n_items, self.total_frames, self.raw_cap, self.bm_cap = n_items.value, total.value, raw_cap.value, bm_cap.value
+        self.plan = JfPlan()
+        _lib.call("sola_jf_sweep_plan", _C.cast(arr, _C.c_void_p), n, _C.byref(self.plan))
+        self.n_items, self.total_frames = self.plan.n_items, self.plan.total_frames
+        self.smem_bytes = (2 * self.plan.raw_cap + 2 * self.plan.bm_cap + 16 * self.plan.mask_steps) * 4
         self.offsets = [arr[k].out_off for k in range(n)]
         self.frames = [arr[k].T for k in range(n)]
         self.bands = [(arr[k].band_rows, arr[k].n_bands) for k in range(n)]
@@ -571,8 +578,8 @@ class JFSweepPlan:
         if self.n_units == 0 or self.total_frames == 0:
             return out
         with torch.cuda.device(dev):
-            _lib.call("sola_jf_sweep", self.units_dev.data_ptr(), self.n_units, self.n_items, self.total_frames, self.raw_cap, self.bm_cap,
-                      out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+            _lib.call("sola_jf_sweep", self.units_dev.data_ptr(), self.n_units, _C.byref(self.plan), out.data_ptr(),
+                      torch.cuda.current_stream(dev).cuda_stream)
         return out
 
 

@@ -85,18 +85,18 @@ int main(void) {
   if (memcmp(h1, h2, (size_t)n * oh * owp * 4) != 0) { printf("fused != K1 then R1\n"); return 1; }
   /* fused J&F sweep through the unit table: the struct layout as a C client sees it; region rows and |b(pred)| vs plain C loops */
   {
-    uint32_t* packed_b; int* jf; sola_jf_unit unit, *unit_dev; long long n_items = 0, total = 0; int raw_cap = 0, bm_cap = 0;
+    uint32_t* packed_b; int* jf; sola_jf_unit unit, *unit_dev; sola_jf_plan plan;
     CK(cudaMalloc((void**)&packed_b, (size_t)n * H * Wp * 4));
     rc = sola_threshold_pack_f32(d, n, H, W, 0.5, packed_b, NULL, 0);
     if (rc) { printf("sola_threshold_pack_f32: %s\n", sola_last_error_string()); return 1; }
     memset(&unit, 0, sizeof(unit));
     unit.pred = packed; unit.gt = packed_b; unit.T = n; unit.H = H; unit.W = W; unit.radius = 2;
     if (sizeof(sola_jf_unit) != 64) { printf("sola_jf_unit is %zu bytes\n", sizeof(sola_jf_unit)); return 1; }
-    rc = sola_jf_sweep_plan(&unit, 1, &n_items, &total, &raw_cap, &bm_cap);
-    if (rc || total != n || n_items < n) { printf("sola_jf_sweep_plan: %s\n", sola_last_error_string()); return 1; }
+    rc = sola_jf_sweep_plan(&unit, 1, &plan);
+    if (rc || plan.total_frames != n || plan.n_items < n) { printf("sola_jf_sweep_plan: %s\n", sola_last_error_string()); return 1; }
     CK(cudaMalloc((void**)&unit_dev, sizeof(unit))); CK(cudaMemcpy(unit_dev, &unit, sizeof(unit), cudaMemcpyHostToDevice));
     CK(cudaMalloc((void**)&jf, 7 * n * sizeof(int)));
-    rc = sola_jf_sweep(unit_dev, 1, n_items, total, raw_cap, bm_cap, jf, 0);
+    rc = sola_jf_sweep(unit_dev, 1, &plan, jf, 0);
     if (rc) { printf("sola_jf_sweep: %s\n", sola_last_error_string()); return 1; }
     int hjf[21];
     CK(cudaMemcpy(hjf, jf, sizeof(hjf), cudaMemcpyDeviceToHost));

@@ -37,7 +37,7 @@ for name, (T, H, W) in {"480x854": (4096, 480, 854), "720x1280": (2560, 720, 128
             buf = torch.empty((7, plan.total_frames), dtype=torch.int32, device="cuda")
             ms = timed(lambda: plan.run(buf), reps=5 if speckle else 20)
             out[f"{name}/{kind}/{'J+F+boundary' if wb else 'J+F'}"] = {"ms": ms, "GBps": nbytes / ms / 1e6, "frames_per_s": T / ms * 1e3,
-                                                                      "bands": plan.bands[0], "smem": (2 * plan.raw_cap + 2 * plan.bm_cap) * 4}
+                                                                      "bands": plan.bands[0], "smem": plan.smem_bytes}
         if kind == "object":
             ms = timed(lambda: S.frame_counts_packed(pp.reshape_lead(1, T), gp.reshape_lead(1, T)), reps=20)
             out[f"{name}/object/old_K3_packed_counts"] = {"ms": ms, "GBps": nbytes / ms / 1e6}
