@@ -102,6 +102,27 @@ def word_slices(words: int, world: int, align: int = 32) -> List[Tuple[int, int]
     return out
 
 
+def _all_to_all(recv: List[torch.Tensor], send: List[torch.Tensor], group=None) -> None:
+    """dist.all_to_all where the backend has it (NCCL); gloo (the CPU tests) has no all-to-all, so there it is point-to-point
+    isend / irecv pairs (slices of different ranks differ in length, which rules out scatter)."""
+    if dist.get_backend(group) != "gloo":
+        dist.all_to_all(recv, send, group=group)
+        return
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    g = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    recv[rank].copy_(send[rank])
+    reqs = []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        if send[peer].numel():
+            reqs.append(dist.isend(send[peer].contiguous(), dst=g(peer), group=group))
+        if recv[peer].numel():
+            reqs.append(dist.irecv(recv[peer], src=g(peer), group=group))
+    for r in reqs:
+        r.wait()
+
+
 def pairwise_inter_matrix_sharded(local_tracks, group=None, split: str = "words") -> torch.Tensor:
     """BASELINE config 5 (one video with more candidate tracks than one GPU should binarise): every rank holds the packed
     planes of ITS tracks (n_local, T, H, Wp) — equal n_local on every rank.  The path has a real exchange step here.
@@ -124,7 +145,7 @@ def pairwise_inter_matrix_sharded(local_tracks, group=None, split: str = "words"
         send = [flat[:, lo:hi].contiguous() for lo, hi in sl]
         mine = sl[rank][1] - sl[rank][0]
         recv = torch.empty((world, n_local, mine), dtype=w.dtype, device=w.device)
-        dist.all_to_all(list(recv.unbind(0)), send, group=group)
+        _all_to_all(list(recv.unbind(0)), send, group=group)
         inter = P.pairwise_inter_matrix_words(recv.view(world * n_local, mine)) if mine > 0 else \
             torch.zeros((world * n_local, world * n_local), dtype=torch.int64, device=w.device)
     else:
