@@ -109,7 +109,7 @@ int sola_pair_iou_st_part(const uint32_t* packed, int N, long long words_per_tra
  * 1/n_parts of its peers' planes; the sum of all parts' outputs is the full matrix. */
 int sola_pair_iou_st_rows(const uint32_t* const* row_ptrs, int N, long long words_per_track, int part, int n_parts, long long* inter_out,
                           sola_stream_t stream);
-/* EXPERIMENTAL (compiled, not yet run on hardware): exchange + K2 in ONE kernel.  bases_host is a HOST array of `world` device
+/* exchange + K2 in ONE kernel (validated on 2 x B200, tests/test_gpu_multirank.py).  bases_host is a HOST array of `world` device
  * pointers, rank r's (n_local, words_per_track) packed planes in peer-mapped memory; the K2 producer lane issues its TMA tile loads
  * against one tensor map per rank, so the rows cross NVLink inside the kernel that reduces them.  part / n_parts partition the
  * word axis as in sola_pair_iou_st_rows.  SOLA_ERR_UNSUPPORTED if gcd(64, n_local) < 8 or world > 8. */
@@ -162,6 +162,11 @@ int sola_binarize_pack_resize_bf16(const void* logits_bf16, long long n_frames, 
 int sola_bit_transpose(const uint32_t* in, long long n_planes, int A, int B, uint32_t* out, sola_stream_t stream);
 int sola_rle_decode_runs(const int* run_plane, const int* run_start, const int* run_end, long long n_runs,
                          long long n_planes, int H, int W, uint32_t* scratch_colmajor, uint32_t* packed_out, sola_stream_t stream);
+/* host-only: the `counts` strings of n_frames RLE frames -> their ones-runs ([start, end) in flat column-major pixel index) in HOST
+ * arrays of capacity cap; plane_ids[f] = output plane of frame f's runs (several tracks may share planes: sola_rle_decode_runs ORs them).
+ * The sequential varint parse of cocoapi's rleFrString, stopped before the H*W-byte fill (dataloader.py:360). */
+int sola_rle_strings_to_runs(const char* const* strings, const long long* lens, const int* plane_ids, long long n_frames, long long n_pixels,
+                             int* run_plane, int* run_start, int* run_end, long long cap, long long* n_runs_out);
 int sola_rle_encode_transitions(const uint32_t* packed, long long n_planes, int H, int W, uint32_t* scratch_colmajor,
                                 int cap, int* out_pos, int* out_n, sola_stream_t stream);
 

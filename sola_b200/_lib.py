@@ -49,6 +49,7 @@ SIGNATURES = {
     "sola_binarize_pack_resize_bf16": [_P, _LL, _I, _I, _I, _I, _D, _D, _P, _P, _P, _P, _P, _P, _P],
     "sola_bit_transpose": [_P, _LL, _I, _I, _P, _P],
     "sola_rle_decode_runs": [_P, _P, _P, _LL, _LL, _I, _I, _P, _P, _P],
+    "sola_rle_strings_to_runs": [_P, _P, _P, _LL, _LL, _P, _P, _P, _LL, _P],
     "sola_rle_encode_transitions": [_P, _LL, _I, _I, _P, _I, _P, _P, _P],
     "sola_jf_sweep_plan": [_P, _I, _P],
     "sola_jf_sweep": [_P, _I, _P, _P, _P],

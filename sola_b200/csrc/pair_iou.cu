@@ -528,7 +528,7 @@ int sola_pair_iou_st_rows(const uint32_t* const* row_ptrs, int N, long long word
   return check_launch("pair_iou_st_rows kernel");
 }
 
-// EXPERIMENTAL (compiled, not yet run on hardware): exchange + K2 in ONE kernel.  bases_host = HOST array of `world` device pointers,
+// Exchange + K2 in ONE kernel (validated on 2 x B200: tests/test_gpu_multirank.py, profiles/r2_cfg5_2gpu_tma.log).  bases_host = HOST array of `world` device pointers,
 // rank r's (n_local, words_per_track) packed planes (peer-mapped symmetric memory); part p of n_parts covers its slice of the word
 // axis as in sola_pair_iou_st_rows.  Returns SOLA_ERR_UNSUPPORTED when the shape cannot be tiled (gcd(64, n_local) < 8, world > 8).
 int sola_pair_iou_st_peer(const uint32_t* const* bases_host, int world, int n_local, long long words_per_track, int part, int n_parts,

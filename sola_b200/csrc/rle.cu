@@ -174,4 +174,51 @@ int sola_rle_encode_transitions(const uint32_t* packed, long long n_planes, int 
   return check_launch("rle_transitions kernel");
 }
 
+
+// Host-only: COCO compressed-RLE strings -> ones-runs.  The reference decodes with pycocotools' C loop (dataloader.py:360,
+// cocoapi maskApi.c rleFrString + rleDecode), which writes H*W bytes per frame; here the same sequential varint parse stops at the
+// run list ([start, end) in flat column-major pixel index), which is what crosses PCIe and what rle_fill_runs_kernel consumes.
+//   strings[f] / lens[f]: the `counts` string of frame f (ASCII, not NUL-terminated); plane_ids[f]: the output plane its runs belong to;
+//   n_pixels = H*W (every frame must cover exactly that many pixels); run_* are HOST arrays of capacity `cap`.
+// Returns SOLA_ERR_INVALID on a malformed string / wrong coverage / overflow of cap (*n_runs_out then holds the runs needed so far).
+int sola_rle_strings_to_runs(const char* const* strings, const long long* lens, const int* plane_ids, long long n_frames, long long n_pixels,
+                             int* run_plane, int* run_start, int* run_end, long long cap, long long* n_runs_out) {
+  SOLA_REQUIRE(n_frames >= 0 && n_pixels >= 0 && n_pixels < (1ll << 31) && cap >= 0 && n_runs_out, "rle_strings_to_runs: bad arguments");
+  SOLA_REQUIRE(n_frames == 0 || (strings && lens && plane_ids), "rle_strings_to_runs: null pointer");
+  long long n = 0;
+  for (long long f = 0; f < n_frames; ++f) {
+    const unsigned char* s = reinterpret_cast<const unsigned char*>(strings[f]);
+    const long long len = lens[f];
+    long long prev1 = 0, prev2 = 0;          // counts[i-1], counts[i-2]
+    long long pos = 0;                       // pixels covered so far
+    long long i = 0, p = 0;
+    while (p < len) {
+      long long x = 0;
+      int k = 0;
+      bool more = true;
+      while (more) {
+        if (p >= len || k > 12) { set_error("rle_strings_to_runs: frame %lld: truncated / oversized varint", f); *n_runs_out = n; return SOLA_ERR_INVALID; }
+        const long long c = (long long)s[p] - 48;
+        x |= (c & 0x1f) << (5 * k);
+        more = (c & 0x20) != 0;
+        ++p; ++k;
+        if (!more && (c & 0x10)) x |= -1ll << (5 * k);
+      }
+      if (i > 2) x += prev2;
+      if (x < 0 || pos + x > n_pixels) { set_error("rle_strings_to_runs: frame %lld: run %lld overruns the frame", f, i); *n_runs_out = n; return SOLA_ERR_INVALID; }
+      if ((i & 1) && x > 0) {                // odd-indexed counts are ones-runs
+        if (n < cap) { run_plane[n] = plane_ids[f]; run_start[n] = (int)pos; run_end[n] = (int)(pos + x); }
+        ++n;
+      }
+      pos += x;
+      prev2 = prev1; prev1 = x;
+      ++i;
+    }
+    if (pos != n_pixels) { set_error("rle_strings_to_runs: frame %lld covers %lld pixels, expected %lld", f, pos, n_pixels); *n_runs_out = n; return SOLA_ERR_INVALID; }
+  }
+  *n_runs_out = n;
+  if (n > cap) { set_error("rle_strings_to_runs: %lld runs, capacity %lld", n, cap); return SOLA_ERR_INVALID; }
+  return SOLA_OK;
+}
+
 }  // extern "C"

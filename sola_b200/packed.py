@@ -375,7 +375,7 @@ def pairwise_inter_matrix_rows(row_ptrs: torch.Tensor, words_per_track: int, par
 
 
 def pairwise_inter_matrix_peer(bases: Sequence[int], n_local: int, words_per_track: int, part: int, n_parts: int, device) -> torch.Tensor:
-    """EXPERIMENTAL (not yet run on hardware): one K2 launch whose TMA producer reads every rank's (n_local, words) planes in place —
+    """One K2 launch whose TMA producer reads every rank's (n_local, words) planes in place over NVLink —
     `bases` are the peer-mapped device addresses of the ranks' buffers.  Returns this part's (N, N) int64 share."""
     import ctypes
     world = len(bases)

@@ -20,7 +20,8 @@ from . import packed as P
 
 # ---- host: varint string <-> counts ----------------------------------------------------------------------------------
 
-def string_to_counts(s) -> np.ndarray:
+def _string_to_counts_scalar(s) -> np.ndarray:
+    """rleFrString, one character at a time (kept as the plain statement of the format; tests cross-check the vectorised parser)."""
     if isinstance(s, str):
         s = s.encode("ascii")
     b = np.frombuffer(s, dtype=np.uint8).astype(np.int64) - 48
@@ -37,6 +38,29 @@ def string_to_counts(s) -> np.ndarray:
             counts.append(x)
             x, k = 0, 0
     return np.asarray(counts, dtype=np.int64)
+
+
+def string_to_counts(s) -> np.ndarray:
+    """rleFrString vectorised over the whole string (numpy): base-32 little-endian varints with a continuation bit (0x20) and sign
+    extension from bit 0x10, then counts[i] += counts[i-2] for i > 2 as two strided running sums.  The reference decodes with
+    pycocotools' C loop (dataloader.py:360); a per-character Python loop here would make the host the bottleneck of the GPU path."""
+    if isinstance(s, str):
+        s = s.encode("ascii")
+    c = np.frombuffer(s, dtype=np.uint8).astype(np.int64) - 48
+    if c.size == 0:
+        return np.zeros(0, dtype=np.int64)
+    last = (c & 0x20) == 0                                   # last character of each varint
+    ends = np.flatnonzero(last)
+    starts = np.concatenate([[0], ends[:-1] + 1])
+    k = np.arange(c.size) - np.repeat(starts, ends - starts + 1)             # position of the character inside its varint
+    x = np.add.reduceat((c & 0x1F) << (5 * k), starts)
+    neg = (c[ends] & 0x10) != 0
+    x = np.where(neg, x - (np.int64(1) << (5 * (ends - starts + 1))), x)      # x |= -1 << (5 * n_chars)
+    if x.size > 3:                                                             # undo the delta coding against counts[i-2]
+        x[3::2] = x[1] + np.cumsum(x[3::2])
+        if x.size > 4:
+            x[4::2] = x[2] + np.cumsum(x[4::2])
+    return x
 
 
 def counts_to_string(counts) -> str:
@@ -57,40 +81,75 @@ def counts_to_string(counts) -> str:
 
 # ---- decode ----------------------------------------------------------------------------------------------------------
 
-def decode_rle_masklet_packed(rle_masklet: Sequence, device=None) -> Optional[P.PackedMasks]:
-    """List of COCO RLE dicts (non-dict entries = missing frames -> empty masks, dataloader.py:364-368) -> packed (T, H, Wp)."""
-    sizes = [tuple(r["size"]) for r in rle_masklet if isinstance(r, dict)]
-    if not sizes:
-        return None
-    H, W = sizes[-1]
-    assert all(s == (H, W) for s in sizes), "all frames of a masklet share one size"
-    dev = P._dev(device)
-    plane_ids, starts, ends = [], [], []
-    for t, r in enumerate(rle_masklet):
-        if not isinstance(r, dict):
-            continue
-        c = string_to_counts(r["counts"])
-        edges = np.concatenate([[0], np.cumsum(c)])
-        assert edges[-1] == H * W, f"RLE of frame {t} covers {edges[-1]} pixels, expected {H * W}"
-        s, e = edges[1:-1:2], edges[2::2]                       # ones-runs are the odd-indexed counts
-        keep = e > s
-        plane_ids.append(np.full(int(keep.sum()), t, dtype=np.int32))
-        starts.append(s[keep].astype(np.int32))
-        ends.append(e[keep].astype(np.int32))
-    T = len(rle_masklet)
-    n_runs = int(sum(len(s) for s in starts))
+def _runs_of_masklets(rle_masklets: Sequence[Sequence], H: int, W: int):
+    """Ones-runs of every frame of several RLE masklets that share planes (frame t of every masklet -> plane t): pinned host int32
+    tensors (plane ids, starts, ends).  One call into the library's sequential C parser (`sola_rle_strings_to_runs`, ~1.5 ns per
+    character) — the reference's pycocotools decode also parses in C, but then fills H*W bytes per frame on the host."""
+    import ctypes as C
+    bufs, planes = [], []
+    for m in rle_masklets:
+        for t, r in enumerate(m):
+            if not isinstance(r, dict):
+                continue
+            assert tuple(r["size"]) == (H, W), "all frames of a masklet share one size"
+            cstr = r["counts"]
+            bufs.append(cstr.encode("ascii") if isinstance(cstr, str) else bytes(cstr))
+            planes.append(t)
+    n = len(bufs)
+    cap = max(16, sum(len(b) for b in bufs) // 2 + n)            # a ones-run costs at least two characters (its count and the next zeros-run)
+    run_p = torch.empty((cap,), dtype=torch.int32).pin_memory() if torch.cuda.is_available() else torch.empty((cap,), dtype=torch.int32)
+    run_s, run_e = torch.empty_like(run_p), torch.empty_like(run_p)
+    if run_p.is_pinned():
+        run_s, run_e = run_s.pin_memory(), run_e.pin_memory()
+    strings = (C.c_char_p * max(n, 1))(*bufs)
+    lens = (C.c_longlong * max(n, 1))(*[len(b) for b in bufs])
+    pids = (C.c_int * max(n, 1))(*planes)
+    n_runs = C.c_longlong(0)
+    _lib.call("sola_rle_strings_to_runs", C.cast(strings, C.c_void_p), C.cast(lens, C.c_void_p), C.cast(pids, C.c_void_p), n, H * W,
+              run_p.data_ptr(), run_s.data_ptr(), run_e.data_ptr(), cap, C.byref(n_runs))
+    k = int(n_runs.value)
+    return run_p[:k], run_s[:k], run_e[:k]
+
+
+def _fill_runs(run_p: torch.Tensor, run_s: torch.Tensor, run_e: torch.Tensor, T: int, H: int, W: int, dev) -> P.PackedMasks:
+    n_runs = int(run_p.numel())
     out = P.PackedMasks.empty((T,), H, W, dev)
     Hp = (H + 31) // 32
     scratch = torch.empty((T, W, Hp), dtype=torch.int32, device=dev)
+    rp = rs = re = None
     if n_runs:
-        rp = P.to_device(np.concatenate(plane_ids), device=dev)
-        rs = P.to_device(np.concatenate(starts), device=dev)
-        re = P.to_device(np.concatenate(ends), device=dev)
-    else:
-        rp = rs = re = None
+        rp, rs, re = (t.to(dev, non_blocking=True) for t in (run_p, run_s, run_e))
     with torch.cuda.device(dev):
         _lib.call("sola_rle_decode_runs", P._ptr(rp), P._ptr(rs), P._ptr(re), n_runs, T, H, W, scratch.data_ptr(), out.words.data_ptr(), P._stream(out.words))
     return out
+
+
+def _masklet_shape(rle_masklet: Sequence):
+    sizes = [tuple(r["size"]) for r in rle_masklet if isinstance(r, dict)]
+    return sizes[-1] if sizes else None
+
+
+def decode_rle_masklet_packed(rle_masklet: Sequence, device=None) -> Optional[P.PackedMasks]:
+    """List of COCO RLE dicts (non-dict entries = missing frames -> empty masks, dataloader.py:364-368) -> packed (T, H, Wp)."""
+    shape = _masklet_shape(rle_masklet)
+    if shape is None:
+        return None
+    H, W = shape
+    dev = P._dev(device)
+    return _fill_runs(*_runs_of_masklets([rle_masklet], H, W), len(rle_masklet), H, W, dev)
+
+
+def decode_rle_masklets_merged(rle_masklets: Sequence[Sequence], device=None) -> Optional[P.PackedMasks]:
+    """OR of several RLE masklets of one video (the selected SAM2 tracks of dataloader.py:339-344, or an expression's GT objects,
+    dataloader.py:285-299) straight into ONE packed (T, H, Wp) masklet: the ones-runs of every track are filled into the same
+    planes with atomicOr, so decode and merge are one launch and no per-track plane ever exists."""
+    live = [m for m in rle_masklets if _masklet_shape(m) is not None]
+    if not live:
+        return None
+    H, W = _masklet_shape(live[0])
+    T = len(live[0])
+    assert all(len(m) == T and _masklet_shape(m) == (H, W) for m in live), "tracks of one video share (T, H, W)"
+    return _fill_runs(*_runs_of_masklets(live, H, W), T, H, W, P._dev(device))
 
 
 def decode_rle_masklet(rle_masklet: Sequence, device=None) -> np.ndarray:

@@ -36,8 +36,8 @@ def main():
         "peer_pull": lambda: peers.pairwise_inter_matrix("pull"),
         "peer_direct": lambda: peers.pairwise_inter_matrix("direct"),
     }
-    if "--tma" in sys.argv:
-        variants["peer_tma"] = lambda: peers.pairwise_inter_matrix("tma")
+    variants["peer_tma"] = lambda: peers.pairwise_inter_matrix("tma")
+    variants["peer_auto"] = lambda: peers.pairwise_inter_matrix()
     for name, fn in variants.items():
         try:
             m = fn()

@@ -1,5 +1,5 @@
 """GPU, 2 ranks over NCCL (skipped on boxes with fewer than 2 GPUs): BASELINE config 5's exchange paths —
-`sharding.pairwise_inter_matrix_sharded` (split="words" / "tiles") and `sharding.PeerPlanes` (pull / direct) — plus the J&F
+`sharding.pairwise_inter_matrix_sharded` (split="words" / "tiles") and `sharding.PeerPlanes` (one-kernel TMA / pull / direct) — plus the J&F
 sweep's final all-reduce, each against the single-rank result (tests/multirank_worker.py)."""
 import json
 import os
@@ -31,5 +31,5 @@ def _run(n, extra=()):
 def test_two_rank_exchange_paths_match_single_rank():
     res = _run(2)
     assert res["world"] == 2
-    for name in ("nccl_words", "nccl_tiles", "peer_pull", "peer_direct", "jf_allreduce_int_totals"):
+    for name in ("nccl_words", "nccl_tiles", "peer_pull", "peer_direct", "peer_tma", "peer_auto", "jf_allreduce_int_totals"):
         assert res[name] is True, (name, res[name])
