@@ -171,8 +171,14 @@ class Evaluator:
     three methods onto a reference Evaluator instance."""
 
     def __init__(self, loader_dict=None, pred_dict=None, eval_output_dir: Optional[str] = None, data_type: str = "valid",
-                 eval_weight_epoch: int = 0, device=None):
+                 eval_weight_epoch: int = 0, device=None, dataset=None, with_boundary: bool = False):
+        """`dataset`: the object compute_JF_metrics asks for masklets — defaults to loader_dict["valid"].dataset as in the reference
+        (evaluator.py:176).  Pass `dataloader_ops.AlignDatasetAdapter.from_dataset(reference_dataset)` to keep RLE decode, OR-merge and
+        counting on the device (bit-packed end to end).  `with_boundary` adds the north-star's boundary F as `F_boundary` per expression
+        and `mean_F_boundary` (extension; the reference's JSON keys are unchanged)."""
         self.loader_dict = loader_dict
+        self.dataset = dataset
+        self.with_boundary = with_boundary
         self.pred_dict = pred_dict or {}
         self.eval_output_dir = eval_output_dir
         self.data_type = data_type
@@ -189,12 +195,12 @@ class Evaluator:
     def compute_JF_metrics(self):
         """evaluator.py:174-225 — same traversal order, same JSON schema, same float64 means; masks are counted by
         the batched sweep, one device read-back per video instead of 2*T + 3 `.item()` per expression."""
-        dataset = self.loader_dict["valid"].dataset
-        JF_dict, Js, Fs, JFs = {}, [], [], []
+        dataset = self.dataset if self.dataset is not None else self.loader_dict["valid"].dataset
+        JF_dict, Js, Fs, JFs, Fbs = {}, [], [], [], []
         for video_id in self.pred_dict:
             JF_dict[video_id] = {}
             dataset.set_video(video_id)
-            sweep = JFSweep(self.device)
+            sweep = JFSweep(self.device, with_boundary=self.with_boundary)
             for expression_id, pred_info in self.pred_dict[video_id].items():
                 gt_masklet = dataset.get_gt_masklet(video_id, expression_id)
                 pred_masklet = dataset.get_sam2_masklet(
@@ -209,6 +215,11 @@ class Evaluator:
                     "J": rec["J"], "F": rec["F"], "JF": rec["JF"],
                 }
                 Js.append(rec["J"]), Fs.append(rec["F"]), JFs.append(rec["JF"])
+                if self.with_boundary and "F_boundary" in rec:
+                    JF_dict[video_id][expression_id]["F_boundary"] = rec["F_boundary"]
+                    Fbs.append(rec["F_boundary"])
+        if Fbs:
+            self.metrics["mean_F_boundary"] = np.mean(Fbs)
         self.metrics["mean_J"] = np.mean(Js)
         self.metrics["mean_F"] = np.mean(Fs)
         self.metrics["mean_JF"] = np.mean(JFs)

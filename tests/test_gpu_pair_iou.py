@@ -257,11 +257,9 @@ def test_gdino_unit_end_to_end_config3_shape():
             assert abs(got["filtered_iou"][pid] - v) < 1e-3
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("SOLA_TEST_EXPERIMENTAL"),
-                    reason="sola_pair_iou_st_peer is compiled but not yet validated on hardware; set SOLA_TEST_EXPERIMENTAL=1 to run")
 @pytest.mark.parametrize("world,n_local", [(3, 16), (2, 64), (4, 8), (1, 40)])
 def test_pairwise_matrix_peer_tma_entry(world, n_local):
-    """sola_pair_iou_st_peer (experimental one-kernel exchange + K2): one tensor map per rank buffer — here `world` separate
+    """sola_pair_iou_st_peer (one-kernel exchange + K2; its 2-GPU run over NVLink is tests/test_gpu_multirank.py): one tensor map per rank buffer — here `world` separate
     allocations on one GPU stand in for the peers' NVLink-mapped buffers; the word-axis parts must sum to the full matrix."""
     import sola_b200 as S
     rng = np.random.default_rng(world * 100 + n_local)
