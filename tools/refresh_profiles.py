@@ -1,47 +1,109 @@
-"""Copy the evidence of the last `tools/gpu_profile.sh` run from gpurun_out/ (scratch) into profiles/ (tracked):
-bench line, launch list of the timed region, `ncu --page raw` CSVs of the full captures, and the DRAM traffic of the dominant kernel
-that bench.py reports as roofline.traffic.   usage: python tools/refresh_profiles.py [round-tag, default r1]"""
-import csv, json, os, shutil, subprocess, sys
+"""Copy the evidence of the last `tools/gpu_profile_r2.sh` run from gpurun_out/<tag>/ (scratch) into profiles/ (tracked):
+the launch list of the bench's timed region, the `ncu --page raw` CSV of every full capture, a compact summary of all captures
+(`<tag>_ncu_summary.json`), and `dominant_kernel_traffic.json` — the DRAM traffic bench.py reports as roofline.traffic, stamped with the
+kernel's register count so that a stale entry is detectable (tests/test_profiles_consistency.py compares it with the built library, and
+this script FAILS if a capture's register count differs from the library's).
+usage: python tools/refresh_profiles.py [round-tag, default r2]"""
+import csv, json, os, re, shutil, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+sys.path.insert(0, ROOT)
+tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
+G, P = os.path.join(ROOT, "gpurun_out", tag), os.path.join(ROOT, "profiles")
+
+KEYS = {
+    "gpu__time_duration.sum": "duration",
+    "dram__bytes_read.sum": "dram_read", "dram__bytes_write.sum": "dram_write",
+    "launch__registers_per_thread": "registers", "launch__grid_size": "grid", "launch__block_size": "block",
+    "launch__occupancy_limit_registers": "occ_limit_regs", "launch__occupancy_limit_shared_mem": "occ_limit_smem",
+    "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active": "pipe_alu_pct",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active": "pipe_fma_pct",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active": "pipe_xu_pct",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active": "pipe_lsu_pct",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed": "smem_wavefronts_pct",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum": "smem_wavefronts",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum": "smem_bank_conflicts",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct",
+    "smsp__inst_executed.sum": "warp_instructions",
+    "smsp__thread_inst_executed_per_inst_executed.ratio": "threads_per_instruction",
+}
+SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 
 
-def raw_csv(rep, dst):
+def library_registers():
+    from sola_b200 import _build
+    res = subprocess.run(["cuobjdump", "-res-usage", _build.build()], capture_output=True, text=True).stdout
+    out = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+)", res):
+        dn = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+        out[re.sub(r"^void\s+", "", dn).split("(")[0]] = int(m.group(2))
+    return out
+
+
+def summarise(rep):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     lines = [l for l in out.splitlines() if l.startswith('"')]
-    with open(dst, "w") as f:
-        f.write("\n".join(lines) + "\n")
     rows = list(csv.reader(lines))
-    return dict(zip(rows[0], zip(rows[1], rows[2])))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    d = dict(zip(hdr, zip(units, vals)))
+    s = {"kernel": d["Kernel Name"][1]}
+    for k, name in KEYS.items():
+        if k in d:
+            u, v = d[k]
+            try:
+                x = float(v.replace(",", ""))
+            except ValueError:
+                continue
+            s[name] = x * SCALE[u] if u in SCALE else x
+    if "duration" in s:
+        s["duration_ms"] = s.pop("duration")
+    stalls = {k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""): float(v[1])
+              for k, v in d.items() if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio")}
+    s["stalls_per_issue"] = {k: round(v, 3) for k, v in sorted(stalls.items(), key=lambda kv: -kv[1])[:6] if k != "selected"}
+    return lines, s
 
 
-def to_bytes(unit, val):
-    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
-    return int(round(float(val) * scale))
+def main():
+    os.makedirs(P, exist_ok=True)
+    regs = library_registers()
+    summary, bad = {}, []
+    for f in sorted(os.listdir(G)):
+        if not f.endswith(".ncu-rep"):
+            continue
+        name = f[:-len(".ncu-rep")]
+        lines, s = summarise(os.path.join(G, f))
+        with open(os.path.join(P, f"{tag}_ncu_{name}_raw.csv"), "w") as out:
+            out.write("\n".join(lines) + "\n")
+        base = s["kernel"].split("(")[0]
+        lib_regs = next((r for k, r in regs.items() if k.replace("sola::", "") == base.replace("sola::", "")), None)
+        s["library_registers"] = lib_regs
+        if lib_regs is not None and "registers" in s and int(s["registers"]) != lib_regs:
+            bad.append(f"{name}: captured with {int(s['registers'])} registers, the built library has {lib_regs} ({base})")
+        summary[name] = s
+    with open(os.path.join(P, f"{tag}_ncu_summary.json"), "w") as f:
+        json.dump(summary, f, indent=1)
+    if os.path.isfile(os.path.join(G, "launches.csv")):
+        shutil.copy(os.path.join(G, "launches.csv"), os.path.join(P, f"{tag}_launches_timed_region.csv"))
+    traffic = {}
+    for key, cap in (("fused_pack_resize_kernel<float>", "fused_f32_720p"), ("jf_fused_kernel", "jf_region"), ("jf_fused_kernel[boundary]", "jf_boundary")):
+        if cap in summary:
+            s = summary[cap]
+            traffic[key] = {"source": f"profiles/{tag}_ncu_{cap}_raw.csv (ncu --set full --clock-control none, one launch)", "kernel": s["kernel"].split("(")[0],
+                            "registers": int(s.get("registers", 0)), "dram_bytes_read": int(s.get("dram_read", 0)), "dram_bytes_write": int(s.get("dram_write", 0)),
+                            "dram_bytes_per_launch": int(s.get("dram_read", 0) + s.get("dram_write", 0)), "gpu_time_ms": s.get("duration_ms")}
+    if traffic:
+        with open(os.path.join(P, "dominant_kernel_traffic.json"), "w") as f:
+            json.dump(traffic, f, indent=1)
+    for name, s in summary.items():
+        print(f"{name:22s} {s['kernel'].split('(')[0][:48]:48s} {s.get('duration_ms', 0) * 1e3:9.1f} us  regs {int(s.get('registers', 0)):3d}  "
+              f"issue {s.get('issue_active_pct', 0):5.1f}%  alu {s.get('pipe_alu_pct', 0):5.1f}%  xu {s.get('pipe_xu_pct', 0):5.1f}%  "
+              f"dram {s.get('dram_throughput_pct', 0):5.1f}%  smem {s.get('smem_wavefronts_pct', 0):5.1f}%")
+    if bad:
+        raise SystemExit("STALE CAPTURES (rebuild or re-capture):\n  " + "\n  ".join(bad))
+    print("profiles refreshed:", tag)
 
 
-with open(os.path.join(G, "bench.log")) as f:
-    line = next(l for l in f if l.startswith("{"))
-with open(os.path.join(P, f"{tag}_bench_1gpu.json"), "w") as f:
-    f.write(line)
-shutil.copy(os.path.join(G, "launches.csv"), os.path.join(P, f"{tag}_launches_timed_region.csv"))
-traffic_path = os.path.join(P, "dominant_kernel_traffic.json")
-traffic = json.load(open(traffic_path)) if os.path.isfile(traffic_path) else {}
-for rep, name, key in (("fused_full.ncu-rep", f"{tag}_fused_ncu_full_raw.csv", "fused_pack_resize_kernel<float>"),
-                       ("k2_full.ncu-rep", f"{tag}_k2_ncu_full_raw.csv", None)):
-    src = os.path.join(G, rep)
-    if not os.path.isfile(src):
-        continue
-    d = raw_csv(src, os.path.join(P, name))
-    if key:
-        rd, wr = to_bytes(*d["dram__bytes_read.sum"]), to_bytes(*d["dram__bytes_write.sum"])
-        old = traffic.get(key, {})
-        traffic[key] = {"source": f"profiles/{name} (ncu --set full --clock-control none, one launch, bench config 2)",
-                        "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
-                        "algorithmic_bytes_per_launch": old.get("algorithmic_bytes_per_launch"),
-                        "gpu_time_ms": float(d["gpu__time_duration.sum"][1]) * ({"us": 1e-3, "ms": 1.0}[d["gpu__time_duration.sum"][0]])}
-with open(traffic_path, "w") as f:
-    json.dump(traffic, f, indent=1)
-print("profiles refreshed:", tag)
+if __name__ == "__main__":
+    main()
