@@ -128,31 +128,43 @@ __host__ __device__ constexpr int jf_isqrt(int x) {
   return v;
 }
 
+// Hot-loop shared-memory accesses go through explicit 32-bit shared-window addresses: the generic pointers an `extern __shared__`
+// array decays to cost a window-base computation (S2UR SR_CgaCtaId / ULEA ...) and 64-bit address arithmetic per access group.
+template <int OFF = 0>
+__device__ __forceinline__ uint32_t lds32(unsigned addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32_if(unsigned addr, uint32_t v, bool pred) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p st.shared.u32 [%0], %1;\n}" ::"r"(addr), "r"(v), "r"((unsigned)pred) : "memory");
+}
+
 struct DilState {
-  const uint32_t* up; const uint32_t* dn;    // rows -vh / +vh of the item's word
+  unsigned up, dn;                           // shared byte addresses of rows -vh / +vh of the item's word
   uint32_t L, C, R, dil;
 };
 
 template <int N>
-__device__ __forceinline__ void dil_grow(DilState& d, int BP) {
+__device__ __forceinline__ void dil_grow(DilState& d, unsigned pitch_bytes) {
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    d.up -= BP; d.dn += BP;
-    d.L |= d.up[-1] | d.dn[-1];
-    d.C |= d.up[0] | d.dn[0];
-    d.R |= d.up[1] | d.dn[1];
+    d.up -= pitch_bytes; d.dn += pitch_bytes;
+    d.L |= lds32<-4>(d.up) | lds32<-4>(d.dn);
+    d.C |= lds32<0>(d.up) | lds32<0>(d.dn);
+    d.R |= lds32<4>(d.up) | lds32<4>(d.dn);
   }
 }
 
 template <int RAD, int K, int VH>
 struct DilStep {
-  static __device__ __forceinline__ void run(DilState& d, int BP) {
+  static __device__ __forceinline__ void run(DilState& d, unsigned pitch_bytes) {
     constexpr int VK = jf_isqrt(RAD * RAD - K * K);
-    dil_grow<VK - VH>(d, BP);
+    dil_grow<VK - VH>(d, pitch_bytes);
     // a source pixel at x-k lands on x (shift towards higher bits, refilled from the left word) and one at x+k on x (the mirror)
     if constexpr (K > 0) {
       d.dil |= __funnelshift_l(d.L, d.C, K) | __funnelshift_r(d.C, d.R, K);
-      DilStep<RAD, K - 1, VK>::run(d, BP);
+      DilStep<RAD, K - 1, VK>::run(d, pitch_bytes);
     } else {
       d.dil |= d.C;
     }
@@ -160,18 +172,18 @@ struct DilStep {
 };
 
 template <int RAD>
-__device__ __forceinline__ uint32_t dilate_word_fixed(const uint32_t* __restrict__ src, int BP) {
-  DilState d{src, src, src[-1], src[0], src[1], 0u};
-  DilStep<RAD, RAD, 0>::run(d, BP);
+__device__ __forceinline__ uint32_t dilate_word_fixed(unsigned src, unsigned pitch_bytes) {
+  DilState d{src, src, lds32<-4>(src), lds32<0>(src), lds32<4>(src), 0u};
+  DilStep<RAD, RAD, 0>::run(d, pitch_bytes);
   return d.dil;
 }
 
-__device__ __forceinline__ uint32_t dilate_word_generic(const uint32_t* __restrict__ src, int BP, int r, const unsigned char* __restrict__ v) {
-  DilState d{src, src, src[-1], src[0], src[1], 0u};
+__device__ __forceinline__ uint32_t dilate_word_generic(unsigned src, unsigned pitch_bytes, int r, const unsigned char* __restrict__ v) {
+  DilState d{src, src, lds32<-4>(src), lds32<0>(src), lds32<4>(src), 0u};
   int vh = 0;
   for (int k = r; k >= 0; --k) {
     const int vk = v[k];
-    for (; vh < vk; ++vh) dil_grow<1>(d, BP);
+    for (; vh < vk; ++vh) dil_grow<1>(d, pitch_bytes);
     d.dil |= k ? (__funnelshift_l(d.L, d.C, k) | __funnelshift_r(d.C, d.R, k)) : d.C;
   }
   return d.dil;
@@ -179,9 +191,9 @@ __device__ __forceinline__ uint32_t dilate_word_generic(const uint32_t* __restri
 
 // RAD > 0: compile-time radius; RAD == 0: run-time radius r with the table v
 template <int RAD>
-__device__ __forceinline__ uint32_t dilate_word(const uint32_t* __restrict__ src, int BP, int r, const unsigned char* __restrict__ v) {
-  if constexpr (RAD > 0) return dilate_word_fixed<RAD>(src, BP);
-  else return dilate_word_generic(src, BP, r, v);
+__device__ __forceinline__ uint32_t dilate_word(unsigned src, unsigned pitch_bytes, int r, const unsigned char* __restrict__ v) {
+  if constexpr (RAD > 0) return dilate_word_fixed<RAD>(src, pitch_bytes);
+  else return dilate_word_generic(src, pitch_bytes, r, v);
 }
 
 // ---- phase 2: match counting over the owned rows of one item --------------------------------------------------------------------
@@ -189,7 +201,7 @@ __device__ __forceinline__ uint32_t dilate_word(const uint32_t* __restrict__ src
 // disk, so a pixel it matches IS matched) settles the words whose pixels all have a partner within 2 px — nearly all of them when
 // pred ≈ gt; only the rest go to queue 2 and pay for the full (2r+1)-row dilation, again 32 at a time.
 template <int RAD>
-__device__ __forceinline__ void jf_phase2(const uint32_t* __restrict__ bmF, const uint32_t* __restrict__ bmG, int BP, int r, int n_steps,
+__device__ __forceinline__ void jf_phase2(unsigned sF, unsigned sG /* shared byte addresses of the two boundary maps */, int BP, int r, int n_steps,
                                           int my_o0 /* this lane's boundary-map offset at step 0 */, const uint2* __restrict__ masks,
                                           const unsigned char* __restrict__ vtab, uint32_t* __restrict__ q1, uint32_t* __restrict__ q2,
                                           int lane, int& fm, int& gm) {
@@ -201,8 +213,8 @@ __device__ __forceinline__ void jf_phase2(const uint32_t* __restrict__ bmF, cons
       const uint32_t e = q2[n2 + lane];
       const int eo = (int)(e & 0x7fffffffu);
       const bool sel = (e >> 31) != 0u;
-      const uint32_t need = (sel ? bmG : bmF)[eo];
-      const int m = __popc(need & dilate_word<RAD>((sel ? bmF : bmG) + eo, BP, r, vtab));
+      const uint32_t need = lds32((sel ? sG : sF) + 4u * eo);
+      const int m = __popc(need & dilate_word<RAD>((sel ? sF : sG) + 4u * eo, 4u * BP, r, vtab));
       if (sel) gm += m; else fm += m;
     }
     __syncwarp();
@@ -214,9 +226,9 @@ __device__ __forceinline__ void jf_phase2(const uint32_t* __restrict__ bmF, cons
       e = q1[n1 + lane];
       const int eo = (int)(e & 0x7fffffffu);
       const bool sel = (e >> 31) != 0u;
-      const uint32_t need = (sel ? bmG : bmF)[eo];
+      const uint32_t need = lds32((sel ? sG : sF) + 4u * eo);
       if (PRE && r > JF_PRE_R) {
-        const uint32_t pre = dilate_word_fixed<JF_PRE_R>((sel ? bmF : bmG) + eo, BP);
+        const uint32_t pre = dilate_word_fixed<JF_PRE_R>((sel ? sF : sG) + 4u * eo, 4u * BP);
         fail = (need & ~pre) != 0u;
         if (!fail) { if (sel) gm += __popc(need); else fm += __popc(need); }
       } else {
@@ -256,6 +268,7 @@ jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_
   uint32_t* bmF = rawG + raw_cap;
   uint32_t* bmG = bmF + bm_cap;
   uint2* masks = reinterpret_cast<uint2*>(bmG + bm_cap);          // [JF_WARPS][mask_steps]: phase 1's ballots = phase 2's work list
+  const unsigned sF = smem_u32(bmF), sG = smem_u32(bmG);
   __shared__ uint64_t bar;
   __shared__ uint32_t queue1[JF_WARPS][JF_QUEUE], queue2[JF_WARPS][64];
   __shared__ int red[7][JF_WARPS];
@@ -315,46 +328,49 @@ jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_
       const uint32_t lastbit = (c == Wp - 1) ? (1u << ((g.W - 1) & 31)) : 0u;
       const bool east = c + 1 < Wp;
       my_o0 = j0 * BP + c + 1;
-      const uint32_t* rp = rawP + off + (ya - g.ra) * Wp + c;        // row y of the raw tile = rp[(y - ya) * Wp]; dereferenced in-frame only
-      const uint32_t* rq = rawG + off + (ya - g.ra) * Wp + c;
-      uint32_t p0 = 0u, pe0 = 0u, q0 = 0u, qe0 = 0u;
+      // shared byte addresses: row y of the raw tile = ap + (y - ya) * Wp * 4 (dereferenced in-frame only); boundary words at ab
+      unsigned ap = smem_u32(rawP) + 4u * (unsigned)(off + (ya - g.ra) * Wp + c);
+      const unsigned dPG = 4u * (unsigned)raw_cap, dFG = sG - sF, Wp4 = 4u * Wp, BP4 = 4u * BP;
+      unsigned ab = sF + 4u * (unsigned)my_o0;
+      // Branch-free pipeline: every step loads row clamp(y + 1) of the staged tile (always a valid address), the registers shift
+      // unconditionally, and validity lives in three masks — in-frame, has-a-row-below, owned — derived from per-lane step ranges.
+      const int n_act = walker ? j1 - j0 : 0;
+      const int k_in0 = max(0, -ya), k_in1 = min(n_act, g.H - ya), k_s1 = min(k_in1, g.H - 1 - ya);
+      const int k_o0 = max(k_in0, g.y0 - ya), k_o1 = min(k_in1, g.y1 - ya);
+      const int row_hi = (int)((g.g1 - g.g0) / Wp) - 1;            // last staged row (tile-relative)
+      const int row0 = ya - g.ra;                                   // tile-relative row of step 0 (may be negative / past the end: clamped)
+      const uint32_t emask = east ? 0xffffffffu : 0u;
+      auto row_addr = [&](int row) { return ap + (unsigned)(min(max(row, 0), row_hi) - row0) * Wp4; };
+      uint32_t p0, pe0, q0, qe0;
       {
-        const int y = max(ya, 0);                                    // first in-frame row of the walk (if any): prime the registers
-        if (walker && y < g.H && y < ya + (j1 - j0)) {
-          const int d = (y - ya) * Wp;
-          p0 = rp[d]; q0 = rq[d];
-          pe0 = __funnelshift_r(p0, east ? rp[d + 1] : 0u, 1);
-          qe0 = __funnelshift_r(q0, east ? rq[d + 1] : 0u, 1);
-        }
+        const unsigned a0 = row_addr(row0);
+        p0 = lds32(a0); q0 = lds32(a0 + dPG);
+        pe0 = __funnelshift_r(p0, lds32<4>(a0) & emask, 1);
+        qe0 = __funnelshift_r(q0, lds32<4>(a0 + dPG) & emask, 1);
       }
       uint2* mk = masks + warp * mask_steps;
 #pragma unroll 2
       for (int k = 0; k < n_steps; ++k) {
-        const int y = ya + k;
-        const bool active = walker && k < j1 - j0;
-        const bool in_frame = active && y >= 0 && y < g.H;
-        const bool south = in_frame && y + 1 < g.H;
-        const bool owned = in_frame && y >= g.y0 && y < g.y1;
-        uint32_t p1 = 0u, q1w = 0u, pe1 = 0u, qe1 = 0u;
-        if (south) {
-          const int d = (k + 1) * Wp;
-          p1 = rp[d]; q1w = rq[d];
-          pe1 = __funnelshift_r(p1, east ? rp[d + 1] : 0u, 1);
-          qe1 = __funnelshift_r(q1w, east ? rq[d + 1] : 0u, 1);
-        }
-        const uint32_t ps = p0 ^ p1, qs = q0 ^ q1w;
+        const uint32_t fmask = (k >= k_in0 && k < k_in1) ? 0xffffffffu : 0u;
+        const uint32_t smask = (k >= k_in0 && k < k_s1) ? 0xffffffffu : 0u;
+        const uint32_t omask = (k >= k_o0 && k < k_o1) ? 0xffffffffu : 0u;
+        const unsigned a1 = row_addr(row0 + k + 1);
+        const uint32_t p1 = lds32(a1), q1w = lds32(a1 + dPG);
+        const uint32_t pe1 = __funnelshift_r(p1, lds32<4>(a1) & emask, 1);
+        const uint32_t qe1 = __funnelshift_r(q1w, lds32<4>(a1 + dPG) & emask, 1);
+        const uint32_t ps = p0 ^ p1, qs = q0 ^ q1w, lbs = lastbit & smask;
         // rows with a row below: (s ^ e) | (s ^ south) | (s ^ south-east), last column: s ^ south only; last row: s ^ e, corner 0
-        uint32_t bp = south ? ((((p0 ^ pe0) | ps | (p0 ^ pe1)) & ~lastbit) | (ps & lastbit)) : ((p0 ^ pe0) & ~lastbit);
-        uint32_t bq = south ? ((((q0 ^ qe0) | qs | (q0 ^ qe1)) & ~lastbit) | (qs & lastbit)) : ((q0 ^ qe0) & ~lastbit);
-        if (!in_frame) { bp = 0u; bq = 0u; }
-        if (owned) {
-          n_p += __popc(p0); n_g += __popc(q0); n_i += __popc(p0 & q0);
-          n_bf += __popc(bp); n_bg += __popc(bq);
-        }
-        if (active) { bmF[my_o0 + k * BP] = bp; bmG[my_o0 + k * BP] = bq; }
-        const unsigned mF = __ballot_sync(FULL, owned && bp != 0u), mG = __ballot_sync(FULL, owned && bq != 0u);
+        const uint32_t bp = ((((p0 ^ pe0) | ((ps | (p0 ^ pe1)) & smask)) & ~lastbit) | (ps & lbs)) & fmask;
+        const uint32_t bq = ((((q0 ^ qe0) | ((qs | (q0 ^ qe1)) & smask)) & ~lastbit) | (qs & lbs)) & fmask;
+        const uint32_t pm = p0 & omask, qm = q0 & omask, bpm = bp & omask, bqm = bq & omask;
+        n_p += __popc(pm); n_g += __popc(qm); n_i += __popc(pm & qm);
+        n_bf += __popc(bpm); n_bg += __popc(bqm);
+        sts32_if(ab, bp, k < n_act);
+        sts32_if(ab + dFG, bq, k < n_act);
+        ab += BP4;
+        const unsigned mF = __ballot_sync(FULL, bpm != 0u), mG = __ballot_sync(FULL, bqm != 0u);
         if (lane == 0) mk[k] = make_uint2(mF, mG);
-        if (south) { p0 = p1; pe0 = pe1; q0 = q1w; qe0 = qe1; }
+        p0 = p1; pe0 = pe1; q0 = q1w; qe0 = qe1;
       }
     }
     __syncthreads();                                        // boundary maps complete; the raw tile is dead
@@ -365,12 +381,12 @@ jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_
       uint32_t* q2 = queue2[warp];
       const uint2* mk = masks + warp * mask_steps;
       switch (r) {
-        case 6: jf_phase2<6>(bmF, bmG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;       // 360 x 640
-        case 8: jf_phase2<8>(bmF, bmG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;       // 480 x 854
-        case 9: jf_phase2<9>(bmF, bmG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;       // 540 x 960
-        case 12: jf_phase2<12>(bmF, bmG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;     // 720 x 1280
-        case 18: jf_phase2<18>(bmF, bmG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;     // 1080 x 1920
-        default: jf_phase2<0>(bmF, bmG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;
+        case 6: jf_phase2<6>(sF, sG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;       // 360 x 640
+        case 8: jf_phase2<8>(sF, sG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;       // 480 x 854
+        case 9: jf_phase2<9>(sF, sG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;       // 540 x 960
+        case 12: jf_phase2<12>(sF, sG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;     // 720 x 1280
+        case 18: jf_phase2<18>(sF, sG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;     // 1080 x 1920
+        default: jf_phase2<0>(sF, sG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;
       }
     }
 

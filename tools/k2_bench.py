@@ -1,4 +1,4 @@
-"""K2 N x N kernel alone on (a) the bench's object-like resized masklets and (b) dense random planes; SOLA_K2_PLAIN selects the variant."""
+"""K2 N x N kernel alone on (a) the bench's object-like resized masklets and (b) dense random planes (no all-zero quad to skip)."""
 import json, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -22,7 +22,7 @@ del logits
 ref = S.pairwise_inter_matrix(resized)
 words = resized.words[0].numel()
 pairs = 64 * 63 // 2
-out = {"plain": os.environ.get("SOLA_K2_PLAIN", "0"), "occ": os.environ.get("SOLA_K2_OCC", "default")}
+out = {}
 ms = timed(lambda: S.pairwise_inter_matrix(resized))
 out["object_like_64x80x540x960"] = {"ms": ms, "pair_words_per_s": pairs * words / ms * 1e3, "checksum": int(ref.sum().item())}
 dense = S.PackedMasks(torch.randint(-2**31, 2**31 - 1, resized.words.shape, dtype=torch.int32, device="cuda"), resized.H, resized.W)
