@@ -406,7 +406,8 @@ def cpu_baseline_sample(n_tracks, n_frames):
 def jf_region(device, rank, world, reps, peak):
     """Two passes over the same config-4-shaped sweep: (1) J + F exactly as the reference defines them (evaluator.py:227-247: region
     counts only — HBM bound), (2) the same plus the north-star's boundary F (seg2bmap + disk dilation + match counting — integer /
-    shared-memory bound).  Each pass is ONE launch of the fused kernel per sweep."""
+    shared-memory bound).  Each pass is one launch of the fused kernel per sweep (two in boundary mode when the sweep mixes
+    1080p-class tiles, which need a whole SM's shared memory, with smaller ones)."""
     import torch.distributed as dist
     import sola_b200 as S
     from oracle import boundary_oracle as BO
@@ -476,7 +477,7 @@ def jf_region(device, rank, world, reps, peak):
         sweep_s, kern_s, total_frames = float(dt[0]), float(dt[1]), float(frames[0])
         ach = plan.algorithmic_bytes / (k_ms * 1e-3) / 1e9
         stage[mode] = {"masklet_frames_per_s": total_frames / sweep_s, "kernel_only_masklet_frames_per_s": total_frames / kern_s,
-                       "ms_per_sweep": sweep_s * 1e3, "kernel_ms": kern_s * 1e3, "launches_per_sweep": 1,
+                       "ms_per_sweep": sweep_s * 1e3, "kernel_ms": kern_s * 1e3, "launches_per_sweep": len(plan.launches),
                        "mean_J": red["mean_J"], "mean_F": red["mean_F"], "int_totals": [int(x) for x in red["int_totals"]]}
         if with_boundary:
             stage[mode]["mean_F_boundary_rank0"] = float(np.mean(Fbs))

@@ -530,20 +530,49 @@ class JfPlan(_C.Structure):
 assert _C.sizeof(JfUnit) == 64 and _C.sizeof(JfPlan) == 32
 
 
+class _JFLaunch:
+    """One planned launch of the fused kernel over a list of (pred words, gt words, T, H, W, radius) units."""
+
+    def __init__(self, units, device):
+        n = len(units)
+        arr = (JfUnit * max(n, 1))()
+        for k, (pw, gw, T, H, W, radius) in enumerate(units):
+            u = arr[k]
+            u.pred, u.gt, u.T, u.H, u.W, u.radius = pw.data_ptr(), gw.data_ptr(), T, H, W, radius
+        self.n_units, self.device = n, device
+        self.plan = JfPlan()
+        _lib.call("sola_jf_sweep_plan", _C.cast(arr, _C.c_void_p), n, _C.byref(self.plan))
+        self.offsets = [arr[k].out_off for k in range(n)]
+        self.bands = [(arr[k].band_rows, arr[k].n_bands) for k in range(n)]
+        self.smem_bytes = (2 * self.plan.raw_cap + 2 * self.plan.bm_cap + 16 * self.plan.mask_steps) * 4
+        self.units_dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)[: 64 * n].clone().to(device) if n else None
+
+    def run(self, out: torch.Tensor) -> None:
+        if self.n_units == 0 or self.plan.total_frames == 0:
+            return
+        with torch.cuda.device(self.device):
+            _lib.call("sola_jf_sweep", self.units_dev.data_ptr(), self.n_units, _C.byref(self.plan), out.data_ptr(),
+                      torch.cuda.current_stream(self.device).cuda_stream)
+
+
+JF_SMALL_TILE_BYTES = 100 * 1024          # the library's two-CTAs-per-SM tile budget (csrc/jf_fused.cu: JF_BUDGET_2CTA)
+
+
 class JFSweepPlan:
-    """A planned J&F sweep over units of different shapes: ONE launch of the fused kernel for all of them.
+    """A planned J&F sweep over units of different shapes through the fused kernel.
 
         plan = JFSweepPlan([(pred0, gt0), (pred1, gt1), ...], with_boundary=True)      # PackedMasks pairs, (T_u, H_u, Wp_u) each
-        counts = plan.run()          # int32 (7, total_frames) on the device; frames in unit order, plan.offsets[u] = first column of unit u
+        counts = plan.run()          # int32 (7, total_frames) on the device; plan.offsets[u] = first column of unit u, plan.frames[u] columns
 
+    All units go into ONE launch, unless the sweep mixes frames whose tile needs the whole SM's shared memory (1080p-class with the
+    boundary disk: one CTA per SM) with smaller ones (two CTAs per SM): those two classes are launched separately so that one large
+    video does not halve the occupancy of every other unit — at most two launches per sweep.
     The plan keeps references to the planes; run() may be called repeatedly (the bench times it)."""
 
     def __init__(self, pairs: Sequence[Tuple["PackedMasks", "PackedMasks"]], with_boundary: bool = True, bound_th: float = 0.008):
-        self.pairs = []
-        self.device = None
-        n = len(pairs)
-        arr = (JfUnit * max(n, 1))()
-        for k, (p, g) in enumerate(pairs):
+        self.pairs, self.device = [], None
+        units = []
+        for p, g in pairs:
             assert isinstance(p, PackedMasks) and isinstance(g, PackedMasks)
             assert (p.H, p.W) == (g.H, g.W) and p.n_frames == g.n_frames, "pred / gt shape mismatch"
             pw, gw = p.words.contiguous(), g.words.contiguous()
@@ -552,34 +581,47 @@ class JFSweepPlan:
                 self.device = pw.device
             assert pw.device == self.device, "all units of a sweep must live on one device"
             self.pairs.append((pw, gw))
-            u = arr[k]
-            u.pred, u.gt = pw.data_ptr(), gw.data_ptr()
-            u.T, u.H, u.W = p.n_frames, p.H, p.W
-            u.radius = bound_pix_for(p.H, p.W, bound_th) if with_boundary else -1
-        self.n_units = n
-        self.plan = JfPlan()
-        _lib.call("sola_jf_sweep_plan", _C.cast(arr, _C.c_void_p), n, _C.byref(self.plan))
-        self.n_items, self.total_frames = self.plan.n_items, self.plan.total_frames
-        self.smem_bytes = (2 * self.plan.raw_cap + 2 * self.plan.bm_cap + 16 * self.plan.mask_steps) * 4
-        self.offsets = [arr[k].out_off for k in range(n)]
-        self.frames = [arr[k].T for k in range(n)]
-        self.bands = [(arr[k].band_rows, arr[k].n_bands) for k in range(n)]
-        self.units_dev = None
-        if n:
-            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)[: 64 * n].clone()
-            self.units_dev = host.to(self.device)
+            units.append((pw, gw, p.n_frames, p.H, p.W, bound_pix_for(p.H, p.W, bound_th) if with_boundary else -1))
+        self.n_units = len(units)
+        self.frames = [u[2] for u in units]
+        # class of every unit: does its tile fit the two-CTAs-per-SM budget?  (planned alone: a host-only call)
+        small, big = [], []
+        for k, u in enumerate(units):
+            alone = _JFLaunch([(u[0], u[1], 1, u[3], u[4], u[5])], self.device)
+            (small if alone.smem_bytes <= JF_SMALL_TILE_BYTES else big).append(k)
+        self.launches, self.offsets, base = [], [0] * self.n_units, 0
+        for group in (small, big):
+            if not group:
+                continue
+            L = _JFLaunch([units[k] for k in group], self.device)
+            for j, k in enumerate(group):
+                self.offsets[k] = base + L.offsets[j]
+            self.launches.append((L, base))
+            base += L.plan.total_frames
+        self.total_frames = base
+        self.n_items = sum(L.plan.n_items for L, _ in self.launches)
+        self.smem_bytes = max([L.smem_bytes for L, _ in self.launches], default=0)
+        self.bands = [None] * self.n_units
+        for (L, _), group in zip(self.launches, [g for g in (small, big) if g]):
+            for j, k in enumerate(group):
+                self.bands[k] = L.bands[j]
         self.algorithmic_bytes = sum(2 * pw.numel() * 4 for pw, _ in self.pairs)
+        self._parts = None
 
     def run(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         dev = self.device if self.device is not None else _dev()
         if out is None:
             out = torch.empty((7, self.total_frames), dtype=torch.int32, device=dev)
         assert out.shape == (7, self.total_frames) and out.dtype == torch.int32 and out.is_contiguous()
-        if self.n_units == 0 or self.total_frames == 0:
+        if len(self.launches) == 1:
+            self.launches[0][0].run(out)
             return out
-        with torch.cuda.device(dev):
-            _lib.call("sola_jf_sweep", self.units_dev.data_ptr(), self.n_units, _C.byref(self.plan), out.data_ptr(),
-                      torch.cuda.current_stream(dev).cuda_stream)
+        # two launches: each writes its own (7, n) table (the kernel's row stride is its launch's frame count), then one strided copy each
+        if self._parts is None:
+            self._parts = [torch.empty((7, L.plan.total_frames), dtype=torch.int32, device=dev) for L, _ in self.launches]
+        for (L, base), part in zip(self.launches, self._parts):
+            L.run(part)
+            out[:, base: base + L.plan.total_frames].copy_(part)
         return out
 
 
