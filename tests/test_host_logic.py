@@ -51,7 +51,7 @@ def test_greedy_state_random_tables_vs_oracle():
     rng = np.random.default_rng(7)
     for trial in range(80):
         n = int(rng.integers(1, 40))
-        T = int(rng.choice([8, 40, 260]))
+        T = int(rng.choice([20, 40, 260]))                       # every frame_idx below stays inside the masklet (out of range raises, as in the reference)
         bin_size = int(rng.choice([1, 4]))
         frame_idx = rng.integers(0, 5, n) * int(rng.choice([1, 2, 4]))
         iou = rng.random((n, n))
@@ -264,3 +264,33 @@ def test_carry_save_accumulation_is_exact():
             f, twos = maj(twos, t1, t2), twos ^ t1 ^ t2
             acc += 4 * pop(f)
         assert acc + 2 * pop(twos) + pop(ones) == sum(pop(int(u & v)) for u, v in zip(a.ravel(), b.ravel()))
+
+
+def test_prompt_frame_idx_out_of_range_raises():
+    """masklets[prompt_id][frame_idx] raises in the reference (generate_tokens_grid.py:273); the kernel must never be asked to compare
+    against a clamped, wrong frame."""
+    import pytest
+    prompts = [{"prompt_id": 0, "frame_idx": 0}, {"prompt_id": 1, "frame_idx": 8}]
+    with pytest.raises(IndexError):
+        dedup.GreedyState(prompts, 8, mode="grid")
+    with pytest.raises(IndexError):
+        dedup.GreedyState([{"prompt_id": 0, "frame_idx": -4}], 8, mode="grid")
+    dedup.GreedyState(prompts, 9, mode="grid")
+
+
+def test_label_metrics_from_counts_match_reference_formulas():
+    """dedup.label_metrics_from_counts (the host half of the label step, generate_tokens_grid.py:253-264) against
+    oracle.compute_mask_metrics on every (track, GT object) pair, incl. the four empty-case rules."""
+    rng = np.random.default_rng(11)
+    N, G, T, H, W = 4, 3, 6, 12, 20
+    tracks = rng.random((N, T, H, W)) > 0.6
+    gts = rng.random((G, T, H, W)) > 0.7
+    tracks[0, 1] = False; gts[0, 1] = False            # both empty
+    tracks[1, 2] = False                               # pred empty, gt not
+    gts[1, 3] = False                                  # gt empty, pred not
+    inter = (tracks[:, None] & gts[None]).sum((-2, -1)).astype(np.int32)
+    lab = dedup.label_metrics_from_counts(inter, tracks.sum((-2, -1)).astype(np.int32), gts.sum((-2, -1)).astype(np.int32))
+    for i in range(N):
+        for g in range(G):
+            p, r, u = O.compute_mask_metrics(torch.from_numpy(tracks[i]).float(), torch.from_numpy(gts[g]).float())
+            assert (float(p), float(r), float(u)) == (float(lab["precision"][i, g]), float(lab["recall"][i, g]), float(lab["iou"][i, g]))

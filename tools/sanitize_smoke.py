@@ -53,5 +53,18 @@ evaluator.compute_JF(*synth.jf_pair(4, 50, 77, 1, device="cuda"))
 pj, gj = synth.jf_pair(4, 50, 77, 1, device="cuda")
 for a_, b_ in ((pj, gj), (pj.float(), gj.float()), (S.pack_masks(pj), S.pack_masks(gj))):
     S.packed.jf_accumulators(a_, b_)
+# fused J&F kernel: both modes, a multi-band frame, a mixed sweep (two tile classes), merged RLE decode, labels in the job
+from sola_b200 import packed as P
+for (T_, H_, W_) in ((3, 48, 85), (2, 300, 70), (1, 1080, 1920)):
+    a_, b_ = synth.object_pair(T_, H_, W_, 3, device="cuda", speckle=0.01)
+    P.jf_boundary_counts(S.pack_masks(a_), S.pack_masks(b_))
+    P.jf_boundary_counts(S.pack_masks(a_), S.pack_masks(b_), with_boundary=False)
+units = synth.mevis_like_sweep(3, 2, 9, "cuda", t_range=(2, 4), shapes=[(48, 85), (120, 214), (1080, 1920)], pack=S.pack_masks)
+P.JFSweepPlan([(p_, g_) for _, _, p_, g_ in units], with_boundary=True).run()
+enc2 = rle.encode_rle_masklet_torch(S.pack_masks(synth.blob_masklet(3, 40, 70, 2, device="cuda")))
+rle.decode_rle_masklets_merged([enc2, enc2])
+job.set_gt_masklets(S.pack_masks(torch.stack([synth.blob_masklet(8, 540, 960, 4 + k, device="cuda") for k in range(2)])))
+job.enqueue(logits.cuda(), torch.from_numpy(np.stack([p["segmentation"] for p in pr])).cuda())
+assert "labels" in job.finish()
 torch.cuda.synchronize()
 print("sanitize smoke ok")
