@@ -18,11 +18,12 @@ from . import packed as P
 # ---- host formulas over exact integer counts -------------------------------------------------------------------
 
 def J_from_counts(inter, n_pred, n_gt):
-    """evaluator.py:227-237 — mean over frames of inter/union (1.0 for an empty union), numpy float64."""
-    Js = []
-    for i, p, g in zip(np.asarray(inter).tolist(), np.asarray(n_pred).tolist(), np.asarray(n_gt).tolist()):
-        union = p + g - i
-        Js.append(1.0 if union == 0 else i / union)
+    """evaluator.py:227-237 — mean over frames of inter/union (1.0 for an empty union), numpy float64.  Vectorised: the counts are exact
+    integers < 2**53, so the float64 quotients equal the reference's Python-float divisions, and np.mean sums them in the same order."""
+    i, p, g = (np.asarray(x, dtype=np.int64) for x in (inter, n_pred, n_gt))
+    union = p + g - i
+    with np.errstate(divide="ignore", invalid="ignore"):
+        Js = np.where(union == 0, 1.0, i / np.where(union == 0, 1, union))
     return np.mean(Js)
 
 
@@ -39,19 +40,14 @@ def F_from_counts(inter, n_pred, n_gt) -> float:
 
 
 def F_boundary_from_counts(n_fg, n_gt, fg_match, gt_match) -> float:
-    """DAVIS boundary F per frame, averaged over frames (oracle/boundary_oracle.py is the spec)."""
-    vals = []
-    for a, b, fm, gm in zip(*(np.asarray(x).tolist() for x in (n_fg, n_gt, fg_match, gt_match))):
-        if a == 0 and b > 0:
-            p, r = 1.0, 0.0
-        elif a > 0 and b == 0:
-            p, r = 0.0, 1.0
-        elif a == 0 and b == 0:
-            p, r = 1.0, 1.0
-        else:
-            p, r = fm / float(a), gm / float(b)
-        vals.append(0.0 if p + r == 0 else 2 * p * r / (p + r))
-    return float(np.mean(vals))
+    """DAVIS boundary F per frame, averaged over frames (oracle/boundary_oracle.py is the spec): precision = fg_match / n_fg,
+    recall = gt_match / n_gt with the three empty-boundary rules, F = 2PR / (P + R) (0 when P + R == 0)."""
+    a, b, fm, gm = (np.asarray(x, dtype=np.int64) for x in (n_fg, n_gt, fg_match, gt_match))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        p = np.where(a == 0, 1.0, np.where(b == 0, 0.0, fm / np.where(a == 0, 1, a)))
+        r = np.where(a == 0, np.where(b == 0, 1.0, 0.0), np.where(b == 0, 1.0, gm / np.where(b == 0, 1, b)))
+        f = np.where(p + r == 0, 0.0, 2 * p * r / np.where(p + r == 0, 1.0, p + r))
+    return float(np.mean(f))
 
 
 # ---- per-call drop-ins -----------------------------------------------------------------------------------------
