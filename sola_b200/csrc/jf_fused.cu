@@ -39,7 +39,6 @@ constexpr int JF_MAX_R = 31;
 constexpr int JF_MAX_WP = 256;                 // one walker per word column: W <= 8192
 constexpr int JF_QUEUE = 96;                   // < 32 left over + at most 64 pushed per scan step
 constexpr int JF_PRE_R = 2;                    // radius of the early-exit pre-test
-constexpr int JF_BLK = 4;                      // walker steps per dynamically scheduled block of phase 2
 
 // row pitch of the boundary maps: the Wp words of a row + one zero word each side, made odd so that vertically adjacent items of
 // phase 2 fall into different banks
@@ -203,8 +202,7 @@ __device__ __forceinline__ uint32_t dilate_word(unsigned src, unsigned pitch_byt
 // pred ≈ gt; only the rest go to queue 2 and pay for the full (2r+1)-row dilation, again 32 at a time.
 template <int RAD>
 __device__ __forceinline__ void jf_phase2(unsigned sF, unsigned sG /* shared byte addresses of the two boundary maps */, int BP, int r, int n_steps,
-                                          int mask_steps, const int* __restrict__ o0_tab /* boundary-map offset of every walker at step 0 */,
-                                          int* __restrict__ next_blk, const uint2* __restrict__ masks,
+                                          int my_o0 /* this lane's boundary-map offset at step 0 */, const uint2* __restrict__ masks,
                                           const unsigned char* __restrict__ vtab, uint32_t* __restrict__ q1, uint32_t* __restrict__ q2,
                                           int lane, int& fm, int& gm) {
   constexpr bool PRE = (RAD == 0) || (RAD > JF_PRE_R);        // run-time radii <= 2 take the pre-test too: harmless, it is exact
@@ -243,30 +241,19 @@ __device__ __forceinline__ void jf_phase2(unsigned sF, unsigned sG /* shared byt
     __syncwarp();
     if (n2 >= 32) { n2 -= 32; full_pass(true); }
   };
-  // Work list = phase 1's ballots: masks[W][k] says which walkers of warp W produced a non-zero owned boundary word at step k.
-  // Blocks of JF_BLK consecutive steps of one walker warp are handed out dynamically (one shared counter), so the eight warps stay
-  // balanced however the contours are spread over the tile; consecutive steps are consecutive rows of the same columns, so a batch of
-  // 32 items is a compact patch of the contour and its shared loads spread over the banks (the row pitch BP is odd).
-  const int bps = (n_steps + JF_BLK - 1) / JF_BLK, n_blocks = JF_WARPS * bps;
-  for (;;) {
-    int blk = 0;
-    if (lane == 0) blk = atomicAdd(next_blk, 1);
-    blk = __shfl_sync(FULL, blk, 0);
-    if (blk >= n_blocks) break;
-    const int W = blk / bps, k0 = (blk - W * bps) * JF_BLK, k1 = min(n_steps, k0 + JF_BLK);
-    const uint2* mk = masks + W * mask_steps;
-    const int my_o0 = o0_tab[W * 32 + lane];
-    for (int k = k0; k < k1; ++k) {
-      const uint2 m = mk[k];
-      if ((m.x | m.y) == 0u) continue;
-      const uint32_t o = (uint32_t)(my_o0 + k * BP);
-      if ((m.x >> lane) & 1u) q1[n1 + __popc(m.x & lt)] = o;
-      n1 += __popc(m.x);
-      if ((m.y >> lane) & 1u) q1[n1 + __popc(m.y & lt)] = o | 0x80000000u;
-      n1 += __popc(m.y);
-      __syncwarp();
-      while (n1 >= 32) { n1 -= 32; pre_pass(true); }
-    }
+  // the warp walks the steps of ITS OWN walkers again: masks[k] = which lanes produced a non-zero owned boundary word at step k.
+  // Consecutive steps are consecutive rows of the same columns, so a batch of 32 items is a compact patch of the contour and its
+  // shared loads spread over the banks (the row pitch BP is odd).
+  for (int k = 0; k < n_steps; ++k) {
+    const uint2 m = masks[k];
+    if ((m.x | m.y) == 0u) continue;
+    const uint32_t o = (uint32_t)(my_o0 + k * BP);
+    if ((m.x >> lane) & 1u) q1[n1 + __popc(m.x & lt)] = o;
+    n1 += __popc(m.x);
+    if ((m.y >> lane) & 1u) q1[n1 + __popc(m.y & lt)] = o | 0x80000000u;
+    n1 += __popc(m.y);
+    __syncwarp();
+    while (n1 >= 32) { n1 -= 32; pre_pass(true); }
   }
   if (n1 > 0) { const int n = n1; n1 = 0; pre_pass(lane < n); }
   if (n2 > 0) { const int n = n2; n2 = 0; full_pass(lane < n); }
@@ -286,8 +273,6 @@ jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_
   __shared__ uint32_t queue1[JF_WARPS][JF_QUEUE], queue2[JF_WARPS][64];
   __shared__ int red[7][JF_WARPS];
   __shared__ unsigned char vtab[JF_MAX_R + 1];
-  __shared__ int o0_tab[JF_THREADS];
-  __shared__ int next_blk;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     mbar_init(&bar, 1);
@@ -343,8 +328,6 @@ jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_
       const uint32_t lastbit = (c == Wp - 1) ? (1u << ((g.W - 1) & 31)) : 0u;
       const bool east = c + 1 < Wp;
       my_o0 = j0 * BP + c + 1;
-      o0_tab[tid] = my_o0;
-      if (tid == 0) next_blk = 0;                                    // read after the barrier below; the previous item's phase 2 ended before the barrier above
       // shared byte addresses: row y of the raw tile = ap + (y - ya) * Wp * 4 (dereferenced in-frame only); boundary words at ab
       unsigned ap = smem_u32(rawP) + 4u * (unsigned)(off + (ya - g.ra) * Wp + c);
       const unsigned dPG = 4u * (unsigned)raw_cap, dFG = sG - sF, Wp4 = 4u * Wp, BP4 = 4u * BP;
@@ -396,13 +379,14 @@ jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_
     if (g.r >= 0) {
       uint32_t* q1 = queue1[warp];
       uint32_t* q2 = queue2[warp];
+      const uint2* mk = masks + warp * mask_steps;
       switch (r) {
-        case 6: jf_phase2<6>(sF, sG, BP, r, n_steps, mask_steps, o0_tab, &next_blk, masks, vtab, q1, q2, lane, fm, gm); break;       // 360 x 640
-        case 8: jf_phase2<8>(sF, sG, BP, r, n_steps, mask_steps, o0_tab, &next_blk, masks, vtab, q1, q2, lane, fm, gm); break;       // 480 x 854
-        case 9: jf_phase2<9>(sF, sG, BP, r, n_steps, mask_steps, o0_tab, &next_blk, masks, vtab, q1, q2, lane, fm, gm); break;       // 540 x 960
-        case 12: jf_phase2<12>(sF, sG, BP, r, n_steps, mask_steps, o0_tab, &next_blk, masks, vtab, q1, q2, lane, fm, gm); break;     // 720 x 1280
-        case 18: jf_phase2<18>(sF, sG, BP, r, n_steps, mask_steps, o0_tab, &next_blk, masks, vtab, q1, q2, lane, fm, gm); break;     // 1080 x 1920
-        default: jf_phase2<0>(sF, sG, BP, r, n_steps, mask_steps, o0_tab, &next_blk, masks, vtab, q1, q2, lane, fm, gm); break;
+        case 6: jf_phase2<6>(sF, sG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;       // 360 x 640
+        case 8: jf_phase2<8>(sF, sG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;       // 480 x 854
+        case 9: jf_phase2<9>(sF, sG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;       // 540 x 960
+        case 12: jf_phase2<12>(sF, sG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;     // 720 x 1280
+        case 18: jf_phase2<18>(sF, sG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;     // 1080 x 1920
+        default: jf_phase2<0>(sF, sG, BP, r, n_steps, my_o0, mk, vtab, q1, q2, lane, fm, gm); break;
       }
     }
 
