@@ -780,8 +780,16 @@ def main():
             tj = json.load(f)
             key = "fused_pack_resize_kernel<float>" if fused_flag else "pack_flat_kernel<float, THRESH3>"
             line["roofline"]["traffic"] = tj.get(key, {}).get("dram_bytes_per_launch")
-            if "roofline_jf" in line:
+            if "roofline_jf" in line:       # the ncu target (tools/ncu_targets.py jf_region / jf_boundary) runs rank 0's sweep of this bench
                 line["roofline_jf"]["traffic"] = tj.get("jf_fused_kernel", {}).get("dram_bytes_per_launch")
+                line["roofline_jf_boundary"]["traffic"] = tj.get("jf_fused_kernel[boundary]", {}).get("dram_bytes_per_launch")
+    ncu_path = os.path.join(ROOT, "profiles", "r2_ncu_summary.json")                       # committed `ncu --set full` summaries
+    if os.path.isfile(ncu_path) and "roofline_jf_boundary" in line:
+        with open(ncu_path) as f:
+            cap = json.load(f).get("jf_boundary", {})
+        line["roofline_jf_boundary"]["ncu"] = {k: cap.get(k) for k in ("issue_active_pct", "smem_wavefronts_pct", "pipe_alu_pct", "pipe_xu_pct",
+                                                                         "warp_instructions", "registers", "stalls_per_issue")}
+        line["roofline_jf_boundary"]["binding"] = "instruction issue + shared-memory wavefronts (see ncu block); HBM is the floor, not the bound"
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -48,10 +48,36 @@ def png_planes(masklet: P.PackedMasks) -> np.ndarray:
     return P.unpack_masks(masklet, torch.uint8, one_value=255).cpu().numpy()
 
 
+SIDECAR_SUFFIX = ".packed.npz"
+
+
 def save_packed_masklet(path: str, masklet: P.PackedMasks) -> None:
     """Packed sidecar format: the uint32 planes + shape, 32x smaller than uint8 masks and loadable
     straight into the kernels without an RLE decode."""
     np.savez_compressed(path, words=masklet.numpy_u32(), H=masklet.H, W=masklet.W)
+
+
+def sidecar_path(json_path: str) -> str:
+    """`<id:05d>.json` (the per-track file generate_tokens_grid.py:280 writes) -> `<id:05d>.packed.npz` next to it."""
+    return os.path.splitext(json_path)[0] + SIDECAR_SUFFIX
+
+
+def write_sidecars(masklet_dir: str, device=None) -> int:
+    """Stage-1 side: next to every per-track JSON of a `sam2_masklets/...` directory write the packed sidecar of its RLE masklet, so
+    that stage 2 (AlignDatasetAdapter.get_sam2_masklet) skips the RLE parse.  Returns the number of sidecars written."""
+    from . import rle
+    n = 0
+    for name in sorted(os.listdir(masklet_dir)):
+        if not name.endswith(".json"):
+            continue
+        path = os.path.join(masklet_dir, name)
+        with open(path, "r") as f:
+            info = json.load(f)
+        packed = rle.decode_rle_masklet_packed(info["rle"], device)
+        if packed is not None:
+            save_packed_masklet(sidecar_path(path), packed)
+            n += 1
+    return n
 
 
 def load_packed_masklet(path: str, device=None) -> P.PackedMasks:
@@ -77,7 +103,7 @@ class AlignDatasetAdapter:
     (dataloader.py:260-274, image I/O: out of scope) and ref-ytbvos raises NotImplementedError like the reference."""
 
     def __init__(self, data_name: str, data_type: str, track_root: str, sam2_output_dirs: Sequence[str], meta: dict,
-                 mask_dict: Optional[dict] = None, device=None):
+                 mask_dict: Optional[dict] = None, device=None, use_sidecars: bool = True):
         self.data_name, self.data_type = data_name, data_type
         self.track_root = track_root
         self.sam2_output_dirs = list(sam2_output_dirs)
@@ -86,6 +112,7 @@ class AlignDatasetAdapter:
         self.device = P._dev(device)
         self.video_id = None
         self.cached_gt_masklet: Dict[str, P.PackedMasks] = {}
+        self.use_sidecars = use_sidecars        # prefer `<id>.packed.npz` next to a track's JSON (write_sidecars) over its RLE strings
 
     @classmethod
     def from_dataset(cls, ds, device=None) -> "AlignDatasetAdapter":
@@ -141,7 +168,7 @@ class AlignDatasetAdapter:
                          sam2_anno_ids: list) -> Optional[P.PackedMasks]:
         from . import rle
         preds = np.asarray(preds.cpu() if isinstance(preds, torch.Tensor) else preds)
-        selected, zeros_shape, have_merged = [], None, False
+        selected, selected_packed, zeros_shape, have_merged = [], [], None, False
         sam2_anno_idx = 0
         for sam2_output_dir in self.sam2_output_dirs:
             sam2_output_dir = os.path.join(self.track_root, sam2_output_dir)
@@ -149,7 +176,7 @@ class AlignDatasetAdapter:
                 sam2_masklet_dir = os.path.join(sam2_output_dir, self.data_name, self.data_type, "sam2_masklets", video_id, expression_id)
             else:
                 sam2_masklet_dir = os.path.join(sam2_output_dir, self.data_name, self.data_type, "sam2_masklets", video_id)
-            for sam2_masklet_path in sorted(os.listdir(sam2_masklet_dir)):
+            for sam2_masklet_path in sorted(n for n in os.listdir(sam2_masklet_dir) if not n.endswith(SIDECAR_SUFFIX)):
                 if preds[sam2_anno_idx] < 1 and have_merged:                       # :323-325 — unselected tracks are not even opened
                     sam2_anno_idx += 1
                     continue
@@ -160,14 +187,23 @@ class AlignDatasetAdapter:
                 assert prompt_type == info["prompt_type"], f"Invalid prompt_type: {prompt_type} != {info['prompt_type']}"
                 assert sam2_anno_id == info["anno_id"], f"Invalid sam2_anno_id: {sam2_anno_id} != {info['anno_id']}"
                 if preds[sam2_anno_idx] > 0:                                        # :339-344
-                    selected.append(info["rle"])
+                    side = sidecar_path(os.path.join(sam2_masklet_dir, sam2_masklet_path))
+                    if self.use_sidecars and os.path.isfile(side):                  # packed planes written by stage 1: no RLE parse at all
+                        selected_packed.append(load_packed_masklet(side, self.device))
+                    else:
+                        selected.append(info["rle"])
                 elif not have_merged:                                               # :345-349 — zeros of the first track's shape
                     h, w = info["rle"][0]["size"]
                     zeros_shape = (len(info["rle"]), int(h), int(w))
                 have_merged = True
                 sam2_anno_idx += 1
-        if selected:
-            return rle.decode_rle_masklets_merged(selected, self.device)            # decode + OR-merge of every selected track: one launch
+        if selected or selected_packed:
+            planes = list(selected_packed)
+            if selected:
+                planes.append(rle.decode_rle_masklets_merged(selected, self.device))   # decode + OR-merge of every selected RLE track: one launch
+            if len(planes) == 1:
+                return planes[0]
+            return P.or_merge(P.PackedMasks(torch.stack([p.words for p in planes]), planes[0].H, planes[0].W))
         if zeros_shape is not None:
             t, h, w = zeros_shape
             return P.PackedMasks(torch.zeros((t, h, P.words_per_row(w)), dtype=torch.int32, device=self.device), h, w)

@@ -104,6 +104,26 @@ def test_adapter_matches_reference_golden(tmp_path):
         assert (pred.n_frames, pred.H, pred.W) == tuple(z[f"shape_{k}"].tolist())
         assert np.array_equal(gt.numpy_u32(), z[f"gt_{k}"]), ("gt", k)
         assert np.array_equal(pred.numpy_u32(), z[f"pred_{k}"]), ("pred", k, c["preds"])
+    # packed sidecars: written next to the per-track JSONs by stage 1, consumed here instead of the RLE strings
+    n_side = 0
+    for root, _, names in os.walk(str(tmp_path)):
+        if any(n.endswith(".json") for n in names):
+            n_side += dataloader_ops.write_sidecars(root)
+    assert n_side == len(files)
+    ds_side = dataloader_ops.AlignDatasetAdapter(G.DATA_NAME, G.DATA_TYPE, str(tmp_path), G.SAM2_DIRS, meta, mask_dict)
+    import sola_b200.rle as rle_mod
+    calls = {"n": 0}
+    orig = rle_mod.decode_rle_masklets_merged
+    rle_mod.decode_rle_masklets_merged = lambda *a, **k: (calls.__setitem__("n", calls["n"] + 1), orig(*a, **k))[1]
+    try:
+        for k, c in enumerate(cases):
+            if ds_side.video_id != c["video_id"]:
+                ds_side.set_video(c["video_id"])
+            pred = ds_side.get_sam2_masklet(c["video_id"], c["expression_id"], np.asarray(c["preds"]), c["root_types"], c["prompt_types"], c["sam2_anno_ids"])
+            assert np.array_equal(pred.numpy_u32(), z[f"pred_{k}"]), ("sidecar pred", k)
+    finally:
+        rle_mod.decode_rle_masklets_merged = orig
+    assert calls["n"] == 0, "with sidecars present no RLE string is parsed"
     with pytest.raises(AssertionError):                                          # wrong bookkeeping is an assertion, as in the reference
         ds.get_sam2_masklet("v0", "0", np.ones(5), ["gdino_tracks"] * 5, cases[0]["prompt_types"], cases[0]["sam2_anno_ids"])
     with pytest.raises(NotImplementedError):
