@@ -134,40 +134,49 @@ static int launch_raw_counts(const T* a, const T* b, long long n_frames, long lo
 // ---- packed planes, batched: inter[Na][Nb][T], area_a[Na][T], area_b[Nb][T] ----------------------------------
 constexpr int NB_TILE = 4;
 
+// The kernel is POPC-bound (xu pipe: 16 lanes/clk/SM), so it only counts what is stored: |b| once per (object, frame) — by the
+// CTAs of the first track —, nothing for tile slots past Nb, and |a| once per (track, frame) — by the first object tile.
 template <int VEC>
 __global__ void __launch_bounds__(256)
 packed_counts_kernel(const uint32_t* __restrict__ A, const uint32_t* __restrict__ B, int Na, int Nb, int T, int FW,
                      int* __restrict__ inter, int* __restrict__ area_a, int* __restrict__ area_b) {
   const int t = blockIdx.x % T, ia = blockIdx.x / T;
   const int jb0 = blockIdx.y * NB_TILE;
+  const int nk = min(NB_TILE, Nb - jb0);                 // live object slots of this tile (CTA-uniform)
+  const bool want_b = ia == 0, want_a = blockIdx.y == 0; // CTA-uniform
   const uint32_t* pa = A + ((long long)ia * T + t) * FW;
   const uint32_t* pb[NB_TILE];
 #pragma unroll
   for (int k = 0; k < NB_TILE; ++k) pb[k] = B + ((long long)min(jb0 + k, Nb - 1) * T + t) * FW;
   int acc[NB_TILE] = {0, 0, 0, 0}, accb[NB_TILE] = {0, 0, 0, 0}, acca = 0;
-  if (VEC == 4) {                                  // planes 16-byte aligned, FW % 4 == 0: 128-bit loads, 5 in flight per iteration
+  if (VEC == 4) {                                  // planes 16-byte aligned, FW % 4 == 0: 128-bit loads, up to 5 in flight per iteration
     const int nq = FW >> 2;
     for (int q = threadIdx.x; q < nq; q += blockDim.x) {
       const uint4 x = __ldg(reinterpret_cast<const uint4*>(pa) + q);
       uint4 y[NB_TILE];
 #pragma unroll
-      for (int k = 0; k < NB_TILE; ++k) y[k] = __ldg(reinterpret_cast<const uint4*>(pb[k]) + q);
-      acca += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+      for (int k = 0; k < NB_TILE; ++k)
+        if (k < nk) y[k] = __ldg(reinterpret_cast<const uint4*>(pb[k]) + q);
+      if (want_a) acca += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
 #pragma unroll
       for (int k = 0; k < NB_TILE; ++k) {
-        acc[k] += __popc(x.x & y[k].x) + __popc(x.y & y[k].y) + __popc(x.z & y[k].z) + __popc(x.w & y[k].w);
-        accb[k] += __popc(y[k].x) + __popc(y[k].y) + __popc(y[k].z) + __popc(y[k].w);
+        if (k < nk) {
+          acc[k] += __popc(x.x & y[k].x) + __popc(x.y & y[k].y) + __popc(x.z & y[k].z) + __popc(x.w & y[k].w);
+          if (want_b) accb[k] += __popc(y[k].x) + __popc(y[k].y) + __popc(y[k].z) + __popc(y[k].w);
+        }
       }
     }
   } else {
     for (int w = threadIdx.x; w < FW; w += blockDim.x) {
       const uint32_t x = pa[w];
-      acca += __popc(x);
+      if (want_a) acca += __popc(x);
 #pragma unroll
       for (int k = 0; k < NB_TILE; ++k) {
-        const uint32_t y = pb[k][w];
-        acc[k] += __popc(x & y);
-        accb[k] += __popc(y);
+        if (k < nk) {
+          const uint32_t y = pb[k][w];
+          acc[k] += __popc(x & y);
+          if (want_b) accb[k] += __popc(y);
+        }
       }
     }
   }
