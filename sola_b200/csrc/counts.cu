@@ -135,7 +135,52 @@ static int launch_raw_counts(const T* a, const T* b, long long n_frames, long lo
 constexpr int NB_TILE = 4;
 
 // The kernel is POPC-bound (xu pipe: 16 lanes/clk/SM), so it only counts what is stored: |b| once per (object, frame) — by the
-// CTAs of the first track —, nothing for tile slots past Nb, and |a| once per (track, frame) — by the first object tile.
+// CTAs of the first track —, nothing for tile slots past Nb, and |a| once per (track, frame) — by the first object tile.  The
+// choices are CTA-uniform and COMPILED in (template flags): a predicated-off POPC still occupies the xu pipe (measured: predication
+// alone left the pipe 85 % busy at 7 POPC slots per word instead of 4).
+template <int VEC, int NK, bool WANT_A, bool WANT_B>
+__device__ __forceinline__ void packed_count_loop(const uint32_t* __restrict__ pa, const uint32_t* const (&pb)[NB_TILE], int FW,
+                                                  int& acca, int (&acc)[NB_TILE], int (&accb)[NB_TILE]) {
+  if (VEC == 4) {                                  // planes 16-byte aligned, FW % 4 == 0: 128-bit loads, up to 5 in flight per iteration
+    const int nq = FW >> 2;
+    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+      const uint4 x = __ldg(reinterpret_cast<const uint4*>(pa) + q);
+      uint4 y[NK];
+#pragma unroll
+      for (int k = 0; k < NK; ++k) y[k] = __ldg(reinterpret_cast<const uint4*>(pb[k]) + q);
+      if (WANT_A) acca += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        acc[k] += __popc(x.x & y[k].x) + __popc(x.y & y[k].y) + __popc(x.z & y[k].z) + __popc(x.w & y[k].w);
+        if (WANT_B) accb[k] += __popc(y[k].x) + __popc(y[k].y) + __popc(y[k].z) + __popc(y[k].w);
+      }
+    }
+  } else {
+    for (int w = threadIdx.x; w < FW; w += blockDim.x) {
+      const uint32_t x = pa[w];
+      if (WANT_A) acca += __popc(x);
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const uint32_t y = pb[k][w];
+        acc[k] += __popc(x & y);
+        if (WANT_B) accb[k] += __popc(y);
+      }
+    }
+  }
+}
+
+template <int VEC, int NK>
+__device__ __forceinline__ void packed_count_dispatch(bool want_a, bool want_b, const uint32_t* __restrict__ pa, const uint32_t* const (&pb)[NB_TILE],
+                                                      int FW, int& acca, int (&acc)[NB_TILE], int (&accb)[NB_TILE]) {
+  if (want_a) {
+    if (want_b) packed_count_loop<VEC, NK, true, true>(pa, pb, FW, acca, acc, accb);
+    else packed_count_loop<VEC, NK, true, false>(pa, pb, FW, acca, acc, accb);
+  } else {
+    if (want_b) packed_count_loop<VEC, NK, false, true>(pa, pb, FW, acca, acc, accb);
+    else packed_count_loop<VEC, NK, false, false>(pa, pb, FW, acca, acc, accb);
+  }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(256)
 packed_counts_kernel(const uint32_t* __restrict__ A, const uint32_t* __restrict__ B, int Na, int Nb, int T, int FW,
@@ -149,36 +194,11 @@ packed_counts_kernel(const uint32_t* __restrict__ A, const uint32_t* __restrict_
 #pragma unroll
   for (int k = 0; k < NB_TILE; ++k) pb[k] = B + ((long long)min(jb0 + k, Nb - 1) * T + t) * FW;
   int acc[NB_TILE] = {0, 0, 0, 0}, accb[NB_TILE] = {0, 0, 0, 0}, acca = 0;
-  if (VEC == 4) {                                  // planes 16-byte aligned, FW % 4 == 0: 128-bit loads, up to 5 in flight per iteration
-    const int nq = FW >> 2;
-    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
-      const uint4 x = __ldg(reinterpret_cast<const uint4*>(pa) + q);
-      uint4 y[NB_TILE];
-#pragma unroll
-      for (int k = 0; k < NB_TILE; ++k)
-        if (k < nk) y[k] = __ldg(reinterpret_cast<const uint4*>(pb[k]) + q);
-      if (want_a) acca += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
-#pragma unroll
-      for (int k = 0; k < NB_TILE; ++k) {
-        if (k < nk) {
-          acc[k] += __popc(x.x & y[k].x) + __popc(x.y & y[k].y) + __popc(x.z & y[k].z) + __popc(x.w & y[k].w);
-          if (want_b) accb[k] += __popc(y[k].x) + __popc(y[k].y) + __popc(y[k].z) + __popc(y[k].w);
-        }
-      }
-    }
-  } else {
-    for (int w = threadIdx.x; w < FW; w += blockDim.x) {
-      const uint32_t x = pa[w];
-      if (want_a) acca += __popc(x);
-#pragma unroll
-      for (int k = 0; k < NB_TILE; ++k) {
-        if (k < nk) {
-          const uint32_t y = pb[k][w];
-          acc[k] += __popc(x & y);
-          if (want_b) accb[k] += __popc(y);
-        }
-      }
-    }
+  switch (nk) {
+    case 1: packed_count_dispatch<VEC, 1>(want_a, want_b, pa, pb, FW, acca, acc, accb); break;
+    case 2: packed_count_dispatch<VEC, 2>(want_a, want_b, pa, pb, FW, acca, acc, accb); break;
+    case 3: packed_count_dispatch<VEC, 3>(want_a, want_b, pa, pb, FW, acca, acc, accb); break;
+    default: packed_count_dispatch<VEC, 4>(want_a, want_b, pa, pb, FW, acca, acc, accb); break;
   }
   __shared__ int red[2 * NB_TILE + 1][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

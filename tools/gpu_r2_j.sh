@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out/r2
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2/pytest_gpu.log; tail -3 gpurun_out/r2/pytest_gpu.log
+timeout 900 python bench.py > gpurun_out/r2/bench_1gpu.json 2> gpurun_out/r2/bench_1gpu.err; echo "bench rc=$?"; tail -2 gpurun_out/r2/bench_1gpu.err; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2/bench_1gpu.json').read().strip().splitlines()[-1])
+print('value', d['value'], 'ms', d['ms_per_step'], d['stage_ms']); print('e2e', d['e2e']['value'])
+PY
+cap() { local name=$1 rx=$2 skip=$3; shift 3
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c 1 -o gpurun_out/r2/$name -f "$@" > gpurun_out/r2/$name.log 2>&1; echo "$name rc=$?"; }
+cap labels packed_counts_kernel 3 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-jf
+timeout 400 ncu --nvtx --nvtx-include "timed/" --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2/launches.csv python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-jf > gpurun_out/r2/bench_under_ncu.log 2>&1; echo "launch list rc=$?"
