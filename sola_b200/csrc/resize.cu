@@ -173,36 +173,38 @@ template <bool PACKED_IN>
 __global__ void __launch_bounds__(256)
 resize_nearest_kernel(const void* __restrict__ in_, int H, int W, int oh, int ow, float sy, float sx,
                       uint32_t* __restrict__ out_packed, int* __restrict__ area) {
-  // grid: x = groups of 8 warps over (row groups x word columns) of one output plane, y = plane; 32-bit index math only
+  // grid: x = CTAs of 8 warps striding over the (row group x word column) items of one output plane, y = plane; 32-bit index math
+  // only.  Each warp walks several items: one item per warp made the launch CTA-scheduling-bound (32 k CTAs of ~100 ns of work for
+  // the 64 prompt masks of a video: 62 us for 59 MB).
   const int lane = threadIdx.x & 31;
   const int owp = (ow + 31) >> 5, Wp = (W + 31) >> 5;
   const int row_groups = (oh + NN_ROWS - 1) / NN_ROWS;
-  const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (item >= row_groups * owp) return;
   const long long f = blockIdx.y;
-  const int rg = item / owp, owx = item - rg * owp;
-  const int ox = owx * 32 + lane;
-  const bool live = ox < ow;
-  const int x = nearest_src(live ? ox : 0, sx, W);
-  bool bit[NN_ROWS];
-#pragma unroll
-  for (int k = 0; k < NN_ROWS; ++k) {
-    const int oy = rg * NN_ROWS + k;
-    bit[k] = false;
-    if (live && oy < oh) {
-      const int y = nearest_src(oy, sy, H);
-      if (PACKED_IN) bit[k] = get_bit(reinterpret_cast<const uint32_t*>(in_) + (f * H + y) * Wp, x) != 0u;
-      else bit[k] = __ldg(reinterpret_cast<const uint8_t*>(in_) + (f * H + y) * W + x) != 0;
-    }
-  }
   int pop = 0;
+  for (int item = blockIdx.x * 8 + (threadIdx.x >> 5); item < row_groups * owp; item += gridDim.x * 8) {
+    const int rg = item / owp, owx = item - rg * owp;
+    const int ox = owx * 32 + lane;
+    const bool live = ox < ow;
+    const int x = nearest_src(live ? ox : 0, sx, W);
+    bool bit[NN_ROWS];
 #pragma unroll
-  for (int k = 0; k < NN_ROWS; ++k) {
-    const int oy = rg * NN_ROWS + k;
-    const uint32_t word = __ballot_sync(FULL, bit[k]);
-    if (lane == 0 && oy < oh) {
-      out_packed[f * (long long)(oh * owp) + oy * owp + owx] = word;
-      pop += __popc(word);
+    for (int k = 0; k < NN_ROWS; ++k) {
+      const int oy = rg * NN_ROWS + k;
+      bit[k] = false;
+      if (live && oy < oh) {
+        const int y = nearest_src(oy, sy, H);
+        if (PACKED_IN) bit[k] = get_bit(reinterpret_cast<const uint32_t*>(in_) + (f * H + y) * Wp, x) != 0u;
+        else bit[k] = __ldg(reinterpret_cast<const uint8_t*>(in_) + (f * H + y) * W + x) != 0;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NN_ROWS; ++k) {
+      const int oy = rg * NN_ROWS + k;
+      const uint32_t word = __ballot_sync(FULL, bit[k]);
+      if (lane == 0 && oy < oh) {
+        out_packed[f * (long long)(oh * owp) + oy * owp + owx] = word;
+        pop += __popc(word);
+      }
     }
   }
   if (lane == 0 && area && pop) atomicAdd(area + f, pop);
@@ -212,9 +214,12 @@ template <bool PACKED_IN>
 static int launch_nearest(const void* in, long long n_frames, int H, int W, int oh, int ow, uint32_t* out_packed, int* area, cudaStream_t stream) {
   const int owp = (ow + 31) >> 5;
   const float sy = (float)H / (float)oh, sx = (float)W / (float)ow;
-  const unsigned gx = (unsigned)((((oh + NN_ROWS - 1) / NN_ROWS) * owp + 7) / 8);
+  const long long gx_all = (((oh + NN_ROWS - 1) / NN_ROWS) * (long long)owp + 7) / 8;       // one item per warp
   for (long long f0 = 0; f0 < n_frames; f0 += 65535) {
     const long long nf = n_frames - f0 < 65535 ? n_frames - f0 : 65535;
+    long long gx_cap = ((long long)num_sms() * 16 + nf - 1) / nf;                             // ~16 CTAs per SM over the whole grid
+    if (gx_cap < 1) gx_cap = 1;
+    const unsigned gx = (unsigned)(gx_all < gx_cap ? gx_all : gx_cap);
     const char* src = reinterpret_cast<const char*>(in) + (PACKED_IN ? f0 * H * ((W + 31) >> 5) * 4 : f0 * H * (long long)W);
     resize_nearest_kernel<PACKED_IN><<<dim3(gx, (unsigned)nf), 256, 0, stream>>>(src, H, W, oh, ow, sy, sx, out_packed + f0 * oh * owp,
                                                                                 area ? area + f0 : nullptr);
