@@ -259,7 +259,8 @@ __device__ __forceinline__ void jf_phase2(unsigned sF, unsigned sG /* shared byt
   if (n2 > 0) { const int n = n2; n2 = 0; full_pass(lane < n); }
 }
 
-__global__ void __launch_bounds__(JF_THREADS, 2)
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(JF_THREADS, MIN_CTAS)
 jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_jf_unit single, long long n_items, int raw_cap,
                 int bm_cap, int mask_steps, int* __restrict__ counts, long long total_frames) {
   extern __shared__ __align__(16) uint32_t jf_smem[];
@@ -431,8 +432,13 @@ static int jf_max_band_rows(int H, int Wp, int r, bool boundary, size_t budget) 
   return lo;
 }
 
-constexpr size_t JF_BUDGET_2CTA = 100 * 1024;     // two resident CTAs per SM: one loads / walks while the other dilates
-constexpr size_t JF_BUDGET_1CTA = 200 * 1024;     // tall halos (1080p: r = 18): fewer, taller bands beat occupancy
+// Tile budgets by resident CTAs per SM.  More CTAs hide the latency-bound phases better, fewer allow taller bands (less halo
+// redundancy).  The 3-CTA build is capped at 80 registers (no spills), the others take 128.
+constexpr int JF_FIRST_CLASS = 1;                 // 0: try the 3-CTA class first; 1: start at 2 CTAs per SM
+constexpr int JF_MAX_HALO_PCT = 30;
+constexpr size_t JF_BUDGET_3CTA = 72 * 1024;
+constexpr size_t JF_BUDGET_2CTA = 100 * 1024;
+constexpr size_t JF_BUDGET_1CTA = 200 * 1024;     // tall halos (1080p: r = 18)
 
 extern "C" {
 typedef struct sola_jf_plan {
@@ -441,10 +447,15 @@ typedef struct sola_jf_plan {
 } sola_jf_plan;
 }
 
-static int jf_plan(sola_jf_unit* units, int n_units, sola_jf_plan* plan) {
-  // one budget for the whole launch: the small one unless some unit would then spend > 30 % of its rows on halo
-  size_t budget = JF_BUDGET_2CTA;
-  for (int pass = 0; pass < 2; ++pass) {
+static int jf_plan(sola_jf_unit* units, int n_units, sola_jf_plan* plan, int force_ctas = 0) {
+  // one budget for the whole launch: the smallest class whose bands do not spend more than JF_MAX_HALO_PCT of their rows on halo
+  // (force_ctas = 1 / 2 / 3 pins the class: experiments, tools/jf_fused_bench.py)
+  const size_t budgets[3] = {JF_BUDGET_3CTA, JF_BUDGET_2CTA, JF_BUDGET_1CTA};
+  const int ctas[3] = {3, 2, 1};
+  int first = JF_FIRST_CLASS, last = 2;
+  if (force_ctas >= 1 && force_ctas <= 3) first = last = 3 - force_ctas;
+  for (int cls = first; cls <= last; ++cls) {
+    const size_t budget = budgets[cls];
     bool retry = false;
     long long items = 0, frames = 0;
     int raw_cap = 4, bm_cap = 0, steps = 0;
@@ -460,14 +471,14 @@ static int jf_plan(sola_jf_unit* units, int n_units, sola_jf_plan* plan) {
       }
       const int bmax = jf_max_band_rows(u.H, Wp, u.radius, boundary, budget);
       if (bmax < 1) {
-        if (pass == 0) { retry = true; break; }
+        if (cls < last) { retry = true; break; }
         set_error("jf_sweep: unit %d (%dx%d, radius %d) does not fit shared memory", i, u.H, u.W, u.radius);
         return SOLA_ERR_UNSUPPORTED;
       }
       u.n_bands = (u.H + bmax - 1) / bmax;
       u.band_rows = (u.H + u.n_bands - 1) / u.n_bands;
       u.n_bands = (u.H + u.band_rows - 1) / u.band_rows;
-      if (pass == 0 && boundary && u.n_bands > 1 && (2 * u.radius + 1) * 10 > 3 * u.band_rows) { retry = true; break; }
+      if (cls < last && boundary && u.n_bands > 1 && (2 * u.radius + 1) * 100 > JF_MAX_HALO_PCT * u.band_rows) { retry = true; break; }
       u.item0 = items;
       u.out_off = frames;
       items += (long long)u.T * u.n_bands;
@@ -478,9 +489,9 @@ static int jf_plan(sola_jf_unit* units, int n_units, sola_jf_plan* plan) {
       if (bc > bm_cap) bm_cap = bc;
       if (st > steps) steps = st;
     }
-    if (retry) { budget = JF_BUDGET_1CTA; continue; }
+    if (retry) continue;
     plan->n_items = items; plan->total_frames = frames; plan->raw_cap = raw_cap; plan->bm_cap = bm_cap; plan->mask_steps = steps;
-    plan->reserved = 0;
+    plan->reserved = ctas[cls];
     return SOLA_OK;
   }
   return SOLA_ERR_UNSUPPORTED;
@@ -495,15 +506,19 @@ static int jf_launch(const sola_jf_unit* units_dev, int n_units, const sola_jf_u
   const size_t smem = (size_t)(2 * p.raw_cap + 2 * p.bm_cap + 2 * JF_WARPS * p.mask_steps) * sizeof(uint32_t);
   SOLA_REQUIRE(p.raw_cap > 0 && p.raw_cap % 4 == 0 && p.bm_cap >= 0 && p.bm_cap % 2 == 0 && p.mask_steps >= 0 && smem <= 220 * 1024,
                "jf_sweep: bad shared-memory plan (raw_cap %d, bm_cap %d, mask_steps %d)", p.raw_cap, p.bm_cap, p.mask_steps);
-  SOLA_CUDA(cudaFuncSetAttribute(jf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jf_fused_kernel, JF_THREADS, smem);
-  if (occ < 1) occ = 1;
-  long long grid = (long long)num_sms() * occ;
-  if (grid > p.n_items) grid = p.n_items;
-  jf_fused_kernel<<<(unsigned)grid, JF_THREADS, smem, stream>>>(units_dev, n_units, single, p.n_items, p.raw_cap, p.bm_cap, p.mask_steps,
-                                                                counts_out, p.total_frames);
-  return check_launch("jf_fused kernel");
+  auto launch = [&](auto kernel) -> int {
+    SOLA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, JF_THREADS, smem);
+    if (occ < 1) occ = 1;
+    long long grid = (long long)num_sms() * occ;
+    if (grid > p.n_items) grid = p.n_items;
+    kernel<<<(unsigned)grid, JF_THREADS, smem, stream>>>(units_dev, n_units, single, p.n_items, p.raw_cap, p.bm_cap, p.mask_steps, counts_out,
+                                                         p.total_frames);
+    return check_launch("jf_fused kernel");
+  };
+  // the plan's tile class decides the build: 3 CTAs per SM need the 80-register build
+  return p.reserved == 3 ? launch(jf_fused_kernel<3>) : launch(jf_fused_kernel<2>);
 }
 
 }  // namespace sola
@@ -518,7 +533,7 @@ int sola_jf_sweep_plan(sola_jf_unit* units_host, int n_units, sola_jf_plan* plan
   SOLA_REQUIRE(plan_out, "jf_sweep_plan: null output");
   sola_jf_plan p{0, 0, 4, 0, 0, 0};
   if (n_units > 0) {
-    const int rc = jf_plan(units_host, n_units, &p);
+    const int rc = jf_plan(units_host, n_units, &p, plan_out->reserved);     // reserved on input: 0 = automatic tile class
     if (rc != SOLA_OK) return rc;
   }
   *plan_out = p;

@@ -533,7 +533,7 @@ assert _C.sizeof(JfUnit) == 64 and _C.sizeof(JfPlan) == 32
 class _JFLaunch:
     """One planned launch of the fused kernel over a list of (pred words, gt words, T, H, W, radius) units."""
 
-    def __init__(self, units, device):
+    def __init__(self, units, device, ctas_per_sm: int = 0):
         n = len(units)
         arr = (JfUnit * max(n, 1))()
         for k, (pw, gw, T, H, W, radius) in enumerate(units):
@@ -541,6 +541,7 @@ class _JFLaunch:
             u.pred, u.gt, u.T, u.H, u.W, u.radius = pw.data_ptr(), gw.data_ptr(), T, H, W, radius
         self.n_units, self.device = n, device
         self.plan = JfPlan()
+        self.plan.reserved = int(ctas_per_sm)                  # 0 = let the library pick the tile class
         _lib.call("sola_jf_sweep_plan", _C.cast(arr, _C.c_void_p), n, _C.byref(self.plan))
         self.offsets = [arr[k].out_off for k in range(n)]
         self.bands = [(arr[k].band_rows, arr[k].n_bands) for k in range(n)]
@@ -569,7 +570,8 @@ class JFSweepPlan:
     video does not halve the occupancy of every other unit — at most two launches per sweep.
     The plan keeps references to the planes; run() may be called repeatedly (the bench times it)."""
 
-    def __init__(self, pairs: Sequence[Tuple["PackedMasks", "PackedMasks"]], with_boundary: bool = True, bound_th: float = 0.008):
+    def __init__(self, pairs: Sequence[Tuple["PackedMasks", "PackedMasks"]], with_boundary: bool = True, bound_th: float = 0.008,
+                 ctas_per_sm: int = 0):
         self.pairs, self.device = [], None
         units = []
         for p, g in pairs:
@@ -593,7 +595,7 @@ class JFSweepPlan:
         for group in (small, big):
             if not group:
                 continue
-            L = _JFLaunch([units[k] for k in group], self.device)
+            L = _JFLaunch([units[k] for k in group], self.device, ctas_per_sm)
             for j, k in enumerate(group):
                 self.offsets[k] = base + L.offsets[j]
             self.launches.append((L, base))

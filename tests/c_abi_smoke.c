@@ -89,7 +89,7 @@ int main(void) {
     CK(cudaMalloc((void**)&packed_b, (size_t)n * H * Wp * 4));
     rc = sola_threshold_pack_f32(d, n, H, W, 0.5, packed_b, NULL, 0);
     if (rc) { printf("sola_threshold_pack_f32: %s\n", sola_last_error_string()); return 1; }
-    memset(&unit, 0, sizeof(unit));
+    memset(&unit, 0, sizeof(unit)); memset(&plan, 0, sizeof(plan));      /* plan.reserved = 0: automatic tile class */
     unit.pred = packed; unit.gt = packed_b; unit.T = n; unit.H = H; unit.W = W; unit.radius = 2;
     if (sizeof(sola_jf_unit) != 64) { printf("sola_jf_unit is %zu bytes\n", sizeof(sola_jf_unit)); return 1; }
     rc = sola_jf_sweep_plan(&unit, 1, &plan);

@@ -38,6 +38,14 @@ for name, (T, H, W) in {"480x854": (4096, 480, 854), "720x1280": (2560, 720, 128
             ms = timed(lambda: plan.run(buf), reps=5 if speckle else 20)
             out[f"{name}/{kind}/{'J+F+boundary' if wb else 'J+F'}"] = {"ms": ms, "GBps": nbytes / ms / 1e6, "frames_per_s": T / ms * 1e3,
                                                                       "bands": plan.bands[0], "smem": plan.smem_bytes}
+        for occ in (3, 2, 1):                                   # forced tile class (CTAs per SM) in boundary mode
+            try:
+                plan = P.JFSweepPlan([(pp, gp)], with_boundary=True, ctas_per_sm=occ)
+                buf = torch.empty((7, plan.total_frames), dtype=torch.int32, device="cuda")
+                ms = timed(lambda: plan.run(buf), reps=5 if speckle else 20)
+                out[f"{name}/{kind}/J+F+boundary/ctas{occ}"] = {"ms": ms, "frames_per_s": T / ms * 1e3, "bands": plan.bands[0], "smem": plan.smem_bytes}
+            except Exception as ex:
+                out[f"{name}/{kind}/J+F+boundary/ctas{occ}"] = {"error": repr(ex)[:120]}
         if kind == "object":
             ms = timed(lambda: S.frame_counts_packed(pp.reshape_lead(1, T), gp.reshape_lead(1, T)), reps=20)
             out[f"{name}/object/old_K3_packed_counts"] = {"ms": ms, "GBps": nbytes / ms / 1e6}
@@ -46,6 +54,11 @@ units = synth.mevis_like_sweep(6 if quick else 24, 4, 1238, "cuda", t_range=(30,
 plan = P.JFSweepPlan([(p, g) for _, _, p, g in units], with_boundary=True)
 buf = torch.empty((7, plan.total_frames), dtype=torch.int32, device="cuda")
 ms = timed(lambda: plan.run(buf), reps=10)
+for occ in (3, 2):
+    pl = P.JFSweepPlan([(p, g) for _, _, p, g in units], with_boundary=True, ctas_per_sm=occ)
+    b2 = torch.empty((7, pl.total_frames), dtype=torch.int32, device="cuda")
+    m2 = timed(lambda: pl.run(b2), reps=10)
+    out[f"mevis_like_sweep/J+F+boundary/ctas{occ}"] = {"ms": m2, "frames_per_s": pl.total_frames / m2 * 1e3, "launches": len(pl.launches)}
 out["mevis_like_sweep/J+F+boundary"] = {"ms": ms, "GBps": plan.algorithmic_bytes / ms / 1e6, "frames_per_s": plan.total_frames / ms * 1e3,
                                         "units": plan.n_units, "frames": plan.total_frames, "items": plan.n_items}
 print(json.dumps(out, indent=1))
