@@ -406,8 +406,7 @@ def cpu_baseline_sample(n_tracks, n_frames):
 def jf_region(device, rank, world, reps, peak):
     """Two passes over the same config-4-shaped sweep: (1) J + F exactly as the reference defines them (evaluator.py:227-247: region
     counts only — HBM bound), (2) the same plus the north-star's boundary F (seg2bmap + disk dilation + match counting — integer /
-    shared-memory bound).  Each pass is one launch of the fused kernel per sweep (two in boundary mode when the sweep mixes
-    1080p-class tiles, which need a whole SM's shared memory, with smaller ones)."""
+    shared-memory bound).  Each pass is ONE launch of the fused kernel per sweep."""
     import torch.distributed as dist
     import sola_b200 as S
     from oracle import boundary_oracle as BO
@@ -782,9 +781,7 @@ def main():
             line["roofline"]["traffic"] = tj.get(key, {}).get("dram_bytes_per_launch")
             if "roofline_jf" in line:       # the ncu target (tools/ncu_targets.py jf_region / jf_boundary) runs rank 0's sweep of this bench
                 line["roofline_jf"]["traffic"] = tj.get("jf_fused_kernel", {}).get("dram_bytes_per_launch")
-                # boundary mode splits this mixed sweep into two launches (tile classes); the committed capture holds one of them, so
-                # no per-sweep DRAM figure is quoted for it (the region-mode capture already shows traffic == algorithmic bytes)
-                line["roofline_jf_boundary"]["traffic"] = None
+                line["roofline_jf_boundary"]["traffic"] = tj.get("jf_fused_kernel[boundary]", {}).get("dram_bytes_per_launch")
     ncu_path = os.path.join(ROOT, "profiles", "r2_ncu_summary.json")                       # committed `ncu --set full` summaries
     if os.path.isfile(ncu_path) and "roofline_jf_boundary" in line:
         with open(ncu_path) as f:

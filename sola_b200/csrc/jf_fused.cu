@@ -433,9 +433,8 @@ static int jf_max_band_rows(int H, int Wp, int r, bool boundary, size_t budget) 
 }
 
 // Tile budgets by resident CTAs per SM.  More CTAs hide the latency-bound phases better, fewer allow taller bands (less halo
-// redundancy).  The 3-CTA build is capped at 80 registers (no spills), the others take 128.
+// redundancy).  The 3-CTA build is capped at 80 registers (no spills), the other takes 128.
 constexpr int JF_FIRST_CLASS = 1;                 // 0: try the 3-CTA class first; 1: start at 2 CTAs per SM
-constexpr int JF_MAX_HALO_PCT = 30;
 constexpr size_t JF_BUDGET_3CTA = 72 * 1024;
 constexpr size_t JF_BUDGET_2CTA = 100 * 1024;
 constexpr size_t JF_BUDGET_1CTA = 200 * 1024;     // tall halos (1080p: r = 18)
@@ -448,7 +447,9 @@ typedef struct sola_jf_plan {
 }
 
 static int jf_plan(sola_jf_unit* units, int n_units, sola_jf_plan* plan, int force_ctas = 0) {
-  // one budget for the whole launch: the smallest class whose bands do not spend more than JF_MAX_HALO_PCT of their rows on halo
+  // one budget for the whole launch: two CTAs per SM unless a unit's tile does not fit, then one.  Measured (profiles/
+  // r2_jf_fused_bench.json): two resident CTAs beat one even at 1080p, where the 100 KB tile spends 37 of 101 rows on halo (1.20 M vs
+  // 1.05 M frame pairs/s); bands for three CTAs lose everywhere except where the 2-CTA tile already fits three times (360p).
   // (force_ctas = 1 / 2 / 3 pins the class: experiments, tools/jf_fused_bench.py)
   const size_t budgets[3] = {JF_BUDGET_3CTA, JF_BUDGET_2CTA, JF_BUDGET_1CTA};
   const int ctas[3] = {3, 2, 1};
@@ -478,7 +479,6 @@ static int jf_plan(sola_jf_unit* units, int n_units, sola_jf_plan* plan, int for
       u.n_bands = (u.H + bmax - 1) / bmax;
       u.band_rows = (u.H + u.n_bands - 1) / u.n_bands;
       u.n_bands = (u.H + u.band_rows - 1) / u.band_rows;
-      if (cls < last && boundary && u.n_bands > 1 && (2 * u.radius + 1) * 100 > JF_MAX_HALO_PCT * u.band_rows) { retry = true; break; }
       u.item0 = items;
       u.out_off = frames;
       items += (long long)u.T * u.n_bands;
@@ -492,6 +492,8 @@ static int jf_plan(sola_jf_unit* units, int n_units, sola_jf_plan* plan, int for
     if (retry) continue;
     plan->n_items = items; plan->total_frames = frames; plan->raw_cap = raw_cap; plan->bm_cap = bm_cap; plan->mask_steps = steps;
     plan->reserved = ctas[cls];
+    // small frames: the 2-CTA plan's tile already leaves room for a third CTA — take the 80-register build so that it can be resident
+    if (force_ctas == 0 && cls == 1 && (size_t)(2 * raw_cap + 2 * bm_cap + 2 * JF_WARPS * steps) * sizeof(uint32_t) <= JF_BUDGET_3CTA) plan->reserved = 3;
     return SOLA_OK;
   }
   return SOLA_ERR_UNSUPPORTED;

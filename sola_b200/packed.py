@@ -565,9 +565,9 @@ class JFSweepPlan:
         plan = JFSweepPlan([(pred0, gt0), (pred1, gt1), ...], with_boundary=True)      # PackedMasks pairs, (T_u, H_u, Wp_u) each
         counts = plan.run()          # int32 (7, total_frames) on the device; plan.offsets[u] = first column of unit u, plan.frames[u] columns
 
-    All units go into ONE launch, unless the sweep mixes frames whose tile needs the whole SM's shared memory (1080p-class with the
-    boundary disk: one CTA per SM) with smaller ones (two CTAs per SM): those two classes are launched separately so that one large
-    video does not halve the occupancy of every other unit — at most two launches per sweep.
+    All units go into ONE launch (frames up to 1080p with the DAVIS disk fit the two-CTAs-per-SM tile).  Only frames whose tile needs a
+    whole SM's shared memory (beyond ~1080p) form a second class, launched separately so that they do not halve the occupancy of every
+    other unit — at most two launches per sweep.
     The plan keeps references to the planes; run() may be called repeatedly (the bench times it)."""
 
     def __init__(self, pairs: Sequence[Tuple["PackedMasks", "PackedMasks"]], with_boundary: bool = True, bound_th: float = 0.008,

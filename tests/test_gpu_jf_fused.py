@@ -106,9 +106,9 @@ def test_fused_mixed_shape_sweep_one_launch():
     plan = P.JFSweepPlan([(S.pack_masks(p), S.pack_masks(g)) for p, g in units], with_boundary=True)
     base = S.launch_count()
     counts = plan.run().cpu().numpy()
-    assert S.launch_count() - base == len(plan.launches) == 2, "two tile classes (1080p + smaller) -> two launches, never one per unit"
-    small_only = P.JFSweepPlan([(S.pack_masks(p), S.pack_masks(g)) for (p, g), sh in zip(units, shapes) if sh[1] < 1080], with_boundary=True)
-    assert len(small_only.launches) == 1
+    assert S.launch_count() - base == len(plan.launches) == 1, "the whole mixed-shape sweep must be one kernel launch"
+    forced = P.JFSweepPlan([(S.pack_masks(p), S.pack_masks(g)) for p, g in units], with_boundary=True, ctas_per_sm=3)     # other tile class, same counts
+    assert np.array_equal(forced.run().cpu().numpy(), counts)
     assert counts.shape == (7, sum(s[0] for s in shapes))
     for k, (p, g) in enumerate(units):
         o, T = plan.offsets[k], plan.frames[k]
