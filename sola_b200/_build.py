@@ -30,6 +30,11 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
 
 
+def _extra_flags():
+    """Build-time experiment hook (tools only): extra nvcc flags, e.g. SOLA_EXTRA_NVCC_FLAGS="-DJF_PRE_R=3".  Part of the digest."""
+    return os.environ.get("SOLA_EXTRA_NVCC_FLAGS", "").split()
+
+
 def _source_digest() -> str:
     h = hashlib.sha256()
     for name in sorted(os.listdir(CSRC)):
@@ -37,7 +42,7 @@ def _source_digest() -> str:
             with open(os.path.join(CSRC, name), "rb") as f:
                 h.update(name.encode())
                 h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + _extra_flags()).encode())
     return h.hexdigest()
 
 
@@ -68,7 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             tmp = LIB_PATH + f".tmp{os.getpid()}"
             # the digest of the sources is compiled in (sola_build_digest()), so the loader can tell a stale library from a current one
             # even when the stamp file did not travel with it
-            cmd = [_nvcc(), *NVCC_FLAGS, f'-DSOLA_SOURCE_DIGEST="{_source_digest()}"', "-I", CSRC, "-o", tmp, *srcs]
+            cmd = [_nvcc(), *NVCC_FLAGS, *_extra_flags(), f'-DSOLA_SOURCE_DIGEST="{_source_digest()}"', "-I", CSRC, "-o", tmp, *srcs]
             if verbose:
                 cmd.insert(1, "-Xptxas")
                 cmd.insert(2, "-v")

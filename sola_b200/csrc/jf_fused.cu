@@ -38,7 +38,10 @@ constexpr int JF_WARPS = JF_THREADS / 32;
 constexpr int JF_MAX_R = 31;
 constexpr int JF_MAX_WP = 256;                 // one walker per word column: W <= 8192
 constexpr int JF_QUEUE = 96;                   // < 32 left over + at most 64 pushed per scan step
-constexpr int JF_PRE_R = 2;                    // radius of the early-exit pre-test
+#ifndef JF_PRE_R_VALUE
+#define JF_PRE_R_VALUE 2
+#endif
+constexpr int JF_PRE_R = JF_PRE_R_VALUE;       // radius of the early-exit pre-test (2: measured against 3 and 4, tools/gpu_r2_o.sh)
 
 // row pitch of the boundary maps: the Wp words of a row + one zero word each side, made odd so that vertically adjacent items of
 // phase 2 fall into different banks

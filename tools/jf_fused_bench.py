@@ -27,6 +27,7 @@ def unit_batch(T, H, W, seed, speckle, chunk=64):
 
 out = {}
 quick = "--quick" in sys.argv
+only_auto = "--auto-only" in sys.argv
 for name, (T, H, W) in {"480x854": (4096, 480, 854), "720x1280": (2560, 720, 1280), "1080x1920": (1024, 1080, 1920), "360x640": (4096, 360, 640)}.items():
     if quick: T //= 8
     for kind, speckle in (("object", 0.0), ("speckle2pct", 0.02)):
@@ -38,7 +39,7 @@ for name, (T, H, W) in {"480x854": (4096, 480, 854), "720x1280": (2560, 720, 128
             ms = timed(lambda: plan.run(buf), reps=5 if speckle else 20)
             out[f"{name}/{kind}/{'J+F+boundary' if wb else 'J+F'}"] = {"ms": ms, "GBps": nbytes / ms / 1e6, "frames_per_s": T / ms * 1e3,
                                                                       "bands": plan.bands[0], "smem": plan.smem_bytes}
-        for occ in (3, 2, 1):                                   # forced tile class (CTAs per SM) in boundary mode
+        for occ in (() if only_auto else (3, 2, 1)):                # forced tile class (CTAs per SM) in boundary mode
             try:
                 plan = P.JFSweepPlan([(pp, gp)], with_boundary=True, ctas_per_sm=occ)
                 buf = torch.empty((7, plan.total_frames), dtype=torch.int32, device="cuda")
@@ -54,7 +55,7 @@ units = synth.mevis_like_sweep(6 if quick else 24, 4, 1238, "cuda", t_range=(30,
 plan = P.JFSweepPlan([(p, g) for _, _, p, g in units], with_boundary=True)
 buf = torch.empty((7, plan.total_frames), dtype=torch.int32, device="cuda")
 ms = timed(lambda: plan.run(buf), reps=10)
-for occ in (3, 2):
+for occ in (() if only_auto else (3, 2)):
     pl = P.JFSweepPlan([(p, g) for _, _, p, g in units], with_boundary=True, ctas_per_sm=occ)
     b2 = torch.empty((7, pl.total_frames), dtype=torch.int32, device="cuda")
     m2 = timed(lambda: pl.run(b2), reps=10)
