@@ -24,8 +24,8 @@
 //            scans the owned words, compacts the non-zero ones into a per-warp queue (ballot) and dilates ONLY those, 32 items per
 //            pass with all lanes busy.  The disk is decomposed by column offset k: dil = OR_k shift(±k)(vertical OR of half-height
 //            v[k]); walking k from r down to 0 the vertical extent only grows, so an item costs 6r shared loads + 3r LOP3 for
-//            the running ORs and 2 funnel shifts + 1 LOP3 per k.  Items whose pixels all match inside a radius-2 disk (the common
-//            case when pred ≈ gt) stop after 5 rows.
+//            the running ORs and 2 funnel shifts + 1 LOP3 per k.  Items whose pixels all match inside a radius-3 disk (the common
+//            case when pred ≈ gt) stop after 7 rows.
 // Everything is exact integer arithmetic; pad bits (x >= W) stay zero through every step.
 #include "tma.cuh"
 #include "jf_unit.h"
@@ -39,9 +39,10 @@ constexpr int JF_MAX_R = 31;
 constexpr int JF_MAX_WP = 256;                 // one walker per word column: W <= 8192
 constexpr int JF_QUEUE = 96;                   // < 32 left over + at most 64 pushed per scan step
 #ifndef JF_PRE_R_VALUE
-#define JF_PRE_R_VALUE 2
+#define JF_PRE_R_VALUE 3
 #endif
-constexpr int JF_PRE_R = JF_PRE_R_VALUE;       // radius of the early-exit pre-test (2: measured against 3 and 4, tools/gpu_r2_o.sh)
+constexpr int JF_PRE_R = JF_PRE_R_VALUE;       // radius of the early-exit pre-test.  Measured 2 / 3 / 4 (profiles/r2_jf_pretest_radius_experiment.json):
+                                               // object-like pairs gain 2-6 % with the larger radii, speckled ones lose 2-10 %; 3 is the compromise
 
 // row pitch of the boundary maps: the Wp words of a row + one zero word each side, made odd so that vertically adjacent items of
 // phase 2 fall into different banks
@@ -124,7 +125,7 @@ __device__ __forceinline__ void jf_issue_load(const JfGeo& g, uint32_t* rawP, ui
 // dil(word) = OR_k shift(±k)( OR of rows within ±v[k] ), v[k] = floor(sqrt(r^2 - k^2)).  Walking k from r down to 0 the vertical extent
 // only grows, so three running words (left / centre / right column) are kept and each extra row pair costs 6 shared loads + 3 LOP3;
 // each k costs 2 funnel shifts + 1 LOP3.  For the radii of the usual frame sizes (360p .. 1080p: 6, 8, 9, 12, 18) and for the
-// radius-2 pre-test the whole walk is unrolled at compile time (no loop control, no table reads, constant shift amounts).
+// radius-3 pre-test the whole walk is unrolled at compile time (no loop control, no table reads, constant shift amounts).
 __host__ __device__ constexpr int jf_isqrt(int x) {
   int v = 0;
   while ((v + 1) * (v + 1) <= x) ++v;
@@ -200,8 +201,8 @@ __device__ __forceinline__ uint32_t dilate_word(unsigned src, unsigned pitch_byt
 }
 
 // ---- phase 2: match counting over the owned rows of one item --------------------------------------------------------------------
-// Two-level compaction keeps the lanes busy: non-zero boundary words -> queue 1; a radius-2 pre-test (5 rows; a subset of the real
-// disk, so a pixel it matches IS matched) settles the words whose pixels all have a partner within 2 px — nearly all of them when
+// Two-level compaction keeps the lanes busy: non-zero boundary words -> queue 1; a radius-3 pre-test (7 rows; a subset of the real
+// disk, so a pixel it matches IS matched) settles the words whose pixels all have a partner within 3 px — nearly all of them when
 // pred ≈ gt; only the rest go to queue 2 and pay for the full (2r+1)-row dilation, again 32 at a time.
 template <int RAD>
 __device__ __forceinline__ void jf_phase2(unsigned sF, unsigned sG /* shared byte addresses of the two boundary maps */, int BP, int r, int n_steps,

@@ -202,3 +202,20 @@ def test_jf_accumulators_abi(shape):
     z = torch.zeros((4, 20, 40), dtype=torch.uint8, device="cuda")
     inter, uni, tot = S.packed.jf_accumulators(z, z)
     assert evaluator.jf_from_accumulators(inter, uni, tot) == (1.0, 0.0) and tot.cpu().tolist() == [0, 0, 0]
+
+
+def test_compute_J_then_compute_F_share_one_pass():
+    """evaluator.py:201-202 calls compute_J and compute_F on the same tensors: one kernel launch, and any in-place edit invalidates."""
+    import sola_b200 as S
+    from sola_b200 import evaluator, synth
+    p, g = synth.jf_pair(5, 40, 70, seed=2, device="cuda")
+    pf, gf = p.float(), g.float()
+    n0 = S.launch_count()
+    J = evaluator.compute_J(pf, gf)
+    n1 = S.launch_count()
+    F = evaluator.compute_F(pf, gf)
+    assert S.launch_count() == n1 and n1 > n0
+    assert J == O.compute_J(pf.cpu(), gf.cpu()) and abs(F - O.compute_F(pf.cpu(), gf.cpu())) < 1e-6
+    pf[0].zero_()                                                   # in-place write -> version bump -> recomputed
+    J2 = evaluator.compute_J(pf, gf)
+    assert S.launch_count() > n1 and J2 == O.compute_J(pf.cpu(), gf.cpu()) and J2 != J
