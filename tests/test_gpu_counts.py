@@ -216,6 +216,7 @@ def test_compute_J_then_compute_F_share_one_pass():
     F = evaluator.compute_F(pf, gf)
     assert S.launch_count() == n1 and n1 > n0
     assert J == O.compute_J(pf.cpu(), gf.cpu()) and abs(F - O.compute_F(pf.cpu(), gf.cpu())) < 1e-6
-    pf[0].zero_()                                                   # in-place write -> version bump -> recomputed
+    assert pf[2].any()
+    pf[2].zero_()                                                   # in-place write -> version bump -> recomputed
     J2 = evaluator.compute_J(pf, gf)
     assert S.launch_count() > n1 and J2 == O.compute_J(pf.cpu(), gf.cpu()) and J2 != J
