@@ -7,7 +7,7 @@ from ._lib import SolaError, load as load_library, launch_count  # noqa: F401
 from . import packed, seg_utils, utils, prompt_generator, evaluator, dedup, dataloader_ops, metric, sharding, rle, api  # noqa: F401
 from .packed import (PackedMasks, binarize_pack_stability, binarize_pack_resize, pack_masks, unpack_masks, frame_counts,  # noqa: F401
                      frame_counts_packed, pairwise_inter_matrix, gathered_inter, resize_bilinear_bin,
-                     resize_nearest, or_merge, boundary_counts)
+                     resize_nearest, or_merge, boundary_counts, jf_boundary_counts, JFSweepPlan)
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 from .api import pairwise_iou_matrix, gathered_iou, greedy_filter, jf_batch  # noqa: F401,E402
