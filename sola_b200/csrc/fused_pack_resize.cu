@@ -17,7 +17,6 @@
 #include "pack_core.cuh"
 #include "resize_core.cuh"
 #include <math.h>
-#include <stdlib.h>
 
 namespace sola {
 
@@ -268,11 +267,9 @@ struct FusedPlan {
 };
 
 // The fp32 kernel is built with a 5-CTA/SM register cap (48 registers, no spills): left alone ptxas takes 64 registers (4 CTAs/SM),
-// which measures 1.1 % slower on the bench (2.968 vs 2.935 ms).  SOLA_FUSED_OCC=0 selects the uncapped build for A/B runs.
-static int fused_occ() {
-  static const int v = [] { const char* e = getenv("SOLA_FUSED_OCC"); return e ? atoi(e) : 5; }();
-  return v;
-}
+// which measured 1.1 % slower on the bench (2.968 vs 2.935 ms, profiles/r1_fused_prefetch_waves_experiment.log).
+template <typename T> struct FusedBuild { static constexpr int MIN_CTAS = 0; };
+template <> struct FusedBuild<float> { static constexpr int MIN_CTAS = 5; };
 
 static FusedPlan plan_fused(const void* base, long long n_frames, int H, int W, int oh, int ow, int elem_size) {
   FusedPlan p{};
@@ -311,14 +308,12 @@ static FusedPlan plan_fused(const void* base, long long n_frames, int H, int W, 
   if (p.generic) {
     if (elem_size == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, band_pack_generic_kernel<float, true>, FU_THREADS, p.smem);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, band_pack_generic_kernel<__nv_bfloat16, true>, FU_THREADS, p.smem);
-  } else if (elem_size == 4 && fused_occ() == 5) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_pack_resize_kernel<float, 5>, FU_THREADS, p.smem);
-  else if (elem_size == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_pack_resize_kernel<float>, FU_THREADS, p.smem);
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_pack_resize_kernel<__nv_bfloat16>, FU_THREADS, p.smem);
+  } else if (elem_size == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_pack_resize_kernel<float, FusedBuild<float>::MIN_CTAS>, FU_THREADS, p.smem);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_pack_resize_kernel<__nv_bfloat16, FusedBuild<__nv_bfloat16>::MIN_CTAS>, FU_THREADS, p.smem);
   if (occ < 1) occ = 1;
   // several waves of resident CTAs: finer slices cost a table rebuild per CTA (~5 % of one frame's work) but shrink the
-  // tail where the last CTAs run alone; SOLA_FUSED_WAVES overrides for experiments
-  int waves = 16;
-  if (const char* e = getenv("SOLA_FUSED_WAVES")) { const int v = atoi(e); if (v > 0) waves = v; }
+  // tail where the last CTAs run alone (12 and 24 waves measured 0.7-1 % slower than 16)
+  const int waves = 16;
   const int target_ctas = num_sms() * occ * waves;
   int slices = target_ctas / p.n_bands;
   if (slices < 1) slices = 1;
@@ -369,17 +364,11 @@ static int launch_fused(const T* logits, long long n_frames, int H, int W, int o
                                                                             cnt_lo, area_resized);
     return check_launch("band_pack_generic<resize> kernel");
   }
-  if (sizeof(T) == 4 && fused_occ() == 5) {
-    SOLA_CUDA(cudaFuncSetAttribute(fused_pack_resize_kernel<T, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    fused_pack_resize_kernel<T, 5><<<grid, FU_THREADS, p.smem, stream>>>(logits, (int)n_frames, p.frames_per_slice, H, W, oh, ow,
-                                                                         (float)H / (float)oh, (float)W / (float)ow, p.max_tile_rows, th,
-                                                                         packed_out, resized_out, cnt_hi, cnt_mid, cnt_lo, area_resized);
-    return check_launch("fused_pack_resize<occ5> kernel");
-  }
-  SOLA_CUDA(cudaFuncSetAttribute(fused_pack_resize_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-  fused_pack_resize_kernel<T><<<grid, FU_THREADS, p.smem, stream>>>(logits, (int)n_frames, p.frames_per_slice, H, W, oh, ow,
-                                                                    (float)H / (float)oh, (float)W / (float)ow, p.max_tile_rows, th,
-                                                                    packed_out, resized_out, cnt_hi, cnt_mid, cnt_lo, area_resized);
+  constexpr int MIN_CTAS = FusedBuild<T>::MIN_CTAS;
+  SOLA_CUDA(cudaFuncSetAttribute(fused_pack_resize_kernel<T, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  fused_pack_resize_kernel<T, MIN_CTAS><<<grid, FU_THREADS, p.smem, stream>>>(logits, (int)n_frames, p.frames_per_slice, H, W, oh, ow,
+                                                                             (float)H / (float)oh, (float)W / (float)ow, p.max_tile_rows, th,
+                                                                             packed_out, resized_out, cnt_hi, cnt_mid, cnt_lo, area_resized);
   return check_launch("fused_pack_resize kernel");
 }
 
