@@ -62,6 +62,11 @@ def parse():
                     help="stage the e2e logits in WRITE-COMBINED pinned host memory (cudaHostAllocWriteCombined): DMA reads do not snoop the "
                          "CPU caches, which matters when 8 ranks stream 18.9 GB per step out of one socket")
     ap.add_argument("--no-fuse", action="store_true", help="run K1 and R1 as two kernels instead of the fused one")
+    ap.add_argument("--overlap", action="store_true",
+                    help="run the tail of a step (R2, K2 gather, K2 N x N, labels) on a second high-priority stream under the next video's K1+R1. "
+                         "Measured (profiles/r3_overlap_experiment.json): 3.50 vs 3.63 ms per step, but K1+R1 slows from 2.93 to 3.49 ms because "
+                         "K2's two 288-thread, 96-register CTAs per SM displace the five K1+R1 CTAs it needs for its loads in flight; off by default")
+    ap.add_argument("--no-aux", action="store_true", help="issue every kernel of a step on one stream (no R2 beside K1+R1, no gather / labels beside K2)")
     ap.add_argument("--no-jf", action="store_true", help="skip the config-4 J&F sweep region")
     ap.add_argument("--no-cfg5", action="store_true", help="skip the config-5 exchange slice (N > 1 only)")
     ap.add_argument("--jf-reps", type=int, default=20)
@@ -156,21 +161,30 @@ class ClockSampler:
 # the step (product path)
 # ---------------------------------------------------------------------------------------------------------------
 class Workload:
-    def __init__(self, device, seed, n_tracks, n_frames, fused=True, st_native=False):
+    def __init__(self, device, seed, n_tracks, n_frames, fused=True, st_native=False, overlap=False, aux=True):
         import sola_b200 as S
         from sola_b200 import synth
         self.fused = fused
         self.st_native = st_native
+        # the tail of video k (R2, K2 gather, K2 N x N, labels, read-backs: integer / latency bound, a few hundred MB) runs on a
+        # second, high-priority stream UNDER the HBM-bound K1+R1 of video k+1; every in-flight video has its own output buffers
+        self.overlap = overlap and fused
+        self.tail_stream = torch.cuda.Stream(device=device, priority=-1) if self.overlap else None
+        # within a video: R2 runs beside K1+R1, K2 gather + label counts beside K2 N x N (they only share read-only inputs)
+        self.aux_stream = torch.cuda.Stream(device=device) if aux else None
         self.S, self.device = S, device
         self.N, self.T, self.H, self.W = n_tracks, n_frames, CFG["H"], CFG["W"]
         self.logits, prompts = synth.dedup_candidates(self.N, self.T, self.H, self.W, seed=seed, device=device, bin_size=CFG["bin_size"])
         self.prompt_meta = [{"prompt_id": p["prompt_id"], "frame_idx": p["frame_idx"]} for p in prompts]
         self.prompt_masks_host = np.stack([p["segmentation"] for p in prompts])                       # (N, H, W) uint8
         self.prompt_masks_dev = torch.from_numpy(self.prompt_masks_host).to(device)
-        self.packed = S.PackedMasks.empty((self.N, self.T), self.H, self.W, device)                   # reused outputs
-        self.counts = torch.empty((3, self.N * self.T), dtype=torch.int32, device=device)
-        self.k1_events = []
         self.oh, self.ow = S.packed.default_target_shape(self.H, self.W)
+        n_slots = 2 if self.overlap else 1                                                            # reused outputs, one set per in-flight video
+        self.slot_packed = [S.PackedMasks.empty((self.N, self.T), self.H, self.W, device) for _ in range(n_slots)]
+        self.slot_counts = [torch.empty((3, self.N * self.T), dtype=torch.int32, device=device) for _ in range(n_slots)]
+        self.slot_resized = [S.PackedMasks.empty((self.N, self.T), self.oh, self.ow, device) for _ in range(n_slots)]
+        self.packed, self.counts = self.slot_packed[0], self.slot_counts[0]                           # the last finished step's outputs
+        self.k1_events = []
         # GT masklets of the video at the resized shape (what `gt_masklets` holds, generate_tokens_grid.py:112): G objects x T frames
         self.gt_masks = torch.stack([synth.blob_masklet(self.T, self.oh, self.ow, seed * 31 + g, device=device, fill=0.12 + 0.05 * g)
                                      for g in range(CFG["n_gt"])])                                    # (G, T, oh, ow) uint8
@@ -182,7 +196,8 @@ class Workload:
     def make_jobs(self):
         from sola_b200 import dedup
         mk = lambda: dedup.VideoDedupJob(self.prompt_meta, self.T, device=self.device, mode="grid", st_on_resized=not self.st_native, bin_size=CFG["bin_size"],
-                                         n_max_tracks=CFG["n_max_tracks"], batch_size=CFG["batch_size"], miou_thresh=CFG["miou_thresh"])
+                                         n_max_tracks=CFG["n_max_tracks"], batch_size=CFG["batch_size"], miou_thresh=CFG["miou_thresh"],
+                                         tail_stream=self.tail_stream, aux_stream=self.aux_stream)
         self.jobs = [mk(), mk()]
         for j in self.jobs:
             j.set_gt_masklets(self.gt_planes)
@@ -193,14 +208,18 @@ class Workload:
         logits = self.logits if logits is None else logits
         prompt_masks = self.prompt_masks_dev if prompt_masks is None else prompt_masks
         S = self.S
+        b = slot % len(self.slot_packed)
+        out_p, out_c, out_r = self.slot_packed[b], self.slot_counts[b], self.slot_resized[b]
+        if self.aux_stream is not None:
+            job.enqueue_prompts(prompt_masks, (self.oh, self.ow))                                         # R2, beside K1+R1
         # the dominant kernel is the first launch of the step: bracket it with events on the launching stream
         if record_k1:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         if self.fused:
-            packed, counts, resized = S.binarize_pack_resize(logits, 0.0, 1.0, out=self.packed, counts_out=self.counts)      # K1 + R1
+            packed, counts, resized = S.binarize_pack_resize(logits, 0.0, 1.0, out=out_p, counts_out=out_c, resized_out=out_r)   # K1 + R1
         else:
-            packed, counts = S.binarize_pack_stability(logits, 0.0, 1.0, out=self.packed, counts_out=self.counts)            # K1
+            packed, counts = S.binarize_pack_stability(logits, 0.0, 1.0, out=out_p, counts_out=out_c)                        # K1
         if record_k1:
             e1.record()
             self.k1_events.append((e0, e1))
@@ -211,6 +230,8 @@ class Workload:
     def finish(self, slot):
         """Host half: wait for that step's read-back, replay both greedy loops, stability scores, label metrics."""
         r = self.jobs[slot].finish()
+        b = slot % len(self.slot_packed)
+        self.packed, self.counts = self.slot_packed[b], self.slot_counts[b]
         return {"tracked": r["tracked"], "filtered": r["filtered"], "kept_st": r["kept_spatiotemporal"], "stability": r["stability"],
                 "inter": r["inter"], "labels": r.get("labels")}
 
@@ -572,7 +593,8 @@ def main():
     # its cpu_baseline leg must see the whole host)
     cpus = sharding.bind_to_gpu_cpus(local_rank) if (world > 1 and not os.environ.get("SOLA_BENCH_NO_AFFINITY")) else []
 
-    w = Workload(device, seed=1234 + 2 + 1000 * rank, n_tracks=n_tracks, n_frames=n_frames, fused=not args.no_fuse, st_native=args.st_native)
+    w = Workload(device, seed=1234 + 2 + 1000 * rank, n_tracks=n_tracks, n_frames=n_frames, fused=not args.no_fuse, st_native=args.st_native,
+                 overlap=args.overlap, aux=not args.no_aux)
     w.make_jobs()
     torch.cuda.synchronize()
 
@@ -726,8 +748,12 @@ def main():
                    "kept_sets": info, "parallelism": f"video-sharded x{world}, no data-path collective",
                    "n_x_n_planes": "native 720x1280" if args.st_native else "540x960 resized masklets (what the reference filter compares)"},
         "clocks": clocks,
-        "stage_ms": {"dominant (K1+R1 fused)" if w.fused else "dominant (K1)": k1_ms, "K2 N x N (int pipe, carry-save, TMA-staged)": k2_ms,
-                     "everything else incl. label counts and gaps": max_ms / args.steps - k1_ms - k2_ms},
+        "stage_ms": ({"dominant (K1+R1 fused), timed while the previous video's tail runs beside it": k1_ms,
+                      "K2 N x N (int pipe, carry-save, TMA-staged), on the tail stream under the next video's K1+R1": k2_ms,
+                      "step time not covered by K1+R1 (tail not hidden + gaps)": max_ms / args.steps - k1_ms,
+                      "streams": "2 (--overlap: tail of video k under K1+R1 of video k+1)"} if w.overlap else
+                     {"dominant (K1+R1 fused)" if w.fused else "dominant (K1)": k1_ms, "K2 N x N (int pipe, carry-save, TMA-staged)": k2_ms,
+                      "everything else incl. label counts and gaps": max_ms / args.steps - k1_ms - k2_ms}),
         "gpu_launches": int(launches),
         "gpu_launches_jf_region": int(launches_jf),
         "e2e": e2e,

@@ -138,10 +138,20 @@ __device__ __forceinline__ void store_tile(const K2Acc& acc, int N, int ti, int 
     }
 }
 
+// Which stages of [stage_lo, stage_hi) the CTA `split` of `splits` reduces: every splits-th one.  Masklets are objects on an empty
+// background, so a CONTIGUOUS K-range per CTA gives some CTAs only all-zero rows (top / bottom of a frame) and others the object
+// centres — with two waves of CTAs the slow ones set the kernel time.  A strided walk hands every CTA the same mix of rows; each
+// stage is its own TMA box / cp.async batch, so the order costs nothing.
+struct StageWalk { long long first, step, count; };
+__device__ __forceinline__ StageWalk stage_walk(long long stage_lo, long long stage_hi, int split, int splits) {
+  const long long stages = stage_hi - stage_lo;
+  return StageWalk{stage_lo + split, (long long)splits, stages > split ? (stages - split + splits - 1) / splits : 0};
+}
+
 // ---- cp.async-staged kernel: rows come from one (N, words) buffer or from a table of per-track pointers (peer GPUs' memory) --------
 template <bool DIAG>
 __device__ __forceinline__ void st_tile_cpasync(const uint32_t* __restrict__ packed, const uint32_t* const* __restrict__ row_ptrs, int N,
-                                                long long words, int ti, int tj, long long s_begin, long long s_end, uint4* smem,
+                                                long long words, int ti, int tj, long long s_first, long long s_step, long long n_st, uint4* smem,
                                                 unsigned long long* __restrict__ inter) {
   constexpr int ROWS = DIAG ? PT : 2 * PT;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -163,16 +173,15 @@ __device__ __forceinline__ void st_tile_cpasync(const uint32_t* __restrict__ pac
       cp_async16(dst + q * ROWS + row, src, nbytes);
     }
   };
-  const long long n_st = s_end - s_begin;
 #pragma unroll
   for (int p = 0; p < NSTAGE - 1; ++p) {
-    if (p < n_st) issue(s_begin + p, p);
+    if (p < n_st) issue(s_first + p * s_step, p);
     cp_async_commit();
   }
   for (long long s = 0; s < n_st; ++s) {
     cp_async_wait<NSTAGE - 2>();
     __syncthreads();
-    if (s + NSTAGE - 1 < n_st) issue(s_begin + s + NSTAGE - 1, (int)((s + NSTAGE - 1) % NSTAGE));
+    if (s + NSTAGE - 1 < n_st) issue(s_first + (s + NSTAGE - 1) * s_step, (int)((s + NSTAGE - 1) % NSTAGE));
     cp_async_commit();
     consume_stage<DIAG>(StageKQ{smem + (size_t)(s % NSTAGE) * (2 * PT) * KQ, ROWS, DIAG ? 0 : PT}, tx, ty, acc);
   }
@@ -190,10 +199,9 @@ pair_iou_st_kernel(const uint32_t* __restrict__ packed, const uint32_t* const* _
   const int tile = tile_first + (blockIdx.x % n_tiles) * tile_step, split = blockIdx.x / n_tiles;
   int ti, tj;
   tile_from_index(tile, nt, ti, tj);
-  const long long stages = stage_hi - stage_lo;
-  const long long s_begin = stage_lo + stages * split / splits, s_end = stage_lo + stages * (split + 1) / splits;
-  if (ti == tj) st_tile_cpasync<true>(packed, row_ptrs, N, words, ti, tj, s_begin, s_end, smem_st, inter);
-  else st_tile_cpasync<false>(packed, row_ptrs, N, words, ti, tj, s_begin, s_end, smem_st, inter);
+  const StageWalk sw = stage_walk(stage_lo, stage_hi, split, splits);
+  if (ti == tj) st_tile_cpasync<true>(packed, row_ptrs, N, words, ti, tj, sw.first, sw.step, sw.count, smem_st, inter);
+  else st_tile_cpasync<false>(packed, row_ptrs, N, words, ti, tj, sw.first, sw.step, sw.count, smem_st, inter);
 }
 
 // ---- TMA-staged, warp-specialised ring (default) ---------------------------------------------------------------------------------
@@ -207,17 +215,17 @@ constexpr int TMA_BOX_BYTES = PT * STAGE_WORDS * 4;      // 64 rows x 128 B
 
 // `load_stage(dst, w0, bar)` issues the TMA loads of one stage (operand A at dst, B at dst + TMA_BOX_BYTES) after the expect_tx.
 template <bool DIAG, class LoadStage>
-__device__ __forceinline__ void st_tile_ring(LoadStage load_stage, int N, int ti, int tj, long long s_begin, long long s_end,
+__device__ __forceinline__ void st_tile_ring(LoadStage load_stage, int N, int ti, int tj, const StageWalk sw,
                                              unsigned char* smem, uint64_t* full, uint64_t* empty, unsigned long long* __restrict__ inter) {
   const int tid = threadIdx.x;
-  const long long n_st = s_end - s_begin;
+  const long long n_st = sw.count;
   if (tid >= ST_THREADS) {                              // producer warp: one lane drives the TMA unit
     if (tid == ST_THREADS) {
       for (long long s = 0; s < n_st; ++s) {
         const int buf = (int)(s % NSTAGE);
         if (s >= NSTAGE) mbar_wait(empty + buf, (unsigned)(((s / NSTAGE) - 1) & 1));     // all 8 warps have left this buffer
         mbar_expect_tx(full + buf, DIAG ? TMA_BOX_BYTES : 2 * TMA_BOX_BYTES);
-        load_stage(smem + (size_t)buf * 2 * TMA_BOX_BYTES, (int)((s_begin + s) * STAGE_WORDS), full + buf);
+        load_stage(smem + (size_t)buf * 2 * TMA_BOX_BYTES, (int)((sw.first + s * sw.step) * STAGE_WORDS), full + buf);
       }
     }
     return;
@@ -236,7 +244,7 @@ __device__ __forceinline__ void st_tile_ring(LoadStage load_stage, int N, int ti
   store_tile<DIAG>(acc, N, ti, tj, tx, ty, inter);
 }
 
-struct RingSetup { unsigned char* boxes; int ti, tj; long long s_begin, s_end; };
+struct RingSetup { unsigned char* boxes; int ti, tj; StageWalk sw; };
 
 __device__ __forceinline__ RingSetup ring_setup(unsigned char* dyn_smem, uint64_t* full, uint64_t* empty, int nt, int n_tiles, int splits,
                                                 int tile_first, int tile_step, long long stage_lo, long long stage_hi) {
@@ -248,9 +256,7 @@ __device__ __forceinline__ RingSetup ring_setup(unsigned char* dyn_smem, uint64_
   RingSetup r;
   const int tile = tile_first + (blockIdx.x % n_tiles) * tile_step, split = blockIdx.x / n_tiles;
   tile_from_index(tile, nt, r.ti, r.tj);
-  const long long stages = stage_hi - stage_lo;
-  r.s_begin = stage_lo + stages * split / splits;
-  r.s_end = stage_lo + stages * (split + 1) / splits;
+  r.sw = stage_walk(stage_lo, stage_hi, split, splits);
   // round the dynamic-smem base up to 1024 B by OFFSET (SWIZZLE_128B boxes; a pointer cast would demote the tile reads to generic loads)
   r.boxes = dyn_smem + ((1024u - (smem_u32(dyn_smem) & 1023u)) & 1023u);
   return r;
@@ -266,12 +272,12 @@ pair_iou_st_ring_kernel(const __grid_constant__ CUtensorMap map, int N, long lon
   const int ti = r.ti, tj = r.tj;
   if (ti == tj) {
     st_tile_ring<true>([=](unsigned char* dst, int w0, uint64_t* bar) { tma_load_2d(dst, m, w0, ti * PT, bar); },
-                       N, ti, tj, r.s_begin, r.s_end, r.boxes, full, empty, inter);
+                       N, ti, tj, r.sw, r.boxes, full, empty, inter);
   } else {
     st_tile_ring<false>([=](unsigned char* dst, int w0, uint64_t* bar) {
       tma_load_2d(dst, m, w0, ti * PT, bar);
       tma_load_2d(dst + TMA_BOX_BYTES, m, w0, tj * PT, bar);
-    }, N, ti, tj, r.s_begin, r.s_end, r.boxes, full, empty, inter);
+    }, N, ti, tj, r.sw, r.boxes, full, empty, inter);
   }
 }
 
@@ -302,12 +308,12 @@ pair_iou_st_ring_peer_kernel(const __grid_constant__ PeerMaps maps, int world, i
   };
   if (ti == tj) {
     st_tile_ring<true>([=](unsigned char* dst, int w0, uint64_t* bar) { load_operand(dst, w0, ti, bar); },
-                       N, ti, tj, r.s_begin, r.s_end, r.boxes, full, empty, inter);
+                       N, ti, tj, r.sw, r.boxes, full, empty, inter);
   } else {
     st_tile_ring<false>([=](unsigned char* dst, int w0, uint64_t* bar) {
       load_operand(dst, w0, ti, bar);
       load_operand(dst + TMA_BOX_BYTES, w0, tj, bar);
-    }, N, ti, tj, r.s_begin, r.s_end, r.boxes, full, empty, inter);
+    }, N, ti, tj, r.sw, r.boxes, full, empty, inter);
   }
 }
 

@@ -255,12 +255,22 @@ class VideoDedupJob:
         finish()                       waits for THIS job's event only, then replays the reference greedy loop, the
                                        spatio-temporal greedy and the float64 stability scores on the host
 
-    Two jobs used alternately keep the GPU busy while the host post-processes the previous video (bench.py)."""
+    Two jobs used alternately keep the GPU busy while the host post-processes the previous video (bench.py).
+    With `tail_stream` set, everything after K1+R1 (R2, K2 gather, K2 N x N, label counts, read-backs: integer-pipe and latency-bound
+    kernels on a few hundred MB) is issued on that stream behind an event, so that it runs UNDER the HBM-bound K1+R1 of the next
+    video, which the caller enqueues on its own stream with per-job output buffers."""
 
     def __init__(self, prompt_meta: Sequence[dict], n_frames: int, *, device=None, mode: str = "grid",
-                 st_on_resized: bool = True, fused: bool = True, **rules):
+                 st_on_resized: bool = True, fused: bool = True, tail_stream: Optional[torch.cuda.Stream] = None,
+                 aux_stream: Optional[torch.cuda.Stream] = None, **rules):
         self.st_on_resized = st_on_resized
         self.fused = fused
+        self.tail_stream = tail_stream
+        self._k1_done = torch.cuda.Event() if tail_stream is not None else None
+        # `aux_stream`: R2 runs beside K1+R1 (enqueue_prompts), and K2 gather + label counts run beside K2 N x N
+        self.aux_stream = aux_stream
+        self._fork, self._join = (torch.cuda.Event(), torch.cuda.Event()) if aux_stream is not None else (None, None)
+        self._planes: Optional[P.PackedMasks] = None
         self.timing_events = None            # set to a list to collect (start, end) CUDA events around the K2 N x N launch
         self.prompt_meta = list(prompt_meta)
         self.n_frames = n_frames
@@ -293,6 +303,8 @@ class VideoDedupJob:
     def enqueue(self, logits: torch.Tensor, prompt_masks: torch.Tensor, *, mask_threshold: float = 0.0, threshold_offset: float = 1.0,
                 packed_out: Optional[P.PackedMasks] = None, counts_out: Optional[torch.Tensor] = None, target_shape=None):
         """logits (N, T, H, W) fp32/bf16 and prompt_masks (N, H, W) uint8, both on the device, in prompt order."""
+        if self.aux_stream is not None:
+            self.enqueue_prompts(prompt_masks, target_shape)                                                          # R2 beside K1+R1
         if self.fused:
             # K1 + R1 in one pass: the resize work hides under the HBM time of reading the logits
             packed, counts, resized = P.binarize_pack_resize(logits, mask_threshold, threshold_offset, target_shape,
@@ -306,11 +318,63 @@ class VideoDedupJob:
         """Same, for callers that already ran K1 (e.g. chunk by chunk behind H2D copies)."""
         self._enqueue_tail(packed, P.resize_bilinear_bin(packed, target_shape), counts, prompt_masks)                # R1
 
+    def enqueue_prompts(self, prompt_masks: torch.Tensor, target_shape=None) -> None:
+        """R2 ahead of time: the nearest resize + pack of the prompt masks depends on nothing K1+R1 produces, so with an `aux_stream`
+        a caller may issue it BEFORE the K1+R1 launch and it runs beside that kernel instead of after it."""
+        oh, ow = P.default_target_shape(int(prompt_masks.shape[-2]), int(prompt_masks.shape[-1])) if target_shape is None else target_shape
+        if self.aux_stream is None:
+            self._planes = P.resize_nearest(prompt_masks, oh, ow)
+            return
+        self._fork.record(torch.cuda.current_stream(self.device))
+        self.aux_stream.wait_event(self._fork)
+        with torch.cuda.stream(self.aux_stream):
+            prompt_masks.record_stream(self.aux_stream)
+            self._planes = P.resize_nearest(prompt_masks, oh, ow)
+
     def _enqueue_tail(self, packed: P.PackedMasks, resized: P.PackedMasks, counts: torch.Tensor, prompt_masks: torch.Tensor):
+        if self.tail_stream is None:
+            return self._tail(packed, resized, counts, prompt_masks)
+        self._k1_done.record(torch.cuda.current_stream(self.device))
+        self.tail_stream.wait_event(self._k1_done)
+        with torch.cuda.stream(self.tail_stream):
+            for t in (packed.words if packed is not None else None, resized.words, counts, prompt_masks):
+                if t is not None:
+                    t.record_stream(self.tail_stream)
+            self._tail(packed, resized, counts, prompt_masks)
+
+    def _tail(self, packed: Optional[P.PackedMasks], resized: P.PackedMasks, counts: torch.Tensor, prompt_masks: torch.Tensor):
         N, T = int(resized.words.shape[0]), int(resized.words.shape[1])
         self.packed, self.resized = packed, resized
-        planes = P.resize_nearest(prompt_masks, self.resized.H, self.resized.W)                                        # R2
-        g = P.gathered_inter(self.resized, planes, self.frame_idx_dev)                                                 # K2 gather
+        main = torch.cuda.current_stream(self.device)
+        aux = self.aux_stream
+        if self._planes is None or (self._planes.H, self._planes.W) != (resized.H, resized.W):
+            self._planes = None
+            self.enqueue_prompts(prompt_masks, (resized.H, resized.W))                                                # R2
+        planes, self._planes = self._planes, None
+        hg, hi, hc = self._pinned(N, int(planes.words.shape[0]), T)
+
+        def side():
+            """K2 gather + label counts + their read-backs: independent of K2 N x N (all three only read the resized planes)."""
+            g = P.gathered_inter(resized, planes, self.frame_idx_dev)                                                  # K2 gather
+            hg.copy_(g, non_blocking=True)
+            if self.gt_planes is not None:
+                # label metrics (generate_tokens_grid.py:253-264): per-frame |track ∩ gt|, |track|, |gt| for all N x G x T frame pairs
+                G = int(self.gt_planes.words.shape[0])
+                li, la, lb = P.frame_counts_packed(resized, self.gt_planes)
+                shapes = ((N, G, T), (N, T), (G, T))
+                if self._host_labels is None or tuple(tuple(t.shape) for t in self._host_labels) != shapes:
+                    self._host_labels = tuple(torch.empty(sh, dtype=torch.int32).pin_memory() for sh in shapes)
+                for h, d in zip(self._host_labels, (li, la, lb)):
+                    h.copy_(d, non_blocking=True)
+
+        if aux is not None:
+            # the integer-pipe-bound N x N kernel on this stream, the latency / POPC-bound gather and label counts beside it
+            self._fork.record(main)
+            aux.wait_event(self._fork)
+            with torch.cuda.stream(aux):
+                resized.words.record_stream(aux)
+                side()
+                self._join.record(aux)
         # K2 N x N on the resized planes: after generate_tokens_grid.py:248-250 only the 540x960 masklets exist, so a
         # masklet-vs-masklet IoU (seg_utils.compute_masklet_iou) in that flow compares those
         if self.timing_events is not None:
@@ -320,20 +384,13 @@ class VideoDedupJob:
         if self.timing_events is not None:
             eb.record()
             self.timing_events.append((ea, eb))
-        hg, hi, hc = self._pinned(N, int(planes.words.shape[0]), T)
-        hg.copy_(g, non_blocking=True)
         hi.copy_(inter, non_blocking=True)
         hc.copy_(counts.reshape(3, N, T), non_blocking=True)
-        if self.gt_planes is not None:
-            # label metrics (generate_tokens_grid.py:253-264): per-frame |track ∩ gt|, |track|, |gt| for all N x G x T frame pairs
-            G = int(self.gt_planes.words.shape[0])
-            li, la, lb = P.frame_counts_packed(self.resized, self.gt_planes)
-            shapes = ((N, G, T), (N, T), (G, T))
-            if self._host_labels is None or tuple(tuple(t.shape) for t in self._host_labels) != shapes:
-                self._host_labels = tuple(torch.empty(sh, dtype=torch.int32).pin_memory() for sh in shapes)
-            for h, d in zip(self._host_labels, (li, la, lb)):
-                h.copy_(d, non_blocking=True)
-        self.event.record(torch.cuda.current_stream(self.device))
+        if aux is not None:
+            main.wait_event(self._join)
+        else:
+            side()
+        self.event.record(main)
         self.counts = counts
 
     def finish(self, miou_thresh_st: Optional[float] = None) -> dict:

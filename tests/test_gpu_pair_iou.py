@@ -153,6 +153,49 @@ def test_video_dedup_job_matches_session_and_oracle():
         np.testing.assert_array_equal(r0["stability"], O.get_stability_score(logits.numpy()))
 
 
+@pytest.mark.parametrize("streams", ["aux", "tail", "aux+tail"])
+def test_video_dedup_job_stream_variants_are_identical(streams):
+    """The job's optional streams (R2 beside K1+R1, gather / label counts beside K2 N x N, the whole tail under the next video's
+    K1+R1) only reorder independent launches: every result equals the one-stream job's, with several videos in flight."""
+    import sola_b200 as S
+    from sola_b200 import dedup, synth
+    T = 8
+    logits, prompts = synth.dedup_candidates(16, T, 72, 128, seed=9, device="cpu", n_clusters=3, jitter=1)
+    meta = [{"prompt_id": p["prompt_id"], "frame_idx": p["frame_idx"]} for p in prompts]
+    pm = torch.from_numpy(np.stack([p["segmentation"] for p in prompts])).cuda()
+    videos = [logits.cuda(), logits.flip(0).contiguous().cuda(), (logits * 0.5 - 0.1).cuda()]
+    oh, ow = S.packed.default_target_shape(72, 128)
+    gt = S.pack_masks(torch.stack([synth.blob_masklet(T, oh, ow, 40 + g, device="cuda") for g in range(2)]))
+    kw = dict(mode="grid", n_max_tracks=64, batch_size=4, miou_thresh=0.7)
+    plain = dedup.VideoDedupJob(meta, T, **kw)
+    plain.set_gt_masklets(gt)
+    want = []
+    for v in videos:
+        plain.enqueue(v, pm)
+        want.append(plain.finish())
+    aux = torch.cuda.Stream() if "aux" in streams else None
+    tail = torch.cuda.Stream(priority=-1) if "tail" in streams else None
+    jobs = [dedup.VideoDedupJob(meta, T, aux_stream=aux, tail_stream=tail, **kw) for _ in range(2)]
+    for j in jobs:
+        j.set_gt_masklets(gt)
+    got, prev = [], None
+    for k, v in enumerate(videos * 3):                       # software-pipelined like bench.py: finish k-1 after enqueueing k
+        jobs[k & 1].enqueue(v, pm)
+        if prev is not None:
+            got.append(jobs[prev].finish())
+        prev = k & 1
+    got.append(jobs[prev].finish())
+    for k, r in enumerate(got):
+        w = want[k % len(videos)]
+        assert r["tracked"] == w["tracked"] and r["filtered"] == w["filtered"] and r["filtered_by"] == w["filtered_by"]
+        assert r["kept_spatiotemporal"] == w["kept_spatiotemporal"]
+        np.testing.assert_array_equal(r["inter"], w["inter"])
+        np.testing.assert_array_equal(r["iou_gather"], w["iou_gather"])
+        np.testing.assert_array_equal(np.nan_to_num(r["stability"], nan=-1), np.nan_to_num(w["stability"], nan=-1))
+        for key in ("precision", "recall", "iou"):
+            np.testing.assert_array_equal(r["labels"][key], w["labels"][key])
+
+
 @pytest.mark.parametrize("N,parts", [(200, 3), (64, 2), (130, 8), (300, 5)])
 def test_pairwise_matrix_parts_sum_to_full(N, parts):
     """Config-5 style tile partition: the shares of all parts sum to the full matrix and never overlap."""
