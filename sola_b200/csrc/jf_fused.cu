@@ -263,7 +263,9 @@ __device__ __forceinline__ void jf_phase2(unsigned sF, unsigned sG /* shared byt
   if (n2 > 0) { const int n = n2; n2 = 0; full_pass(lane < n); }
 }
 
-template <int MIN_CTAS>
+// BOUNDARY = false is the region-counts-only build (J and F exactly as evaluator.py:227-247 defines them): no boundary maps, queues
+// or disk tables, few registers, small tiles — many resident CTAs per SM keep enough bulk copies in flight for HBM speed.
+template <int MIN_CTAS, bool BOUNDARY>
 __global__ void __launch_bounds__(JF_THREADS, MIN_CTAS)
 jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_jf_unit single, long long n_items, int raw_cap,
                 int bm_cap, int mask_steps, int* __restrict__ counts, long long total_frames) {
@@ -299,7 +301,7 @@ jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_
     if (has_next) jf_decode(units, n_units, single, next, gn);
     const int Wp = g.Wp, BP = jf_pitch(Wp), r = g.r < 0 ? 0 : g.r;
     const int off = (int)(g.g0 & 3ll);
-    if (g.r >= 0) {
+    if (BOUNDARY && g.r >= 0) {
       if (r != r_cached && tid <= r) vtab[tid] = (unsigned char)jf_isqrt(r * r - tid * tid);     // disk table for run-time radii
       r_cached = r;
       for (int j = tid; j < g.NB; j += JF_THREADS) {       // zero halo columns of both boundary maps
@@ -313,12 +315,24 @@ jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_
 
     int n_i = 0, n_p = 0, n_g = 0, n_bf = 0, n_bg = 0, fm = 0, gm = 0;
     int n_steps = 0, my_o0 = 0;
-    if (g.r < 0) {
-      // region counts only: flat pass over the owned words
+    if (!BOUNDARY || g.r < 0) {
+      // region counts only: flat pass over the owned words [off, off + n_words) of the staged tile — whole 16-byte quads with
+      // 128-bit shared loads, the few words before the first / after the last whole quad one by one
       const int n_words = (g.y1 - g.y0) * Wp;
-      for (int i = tid; i < n_words; i += JF_THREADS) {
-        const uint32_t p = rawP[off + i], q = rawG[off + i];
-        n_p += __popc(p); n_g += __popc(q); n_i += __popc(p & q);
+      const int q_lo = (off + 3) >> 2, q_hi = (off + n_words) >> 2;
+      auto count = [&](uint32_t p, uint32_t q) { n_p += __popc(p); n_g += __popc(q); n_i += __popc(p & q); };
+      if (q_hi > q_lo) {
+        const uint4* P4 = reinterpret_cast<const uint4*>(rawP);
+        const uint4* G4 = reinterpret_cast<const uint4*>(rawG);
+        for (int i = q_lo + tid; i < q_hi; i += JF_THREADS) {
+          const uint4 p = P4[i], q = G4[i];
+          count(p.x, q.x); count(p.y, q.y); count(p.z, q.z); count(p.w, q.w);
+        }
+        const int head = 4 * q_lo - off, tail = off + n_words - 4 * q_hi;          // 0..3 words each
+        if (tid < head) count(rawP[off + tid], rawG[off + tid]);
+        else if (tid >= 32 && tid - 32 < tail) count(rawP[4 * q_hi + tid - 32], rawG[4 * q_hi + tid - 32]);
+      } else {
+        for (int i = tid; i < n_words; i += JF_THREADS) count(rawP[off + i], rawG[off + i]);
       }
     } else {
       // ---- phase 1: column walkers build both boundary maps ------------------------------------------------------------------
@@ -381,7 +395,7 @@ jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_
     __syncthreads();                                        // boundary maps complete; the raw tile is dead
     if (has_next) jf_issue_load(gn, rawP, rawG, &bar, tid);  // next tile streams in while this one is matched
 
-    if (g.r >= 0) {
+    if (BOUNDARY && g.r >= 0) {
       uint32_t* q1 = queue1[warp];
       uint32_t* q2 = queue2[warp];
       const uint2* mk = masks + warp * mask_steps;
@@ -396,12 +410,12 @@ jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_
     }
 
     n_i = warp_sum(n_i); n_p = warp_sum(n_p); n_g = warp_sum(n_g);
-    if (g.r >= 0) { n_bf = warp_sum(n_bf); n_bg = warp_sum(n_bg); fm = warp_sum(fm); gm = warp_sum(gm); }
+    if (BOUNDARY && g.r >= 0) { n_bf = warp_sum(n_bf); n_bg = warp_sum(n_bg); fm = warp_sum(fm); gm = warp_sum(gm); }
     if (lane == 0) {
       red[0][warp] = n_i; red[1][warp] = n_p; red[2][warp] = n_g; red[3][warp] = n_bf; red[4][warp] = n_bg; red[5][warp] = fm; red[6][warp] = gm;
     }
     __syncthreads();
-    if (tid < (g.r >= 0 ? 7 : 3)) {
+    if (tid < ((BOUNDARY && g.r >= 0) ? 7 : 3)) {
       int sum = 0;
 #pragma unroll
       for (int w = 0; w < JF_WARPS; ++w) sum += red[tid][w];
@@ -442,6 +456,14 @@ constexpr int JF_FIRST_CLASS = 1;                 // 0: try the 3-CTA class firs
 constexpr size_t JF_BUDGET_3CTA = 72 * 1024;
 constexpr size_t JF_BUDGET_2CTA = 100 * 1024;
 constexpr size_t JF_BUDGET_1CTA = 200 * 1024;     // tall halos (1080p: r = 18)
+// sweeps without a single boundary unit run the region-only build: JF_REGION_CTAS resident CTAs per SM, each with a small tile.
+// Measured on the bench's mixed sweep (profiles/r3_jf_region_ctas.jsonl): 8 / 6 / 4 / 3 / 2 CTAs -> 5.27 / 6.02 / 6.19 / 6.04 / 5.01 TB/s
+// (the 128-register build with two 100 KB tiles: 5.4 TB/s)
+#ifndef JF_REGION_CTAS_VALUE
+#define JF_REGION_CTAS_VALUE 4
+#endif
+constexpr int JF_REGION_CTAS = JF_REGION_CTAS_VALUE;
+constexpr size_t JF_BUDGET_REGION = (size_t)(216 / JF_REGION_CTAS - 1) * 1024;
 
 extern "C" {
 typedef struct sola_jf_plan {
@@ -455,10 +477,13 @@ static int jf_plan(sola_jf_unit* units, int n_units, sola_jf_plan* plan, int for
   // r2_jf_fused_bench.json): two resident CTAs beat one even at 1080p, where the 100 KB tile spends 37 of 101 rows on halo (1.20 M vs
   // 1.05 M frame pairs/s); bands for three CTAs lose everywhere except where the 2-CTA tile already fits three times (360p).
   // (force_ctas = 1 / 2 / 3 pins the class: experiments, tools/jf_fused_bench.py)
-  const size_t budgets[3] = {JF_BUDGET_3CTA, JF_BUDGET_2CTA, JF_BUDGET_1CTA};
-  const int ctas[3] = {3, 2, 1};
-  int first = JF_FIRST_CLASS, last = 2;
-  if (force_ctas >= 1 && force_ctas <= 3) first = last = 3 - force_ctas;
+  bool all_region = n_units > 0;
+  for (int i = 0; i < n_units; ++i) all_region = all_region && units[i].radius < 0;
+  const bool region_class = all_region && (force_ctas == 0 || force_ctas == JF_REGION_CTAS);
+  const size_t budgets[3] = {region_class ? JF_BUDGET_REGION : JF_BUDGET_3CTA, JF_BUDGET_2CTA, JF_BUDGET_1CTA};
+  const int ctas[3] = {region_class ? JF_REGION_CTAS : 3, 2, 1};
+  int first = region_class ? 0 : JF_FIRST_CLASS, last = 2;
+  if (!region_class && force_ctas >= 1 && force_ctas <= 3) first = last = 3 - force_ctas;
   for (int cls = first; cls <= last; ++cls) {
     const size_t budget = budgets[cls];
     bool retry = false;
@@ -497,7 +522,7 @@ static int jf_plan(sola_jf_unit* units, int n_units, sola_jf_plan* plan, int for
     plan->n_items = items; plan->total_frames = frames; plan->raw_cap = raw_cap; plan->bm_cap = bm_cap; plan->mask_steps = steps;
     plan->reserved = ctas[cls];
     // small frames: the 2-CTA plan's tile already leaves room for a third CTA — take the 80-register build so that it can be resident
-    if (force_ctas == 0 && cls == 1 && (size_t)(2 * raw_cap + 2 * bm_cap + 2 * JF_WARPS * steps) * sizeof(uint32_t) <= JF_BUDGET_3CTA) plan->reserved = 3;
+    if (force_ctas == 0 && !region_class && cls == 1 && (size_t)(2 * raw_cap + 2 * bm_cap + 2 * JF_WARPS * steps) * sizeof(uint32_t) <= JF_BUDGET_3CTA) plan->reserved = 3;
     return SOLA_OK;
   }
   return SOLA_ERR_UNSUPPORTED;
@@ -523,8 +548,9 @@ static int jf_launch(const sola_jf_unit* units_dev, int n_units, const sola_jf_u
                                                          p.total_frames);
     return check_launch("jf_fused kernel");
   };
-  // the plan's tile class decides the build: 3 CTAs per SM need the 80-register build
-  return p.reserved == 3 ? launch(jf_fused_kernel<3>) : launch(jf_fused_kernel<2>);
+  // the plan's tile class decides the build: 3 CTAs per SM need the 80-register build; the region class has its own lean build
+  if (p.reserved == JF_REGION_CTAS) return launch(jf_fused_kernel<JF_REGION_CTAS, false>);
+  return p.reserved == 3 ? launch(jf_fused_kernel<3, true>) : launch(jf_fused_kernel<2, true>);
 }
 
 }  // namespace sola

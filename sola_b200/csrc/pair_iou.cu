@@ -8,8 +8,9 @@
 //
 // The N x N kernel is integer-pipe bound for N >~ 16 (each word is used by N-1 pairs), so it is organised like a
 // register-tiled GEMM whose multiply-add is LOP3+POPC+IADD:
-//   * a CTA owns one 64 x 64 tile of pairs and a contiguous range of the word (k) axis; K-ranges are split so
-//     that the grid fills every SM several times even when N = 64 gives a single tile;
+//   * a CTA owns one 64 x 64 tile of pairs and every splits-th 32-word stage of the word (k) axis (a strided walk, so that every
+//     CTA sees the same mix of background and object rows); the K axis is split so that the grid fills every SM several times
+//     even when N = 64 gives a single tile;
 //   * rows are staged global -> shared with 16-byte cp.async in a 4-stage ring, stored k-quad-major
 //     ([k/4][row] uint4) so that the 16 lanes that read 16 consecutive rows hit 16 distinct bank groups;
 //   * each of the 256 threads accumulates a strided 4 x 4 micro-tile (rows ty+16r, cols tx+16r) in int32

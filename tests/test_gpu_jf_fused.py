@@ -95,6 +95,32 @@ def test_fused_region_only_and_unaligned_planes():
     assert np.array_equal(c2, _expected(pred, gt))
 
 
+@pytest.mark.parametrize("T,H,W", SHAPES + [(2, 1080, 1920), (40, 9, 40), (3, 2160, 3840)])
+def test_region_build_vs_oracle(T, H, W):
+    """Sweeps without a boundary unit run the lean region-only build (small tiles, many CTAs per SM, 128-bit shared loads with scalar
+    head / tail words): every shape class, aligned and word-shifted planes, one unit and the same unit inside a mixed sweep."""
+    import sola_b200 as S
+    from sola_b200 import packed as P
+    pred, gt = _pair(T, H, W, seed=T * 7 + H + W)
+    want = _expected(pred, gt, with_boundary=False)
+    pp, gp = S.pack_masks(pred), S.pack_masks(gt)
+    assert np.array_equal(P.jf_boundary_counts(pp, gp, with_boundary=False).cpu().numpy(), want)
+
+    def shifted(pm, k):
+        flat = torch.zeros(pm.words.numel() + k, dtype=torch.int32, device=pm.words.device)
+        flat[k:] = pm.words.reshape(-1)
+        return P.PackedMasks(flat[k:].view(pm.words.shape), pm.H, pm.W)
+    for k in (1, 3):
+        assert np.array_equal(P.jf_boundary_counts(shifted(pp, k), shifted(gp, k), with_boundary=False).cpu().numpy(), want), k
+    other = _pair(3, 48, 85, seed=3)
+    plan = P.JFSweepPlan([(S.pack_masks(other[0]), S.pack_masks(other[1])), (pp, gp), (shifted(pp, 2), gp)], with_boundary=False)
+    assert len(plan.launches) == 1
+    c = plan.run().cpu().numpy()
+    assert np.array_equal(c[:, plan.offsets[0]: plan.offsets[0] + 3], _expected(*other, with_boundary=False))
+    for u in (1, 2):
+        assert np.array_equal(c[:, plan.offsets[u]: plan.offsets[u] + T], want)
+
+
 def test_fused_mixed_shape_sweep_one_launch():
     """A MeViS-like sweep: units of different (T, H, W) in ONE launch; per-unit slices equal the per-unit oracles, and JFSweep's J / F /
     F_boundary equal the reference formulas on them."""
