@@ -13,8 +13,8 @@
 //     even when N = 64 gives a single tile;
 //   * rows are staged global -> shared with 16-byte cp.async in a 4-stage ring, stored k-quad-major
 //     ([k/4][row] uint4) so that the 16 lanes that read 16 consecutive rows hit 16 distinct bank groups;
-//   * each of the 256 threads accumulates a strided 4 x 4 micro-tile (rows ty+16r, cols tx+16r) in int32
-//     registers; diagonal tiles stage their 64 rows once and skip the strictly-lower micro-tile entries;
+//   * each of the 512 consumer threads accumulates a strided 4 x 2 micro-tile (rows warp+16r, cols lane+32c) in carry-save
+//     registers; diagonal tiles stage their 64 rows once and skip the blocks below the diagonal;
 //   * partial sums leave the CTA as 64-bit atomics on the N x N output (a few hundred adds per address).
 #include "tma.cuh"
 #include <cuda.h>
@@ -26,7 +26,7 @@ constexpr int PT = 64;            // tile side (tracks)
 constexpr int KQ = 8;             // uint4 per row per stage -> 32 words = 128 B per row per stage
 constexpr int STAGE_WORDS = KQ * 4;
 constexpr int NSTAGE = 4;
-constexpr int ST_THREADS = 256;   // consumer threads: 16 x 16, each a strided 4 x 4 micro-tile of pairs
+constexpr int ST_THREADS = 512;   // consumer threads: 16 warps (ty) x 32 lanes (tx), each a strided 4 x 2 micro-tile of pairs
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(src_bytes));
@@ -87,36 +87,45 @@ struct StageSwz {       // TMA loader, SWIZZLE_128B: chunk q of row r sits at ch
   __device__ __forceinline__ uint4 b(int q, int r) const { return B[r * KQ + (q ^ (r & 7))]; }
 };
 
+// Thread (ty = warp, tx = lane) owns the pairs (row ty + 16 r, column tx + 32 c), r < 4, c < 2: the four operand rows of a warp are
+// the same for all of its lanes (broadcast shared loads), its 32 lanes read 32 consecutive column rows (512 contiguous or
+// swizzle-spread bytes: conflict-free).  Sixteen consumer warps per CTA (two CTAs per SM: 8 warps per scheduler) hide the
+// fixed-latency LOP3 chains and the shared loads that the former 8-warp / 4 x 4 layout left exposed.
 struct K2Acc {
-  Csa c[4][4];
+  Csa c[4][2];
   __device__ __forceinline__ void clear() {
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) c[a][b] = Csa{0u, 0u, 0};
+      for (int b = 0; b < 2; ++b) c[a][b] = Csa{0u, 0u, 0};
   }
 };
 
+// On a diagonal tile the block (rows 16 r .., columns 32 c ..) is needed only where column >= row: 6 of the 8 blocks.  (Remapping the
+// diagonal tile's 2080 pairs onto 5 slots with per-lane operand rows executes fewer chains but needs non-broadcast shared loads and
+// measured slower, 0.32 vs 0.26 ms: profiles/r3_k2_variants.json.)
+__host__ __device__ constexpr bool k2_block_needed(bool diag, int r, int c) { return !diag || 32 * c + 31 >= 16 * r; }
+
 template <bool DIAG, class Stage>
 __device__ __forceinline__ void consume_stage(const Stage& st, int tx, int ty, K2Acc& acc) {
+  // Masklets are mostly background: an all-zero quad of operand row i contributes nothing to any of its pairs (the carry-save state
+  // is unchanged by zero inputs), so its compressor chains are skipped.  The rows are warp-uniform, so the 4 rows x 8 quads = 32
+  // tests of a stage are ONE per lane and a ballot: bit 8 r + q <=> quad q of row ty + 16 r is non-zero.  Skips never diverge.
+  const uint4 probe = st.a(tx & 7, ty + 16 * (tx >> 3));
+  const unsigned nz = __ballot_sync(FULL, (probe.x | probe.y | probe.z | probe.w) != 0u);
 #pragma unroll
   for (int q = 0; q < KQ; ++q) {
-    uint4 a[4], b[4];
+    if (((nz >> q) & 0x01010101u) == 0u) continue;           // no row of this warp has anything in quad q
+    uint4 b[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) b[c] = st.b(q, tx + 32 * c);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      a[r] = st.a(q, ty + 16 * r);
-      b[r] = st.b(q, tx + 16 * r);
-    }
+      if (!((nz >> (8 * r + q)) & 1u)) continue;
+      const uint4 a = st.a(q, ty + 16 * r);
 #pragma unroll
-    for (int ri = 0; ri < 4; ++ri) {
-      // masklets are mostly background: an all-zero quad of row i contributes nothing to any of its pairs (the carry-save
-      // state is unchanged by zero inputs), so skip its 4 compressor chains.  The 16 lanes that share `ty` agree on this.
-      if ((a[ri].x | a[ri].y | a[ri].z | a[ri].w) == 0u) continue;
-#pragma unroll
-      for (int rj = 0; rj < 4; ++rj) {
-        if (DIAG && rj < ri) continue;                 // mirror entry is produced by another (ri, rj)
-        csa_quad(acc.c[ri][rj], a[ri], b[rj]);
-      }
+      for (int c = 0; c < 2; ++c)
+        if (k2_block_needed(DIAG, r, c)) csa_quad(acc.c[r][c], a, b[c]);
     }
   }
 }
@@ -125,14 +134,14 @@ __device__ __forceinline__ void consume_stage(const Stage& st, int tx, int ty, K
 template <bool DIAG>
 __device__ __forceinline__ void store_tile(const K2Acc& acc, int N, int ti, int tj, int tx, int ty, unsigned long long* __restrict__ inter) {
 #pragma unroll
-  for (int ri = 0; ri < 4; ++ri)
+  for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int rj = 0; rj < 4; ++rj) {
-      if (DIAG && rj < ri) continue;
-      const int i = ti * PT + ty + 16 * ri, j = tj * PT + tx + 16 * rj;
+    for (int c = 0; c < 2; ++c) {
+      if (!k2_block_needed(DIAG, r, c)) continue;
+      const int i = ti * PT + ty + 16 * r, j = tj * PT + tx + 32 * c;
       if (i >= N || j >= N) continue;
-      if (DIAG && ri == rj && tx < ty) continue;       // lower half of the 16x16 diagonal blocks
-      const unsigned long long v = (unsigned long long)csa_total(acc.c[ri][rj]);
+      if (DIAG && j < i) continue;                     // below the diagonal: the mirror entry is produced by another thread
+      const unsigned long long v = (unsigned long long)csa_total(acc.c[r][c]);
       if (v == 0) continue;
       atomicAdd(inter + (long long)i * N + j, v);
       if (i != j) atomicAdd(inter + (long long)j * N + i, v);
@@ -155,7 +164,7 @@ __device__ __forceinline__ void st_tile_cpasync(const uint32_t* __restrict__ pac
                                                 long long words, int ti, int tj, long long s_first, long long s_step, long long n_st, uint4* smem,
                                                 unsigned long long* __restrict__ inter) {
   constexpr int ROWS = DIAG ? PT : 2 * PT;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   K2Acc acc;
   acc.clear();
   // stage loader: ROWS*KQ 16-byte copies, thread t copies (row = c / KQ, q = c % KQ) for c = t, t+256, ...
@@ -207,8 +216,8 @@ pair_iou_st_kernel(const uint32_t* __restrict__ packed, const uint32_t* const* _
 
 // ---- TMA-staged, warp-specialised ring (default) ---------------------------------------------------------------------------------
 // The (rows x 32 words) stage tiles are regular, so they are fetched by the TMA unit: a rank-2 tensor map over packed[N][words]
-// (uint32), box = 32 words x 64 rows = 8 KB, SWIZZLE_128B, hardware zero fill for rows >= N and for the K tail.  A 9th warp's elected
-// lane is the producer (arms the stage's `full` mbarrier with the byte count, issues `cp.async.bulk.tensor.2d`); the 8 consumer
+// (uint32), box = 32 words x 64 rows = 8 KB, SWIZZLE_128B, hardware zero fill for rows >= N and for the K tail.  A 17th warp's elected
+// lane is the producer (arms the stage's `full` mbarrier with the byte count, issues `cp.async.bulk.tensor.2d`); the 16 consumer
 // warps hand each stage buffer back through an `empty` mbarrier (one arrive per warp), so there is no CTA-wide barrier in the stage
 // loop and a warp that skipped many all-zero quads runs up to NSTAGE-1 stages ahead of its slowest sibling.
 constexpr int RING_THREADS = ST_THREADS + 32;
@@ -224,14 +233,14 @@ __device__ __forceinline__ void st_tile_ring(LoadStage load_stage, int N, int ti
     if (tid == ST_THREADS) {
       for (long long s = 0; s < n_st; ++s) {
         const int buf = (int)(s % NSTAGE);
-        if (s >= NSTAGE) mbar_wait(empty + buf, (unsigned)(((s / NSTAGE) - 1) & 1));     // all 8 warps have left this buffer
+        if (s >= NSTAGE) mbar_wait(empty + buf, (unsigned)(((s / NSTAGE) - 1) & 1));     // all 16 consumer warps have left this buffer
         mbar_expect_tx(full + buf, DIAG ? TMA_BOX_BYTES : 2 * TMA_BOX_BYTES);
         load_stage(smem + (size_t)buf * 2 * TMA_BOX_BYTES, (int)((sw.first + s * sw.step) * STAGE_WORDS), full + buf);
       }
     }
     return;
   }
-  const int tx = tid & 15, ty = tid >> 4, lane = tid & 31;
+  const int tx = tid & 31, ty = tid >> 5, lane = tx;
   K2Acc acc;
   acc.clear();
   for (long long s = 0; s < n_st; ++s) {
@@ -286,7 +295,7 @@ pair_iou_st_ring_kernel(const __grid_constant__ CUtensorMap map, int N, long lon
 // One kernel that is both the exchange and the math of BASELINE config 5: every rank's packed planes sit in an NVLink-mapped buffer
 // (n_local tracks x words), one rank-2 tensor map per rank; the producer lane splits each 64-row operand tile into pieces of
 // `box_rows` rows (a divisor of 64 and of n_local, so a piece never straddles two ranks) and issues one `cp.async.bulk.tensor.2d`
-// per piece against the owner's map — the TMA unit pulls the rows over NVLink while the 8 consumer warps reduce the previous stages.
+// per piece against the owner's map — the TMA unit pulls the rows over NVLink while the 16 consumer warps reduce the previous stages.
 // Rows beyond a rank's n_local (and the K tail) are zero-filled by the hardware and still count towards the stage's byte total.
 struct PeerMaps { CUtensorMap m[8]; };
 
