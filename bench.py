@@ -67,6 +67,7 @@ def parse():
                          "Measured (profiles/r3_overlap_experiment.json): 3.50 vs 3.63 ms per step, but K1+R1 slows from 2.93 to 3.49 ms because "
                          "K2's two 288-thread, 96-register CTAs per SM displace the five K1+R1 CTAs it needs for its loads in flight; off by default")
     ap.add_argument("--no-aux", action="store_true", help="issue every kernel of a step on one stream (no R2 beside K1+R1, no gather / labels beside K2)")
+    ap.add_argument("--r2-late", action="store_true", help="issue R2 with the gather / label counts beside K2 N x N instead of beside K1+R1")
     ap.add_argument("--no-jf", action="store_true", help="skip the config-4 J&F sweep region")
     ap.add_argument("--no-cfg5", action="store_true", help="skip the config-5 exchange slice (N > 1 only)")
     ap.add_argument("--jf-reps", type=int, default=20)
@@ -161,7 +162,7 @@ class ClockSampler:
 # the step (product path)
 # ---------------------------------------------------------------------------------------------------------------
 class Workload:
-    def __init__(self, device, seed, n_tracks, n_frames, fused=True, st_native=False, overlap=False, aux=True):
+    def __init__(self, device, seed, n_tracks, n_frames, fused=True, st_native=False, overlap=False, aux=True, r2_late=False):
         import sola_b200 as S
         from sola_b200 import synth
         self.fused = fused
@@ -172,6 +173,7 @@ class Workload:
         self.tail_stream = torch.cuda.Stream(device=device, priority=-1) if self.overlap else None
         # within a video: R2 runs beside K1+R1, K2 gather + label counts beside K2 N x N (they only share read-only inputs)
         self.aux_stream = torch.cuda.Stream(device=device) if aux else None
+        self.r2_late = r2_late
         self.S, self.device = S, device
         self.N, self.T, self.H, self.W = n_tracks, n_frames, CFG["H"], CFG["W"]
         self.logits, prompts = synth.dedup_candidates(self.N, self.T, self.H, self.W, seed=seed, device=device, bin_size=CFG["bin_size"])
@@ -210,7 +212,7 @@ class Workload:
         S = self.S
         b = slot % len(self.slot_packed)
         out_p, out_c, out_r = self.slot_packed[b], self.slot_counts[b], self.slot_resized[b]
-        if self.aux_stream is not None:
+        if self.aux_stream is not None and not self.r2_late:
             job.enqueue_prompts(prompt_masks, (self.oh, self.ow))                                         # R2, beside K1+R1
         # the dominant kernel is the first launch of the step: bracket it with events on the launching stream
         if record_k1:
@@ -594,7 +596,7 @@ def main():
     cpus = sharding.bind_to_gpu_cpus(local_rank) if (world > 1 and not os.environ.get("SOLA_BENCH_NO_AFFINITY")) else []
 
     w = Workload(device, seed=1234 + 2 + 1000 * rank, n_tracks=n_tracks, n_frames=n_frames, fused=not args.no_fuse, st_native=args.st_native,
-                 overlap=args.overlap, aux=not args.no_aux)
+                 overlap=args.overlap, aux=not args.no_aux, r2_late=args.r2_late)
     w.make_jobs()
     torch.cuda.synchronize()
 

@@ -13,6 +13,7 @@
 //   * bit-packed planes: batched (Na tracks x Nb objects x T frames) and ragged (a J&F sweep over units of
 //     different shape, concatenated) variants.
 #include "common.cuh"
+#include "csa.cuh"
 
 namespace sola {
 
@@ -132,46 +133,75 @@ static int launch_raw_counts(const T* a, const T* b, long long n_frames, long lo
 }
 
 // ---- packed planes, batched: inter[Na][Nb][T], area_a[Na][T], area_b[Nb][T] ----------------------------------
-constexpr int NB_TILE = 4;
+constexpr int NB_TILE = 4;     // objects (B planes) per CTA
+constexpr int NA_TILE = 2;     // tracks (A planes) per CTA: every B word fetched from L2 serves NA_TILE tracks
+#ifndef LABEL_MIN_CTAS
+#define LABEL_MIN_CTAS 4
+#endif
 
-// The kernel is POPC-bound (xu pipe: 16 lanes/clk/SM), so it only counts what is stored: |b| once per (object, frame) — by the
-// CTAs of the first track —, nothing for tile slots past Nb, and |a| once per (track, frame) — by the first object tile.  The
-// choices are CTA-uniform and COMPILED in (template flags): a predicated-off POPC still occupies the xu pipe (measured: predication
-// alone left the pipe 85 % busy at 7 POPC slots per word instead of 4).
+// CTA = one frame x NA_TILE tracks x up to NB_TILE objects.  History of the bound: plain POPCs made it xu-pipe bound (16 lanes/clk/SM;
+// a predicated-off POPC still occupies the pipe, so the live-slot choices are COMPILED in as template flags), carry-save counters
+// (csa.cuh) moved that work to the alu pipe, and what remained was L2 traffic — with one track per CTA every track word pulled
+// NK object words out of L2 (4 words moved per word counted), hence the track tile.  |b| is stored once per (object, frame) — by the
+// CTAs of the first track tile, with plain POPCs —, |a| once per (track, frame) — by the first object tile.
 template <int VEC, int NK, bool WANT_A, bool WANT_B>
-__device__ __forceinline__ void packed_count_loop(const uint32_t* __restrict__ pa, const uint32_t* const (&pb)[NB_TILE], int FW,
-                                                  int& acca, int (&acc)[NB_TILE], int (&accb)[NB_TILE]) {
-  if (VEC == 4) {                                  // planes 16-byte aligned, FW % 4 == 0: 128-bit loads, up to 5 in flight per iteration
+__device__ __forceinline__ void packed_count_loop(const uint32_t* const (&pa)[NA_TILE], const uint32_t* const (&pb)[NB_TILE], int FW,
+                                                  int (&acca)[NA_TILE], int (&acc)[NA_TILE][NB_TILE], int (&accb)[NB_TILE]) {
+  if (VEC == 4) {                                  // planes 16-byte aligned, FW % 4 == 0: 128-bit loads, NA_TILE + NK in flight per iteration
     const int nq = FW >> 2;
+    Csa ca[NA_TILE], ci[NA_TILE][NK];
+#pragma unroll
+    for (int i = 0; i < NA_TILE; ++i) {
+      ca[i] = Csa{0u, 0u, 0};
+#pragma unroll
+      for (int k = 0; k < NK; ++k) ci[i][k] = Csa{0u, 0u, 0};
+    }
     for (int q = threadIdx.x; q < nq; q += blockDim.x) {
-      const uint4 x = __ldg(reinterpret_cast<const uint4*>(pa) + q);
-      uint4 y[NK];
+      uint4 x[NA_TILE], y[NK];
+#pragma unroll
+      for (int i = 0; i < NA_TILE; ++i) x[i] = __ldg(reinterpret_cast<const uint4*>(pa[i]) + q);
 #pragma unroll
       for (int k = 0; k < NK; ++k) y[k] = __ldg(reinterpret_cast<const uint4*>(pb[k]) + q);
-      if (WANT_A) acca += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
 #pragma unroll
-      for (int k = 0; k < NK; ++k) {
-        acc[k] += __popc(x.x & y[k].x) + __popc(x.y & y[k].y) + __popc(x.z & y[k].z) + __popc(x.w & y[k].w);
-        if (WANT_B) accb[k] += __popc(y[k].x) + __popc(y[k].y) + __popc(y[k].z) + __popc(y[k].w);
+      for (int i = 0; i < NA_TILE; ++i) {
+        if (WANT_A) csa_add4(ca[i], x[i].x, x[i].y, x[i].z, x[i].w);
+#pragma unroll
+        for (int k = 0; k < NK; ++k) csa_quad(ci[i][k], x[i], y[k]);
       }
+      if (WANT_B) {
+#pragma unroll
+        for (int k = 0; k < NK; ++k) accb[k] += __popc(y[k].x) + __popc(y[k].y) + __popc(y[k].z) + __popc(y[k].w);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NA_TILE; ++i) {
+      if (WANT_A) acca[i] += csa_total(ca[i]);
+#pragma unroll
+      for (int k = 0; k < NK; ++k) acc[i][k] += csa_total(ci[i][k]);
     }
   } else {
     for (int w = threadIdx.x; w < FW; w += blockDim.x) {
-      const uint32_t x = pa[w];
-      if (WANT_A) acca += __popc(x);
+      uint32_t y[NK];
 #pragma unroll
       for (int k = 0; k < NK; ++k) {
-        const uint32_t y = pb[k][w];
-        acc[k] += __popc(x & y);
-        if (WANT_B) accb[k] += __popc(y);
+        y[k] = pb[k][w];
+        if (WANT_B) accb[k] += __popc(y[k]);
+      }
+#pragma unroll
+      for (int i = 0; i < NA_TILE; ++i) {
+        const uint32_t x = pa[i][w];
+        if (WANT_A) acca[i] += __popc(x);
+#pragma unroll
+        for (int k = 0; k < NK; ++k) acc[i][k] += __popc(x & y[k]);
       }
     }
   }
 }
 
 template <int VEC, int NK>
-__device__ __forceinline__ void packed_count_dispatch(bool want_a, bool want_b, const uint32_t* __restrict__ pa, const uint32_t* const (&pb)[NB_TILE],
-                                                      int FW, int& acca, int (&acc)[NB_TILE], int (&accb)[NB_TILE]) {
+__device__ __forceinline__ void packed_count_dispatch(bool want_a, bool want_b, const uint32_t* const (&pa)[NA_TILE],
+                                                      const uint32_t* const (&pb)[NB_TILE], int FW, int (&acca)[NA_TILE],
+                                                      int (&acc)[NA_TILE][NB_TILE], int (&accb)[NB_TILE]) {
   if (want_a) {
     if (want_b) packed_count_loop<VEC, NK, true, true>(pa, pb, FW, acca, acc, accb);
     else packed_count_loop<VEC, NK, true, false>(pa, pb, FW, acca, acc, accb);
@@ -182,45 +212,67 @@ __device__ __forceinline__ void packed_count_dispatch(bool want_a, bool want_b, 
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, LABEL_MIN_CTAS)
 packed_counts_kernel(const uint32_t* __restrict__ A, const uint32_t* __restrict__ B, int Na, int Nb, int T, int FW,
                      int* __restrict__ inter, int* __restrict__ area_a, int* __restrict__ area_b) {
-  const int t = blockIdx.x % T, ia = blockIdx.x / T;
+  const int t = blockIdx.x % T, ia0 = (blockIdx.x / T) * NA_TILE;
   const int jb0 = blockIdx.y * NB_TILE;
   const int nk = min(NB_TILE, Nb - jb0);                 // live object slots of this tile (CTA-uniform)
-  const bool want_b = ia == 0, want_a = blockIdx.y == 0; // CTA-uniform
-  const uint32_t* pa = A + ((long long)ia * T + t) * FW;
+  const bool want_b = ia0 == 0, want_a = blockIdx.y == 0; // CTA-uniform
+  const uint32_t* pa[NA_TILE];
   const uint32_t* pb[NB_TILE];
 #pragma unroll
+  for (int i = 0; i < NA_TILE; ++i) pa[i] = A + ((long long)min(ia0 + i, Na - 1) * T + t) * FW;     // past Na: the last track again, not stored
+#pragma unroll
   for (int k = 0; k < NB_TILE; ++k) pb[k] = B + ((long long)min(jb0 + k, Nb - 1) * T + t) * FW;
-  int acc[NB_TILE] = {0, 0, 0, 0}, accb[NB_TILE] = {0, 0, 0, 0}, acca = 0;
+  int acc[NA_TILE][NB_TILE], accb[NB_TILE] = {0, 0, 0, 0}, acca[NA_TILE];
+#pragma unroll
+  for (int i = 0; i < NA_TILE; ++i) {
+    acca[i] = 0;
+#pragma unroll
+    for (int k = 0; k < NB_TILE; ++k) acc[i][k] = 0;
+  }
   switch (nk) {
     case 1: packed_count_dispatch<VEC, 1>(want_a, want_b, pa, pb, FW, acca, acc, accb); break;
     case 2: packed_count_dispatch<VEC, 2>(want_a, want_b, pa, pb, FW, acca, acc, accb); break;
     case 3: packed_count_dispatch<VEC, 3>(want_a, want_b, pa, pb, FW, acca, acc, accb); break;
     default: packed_count_dispatch<VEC, 4>(want_a, want_b, pa, pb, FW, acca, acc, accb); break;
   }
-  __shared__ int red[2 * NB_TILE + 1][8];
+  constexpr int NRED = NA_TILE * NB_TILE + NB_TILE + NA_TILE;      // [i][k] intersections, |b_k|, |a_i|
+  __shared__ int red[NRED][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  acca = warp_sum(acca);
 #pragma unroll
-  for (int k = 0; k < NB_TILE; ++k) { acc[k] = warp_sum(acc[k]); accb[k] = warp_sum(accb[k]); }
+  for (int i = 0; i < NA_TILE; ++i) {
+    acca[i] = warp_sum(acca[i]);
+#pragma unroll
+    for (int k = 0; k < NB_TILE; ++k) acc[i][k] = warp_sum(acc[i][k]);
+  }
+#pragma unroll
+  for (int k = 0; k < NB_TILE; ++k) accb[k] = warp_sum(accb[k]);
   if (lane == 0) {
-    red[2 * NB_TILE][warp] = acca;
 #pragma unroll
-    for (int k = 0; k < NB_TILE; ++k) { red[k][warp] = acc[k]; red[NB_TILE + k][warp] = accb[k]; }
+    for (int i = 0; i < NA_TILE; ++i) {
+      red[NA_TILE * NB_TILE + NB_TILE + i][warp] = acca[i];
+#pragma unroll
+      for (int k = 0; k < NB_TILE; ++k) red[i * NB_TILE + k][warp] = acc[i][k];
+    }
+#pragma unroll
+    for (int k = 0; k < NB_TILE; ++k) red[NA_TILE * NB_TILE + k][warp] = accb[k];
   }
   __syncthreads();
-  if (threadIdx.x < 2 * NB_TILE + 1) {
+  if (threadIdx.x < NRED) {
     int s = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
-    const int k = threadIdx.x;
-    if (k < NB_TILE) {
-      if (jb0 + k < Nb) inter[((long long)ia * Nb + jb0 + k) * T + t] = s;
-    } else if (k < 2 * NB_TILE) {
-      if (ia == 0 && jb0 + (k - NB_TILE) < Nb) area_b[(long long)(jb0 + k - NB_TILE) * T + t] = s;
-    } else if (blockIdx.y == 0) {
-      area_a[(long long)ia * T + t] = s;
+    const int e = threadIdx.x;
+    if (e < NA_TILE * NB_TILE) {
+      const int i = e / NB_TILE, k = e % NB_TILE;
+      if (ia0 + i < Na && jb0 + k < Nb) inter[((long long)(ia0 + i) * Nb + jb0 + k) * T + t] = s;
+    } else if (e < NA_TILE * NB_TILE + NB_TILE) {
+      const int k = e - NA_TILE * NB_TILE;
+      if (want_b && jb0 + k < Nb) area_b[(long long)(jb0 + k) * T + t] = s;
+    } else {
+      const int i = e - NA_TILE * NB_TILE - NB_TILE;
+      if (want_a && ia0 + i < Na) area_a[(long long)(ia0 + i) * T + t] = s;
     }
   }
 }
@@ -311,7 +363,7 @@ int sola_frame_counts_packed(const uint32_t* a, const uint32_t* b, int Na, int N
                "frame_counts_packed: bad shape Na=%d Nb=%d T=%d frame_words=%lld", Na, Nb, T, frame_words);
   if (Na == 0 || Nb == 0 || T == 0) return SOLA_OK;
   SOLA_REQUIRE((long long)Na * T < (1ll << 31) && (Nb + NB_TILE - 1) / NB_TILE <= 65535, "frame_counts_packed: grid too large");
-  dim3 grid((unsigned)((long long)Na * T), (unsigned)((Nb + NB_TILE - 1) / NB_TILE));
+  dim3 grid((unsigned)((long long)((Na + NA_TILE - 1) / NA_TILE) * T), (unsigned)((Nb + NB_TILE - 1) / NB_TILE));
   if (frame_words % 4 == 0 && aligned16(a) && aligned16(b))
     packed_counts_kernel<4><<<grid, 256, 0, stream>>>(a, b, Na, Nb, T, (int)frame_words, inter, area_a, area_b);
   else

@@ -17,6 +17,7 @@
 //     registers; diagonal tiles stage their 64 rows once and skip the blocks below the diagonal;
 //   * partial sums leave the CTA as 64-bit atomics on the N x N output (a few hundred adds per address).
 #include "tma.cuh"
+#include "csa.cuh"
 #include <cuda.h>
 #include <stdlib.h>          // CUtensorMap + enums only; the encoder is fetched at run time through cudaGetDriverEntryPoint
 
@@ -33,39 +34,6 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
-
-// Carry-save accumulation (Harley-Seal): POPC issues at 16 lanes/clk/SM on sm_100 (measured, profiles/r1_microbench_int_b200.jsonl)
-// against 64 for LOP3, so the plain AND+POPC+IADD loop is POPC-bound.  Per pair we keep bit-sliced counters `ones`, `twos`
-// and feed the four AND-ed words of a k-quad through three 3:2 compressors; only the weight-4 carry word is popcounted:
-//   4 AND + 6 LOP3 + 1 POPC per 4 words  (2.5 alu ops and 0.25 POPC per word instead of 1 and 1).
-// The compressors are written as explicit 3-input LOP3s (majority 0xE8, parity 0x96): left to itself the compiler fuses the ANDs
-// into a chain of half adders (a ^ (b & c), a & b & c, or) that costs 12 LOP3 per quad instead of 10.  (A hybrid that sends some
-// k-quads down the plain POPC route to use the idle POPC pipe measured 3-5 % slower, profiles/r1_k2_variants.jsonl.)
-// total = acc + 2 * popc(twos) + popc(ones).
-struct Csa { uint32_t ones, twos; int acc; };
-
-__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t r;
-  asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-  return r;
-}
-__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t r;
-  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-  return r;
-}
-
-__device__ __forceinline__ void csa_quad(Csa& st, const uint4& a, const uint4& b) {
-  const uint32_t x0 = a.x & b.x, x1 = a.y & b.y, x2 = a.z & b.z, x3 = a.w & b.w;
-  const uint32_t t1 = lop3_maj(st.ones, x0, x1), s1 = lop3_xor3(st.ones, x0, x1);
-  const uint32_t t2 = lop3_maj(s1, x2, x3);
-  st.ones = lop3_xor3(s1, x2, x3);
-  const uint32_t f = lop3_maj(st.twos, t1, t2);
-  st.twos = lop3_xor3(st.twos, t1, t2);
-  st.acc = __popc(f) * 4 + st.acc;
-}
-
-__device__ __forceinline__ int csa_total(const Csa& st) { return st.acc + 2 * __popc(st.twos) + __popc(st.ones); }
 
 // tile list: (ti, tj) with ti <= tj, enumerated row-major over the upper triangle
 __device__ __forceinline__ void tile_from_index(int idx, int nt, int& ti, int& tj) {
@@ -395,20 +363,26 @@ pair_iou_gather_kernel(const uint32_t* __restrict__ tracks, const uint32_t* __re
   for (int k = 0; k < GT_TILE; ++k) pt[k] = tracks + ((long long)min(i0 + k, N - 1) * T + f) * FW;
   int ni[GT_TILE] = {0, 0, 0, 0}, na[GT_TILE] = {0, 0, 0, 0}, np = 0;
   if (VEC == 4) {
+    // carry-save counters (csa.cuh): 9 POPC per 16-byte quad instead of 36 — the kernel was POPC-bound (ncu r2: xu pipe 71 %)
     const int nq = FW >> 2;
-#pragma unroll 2
+    Csa cp{0u, 0u, 0}, ci[GT_TILE], ca[GT_TILE];
+#pragma unroll
+    for (int k = 0; k < GT_TILE; ++k) ci[k] = ca[k] = Csa{0u, 0u, 0};
     for (int q = threadIdx.x; q < nq; q += GT_THREADS) {
       const uint4 p = __ldg(reinterpret_cast<const uint4*>(pp) + q);
       uint4 t[GT_TILE];
 #pragma unroll
       for (int k = 0; k < GT_TILE; ++k) t[k] = __ldg(reinterpret_cast<const uint4*>(pt[k]) + q);
-      np += __popc(p.x) + __popc(p.y) + __popc(p.z) + __popc(p.w);
+      csa_add4(cp, p.x, p.y, p.z, p.w);
 #pragma unroll
       for (int k = 0; k < GT_TILE; ++k) {
-        ni[k] += __popc(p.x & t[k].x) + __popc(p.y & t[k].y) + __popc(p.z & t[k].z) + __popc(p.w & t[k].w);
-        na[k] += __popc(t[k].x) + __popc(t[k].y) + __popc(t[k].z) + __popc(t[k].w);
+        csa_quad(ci[k], p, t[k]);
+        csa_add4(ca[k], t[k].x, t[k].y, t[k].z, t[k].w);
       }
     }
+    np = csa_total(cp);
+#pragma unroll
+    for (int k = 0; k < GT_TILE; ++k) { ni[k] = csa_total(ci[k]); na[k] = csa_total(ca[k]); }
   } else {
     for (int w = threadIdx.x; w < FW; w += GT_THREADS) {
       const uint32_t p = pp[w];

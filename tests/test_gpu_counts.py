@@ -89,6 +89,22 @@ def test_unaligned_and_odd_sizes_take_scalar_path():
     np.testing.assert_array_equal(c[0], exp[0])
 
 
+@pytest.mark.parametrize("Na,Nb,T,H,W", [(3, 3, 2, 40, 128), (1, 1, 3, 16, 256), (7, 5, 2, 24, 96), (64, 3, 2, 54, 96), (2, 9, 1, 8, 130)])
+def test_packed_batched_counts_track_tiles(Na, Nb, T, H, W):
+    """The batched label counts tile the tracks (two per CTA) and the objects (four per CTA): odd counts on both axes, the 128-bit
+    path (frame words a multiple of 4) and the scalar one, all-zero and all-one planes."""
+    import sola_b200 as S
+    rng = np.random.default_rng(Na * 100 + Nb)
+    A = rng.random((Na, T, H, W)) > 0.55
+    B = rng.random((Nb, T, H, W)) > 0.45
+    A[0, 0] = True
+    B[-1, -1] = False
+    inter, area_a, area_b = S.frame_counts_packed(S.pack_masks(A), S.pack_masks(B))
+    np.testing.assert_array_equal(inter.cpu().numpy(), (A[:, None] & B[None]).sum((-2, -1)))
+    np.testing.assert_array_equal(area_a.cpu().numpy(), A.sum((-2, -1)))
+    np.testing.assert_array_equal(area_b.cpu().numpy(), B.sum((-2, -1)))
+
+
 def test_packed_batched_and_ragged_counts():
     import sola_b200 as S
     from sola_b200 import utils
