@@ -11,6 +11,9 @@ One step = one video's pass over the path, inputs already in HBM:
     M1     the J-type half the grid loop really runs: per-frame |track ∩ gt|, |track|, |gt| of every track against G = 3 GT masklets
            -> frame-mean precision / recall / IoU labels (generate_tokens_grid.py:253-264, utils.compute_mask_metrics)
     one D2H of the count tables -> float64 scores on the host (overlapped with the next step)
+Launches that only share read-only inputs run side by side on a second stream (dedup.VideoDedupJob(aux_stream=...)): R2 beside
+K1+R1, the K2 gather, the label counts and the read-backs beside K2 N x N; `--no-aux` issues everything on one stream, `--overlap`
+additionally puts the whole tail of video k under K1+R1 of video k+1 (measured slower for the dominant kernel; off).
 `value` = masklet-frames processed by all ranks / max-over-ranks device time (weak scaling: one video per GPU per step, no
 data-path collective).  `e2e` = the same step with the logits, prompt masks and GT masks starting in pinned HOST memory (H2D inside
 the timed region, results read back).
@@ -67,7 +70,6 @@ def parse():
                          "Measured (profiles/r3_overlap_experiment.json): 3.50 vs 3.63 ms per step, but K1+R1 slows from 2.93 to 3.49 ms because "
                          "K2's two 288-thread, 96-register CTAs per SM displace the five K1+R1 CTAs it needs for its loads in flight; off by default")
     ap.add_argument("--no-aux", action="store_true", help="issue every kernel of a step on one stream (no R2 beside K1+R1, no gather / labels beside K2)")
-    ap.add_argument("--r2-late", action="store_true", help="issue R2 with the gather / label counts beside K2 N x N instead of beside K1+R1")
     ap.add_argument("--no-jf", action="store_true", help="skip the config-4 J&F sweep region")
     ap.add_argument("--no-cfg5", action="store_true", help="skip the config-5 exchange slice (N > 1 only)")
     ap.add_argument("--jf-reps", type=int, default=20)
@@ -162,7 +164,7 @@ class ClockSampler:
 # the step (product path)
 # ---------------------------------------------------------------------------------------------------------------
 class Workload:
-    def __init__(self, device, seed, n_tracks, n_frames, fused=True, st_native=False, overlap=False, aux=True, r2_late=False):
+    def __init__(self, device, seed, n_tracks, n_frames, fused=True, st_native=False, overlap=False, aux=True):
         import sola_b200 as S
         from sola_b200 import synth
         self.fused = fused
@@ -173,7 +175,6 @@ class Workload:
         self.tail_stream = torch.cuda.Stream(device=device, priority=-1) if self.overlap else None
         # within a video: R2 runs beside K1+R1, K2 gather + label counts beside K2 N x N (they only share read-only inputs)
         self.aux_stream = torch.cuda.Stream(device=device) if aux else None
-        self.r2_late = r2_late
         self.S, self.device = S, device
         self.N, self.T, self.H, self.W = n_tracks, n_frames, CFG["H"], CFG["W"]
         self.logits, prompts = synth.dedup_candidates(self.N, self.T, self.H, self.W, seed=seed, device=device, bin_size=CFG["bin_size"])
@@ -181,7 +182,7 @@ class Workload:
         self.prompt_masks_host = np.stack([p["segmentation"] for p in prompts])                       # (N, H, W) uint8
         self.prompt_masks_dev = torch.from_numpy(self.prompt_masks_host).to(device)
         self.oh, self.ow = S.packed.default_target_shape(self.H, self.W)
-        n_slots = 2 if self.overlap else 1                                                            # reused outputs, one set per in-flight video
+        n_slots = 2 if (self.overlap or aux) else 1                                                            # reused outputs, one set per in-flight video
         self.slot_packed = [S.PackedMasks.empty((self.N, self.T), self.H, self.W, device) for _ in range(n_slots)]
         self.slot_counts = [torch.empty((3, self.N * self.T), dtype=torch.int32, device=device) for _ in range(n_slots)]
         self.slot_resized = [S.PackedMasks.empty((self.N, self.T), self.oh, self.ow, device) for _ in range(n_slots)]
@@ -212,7 +213,7 @@ class Workload:
         S = self.S
         b = slot % len(self.slot_packed)
         out_p, out_c, out_r = self.slot_packed[b], self.slot_counts[b], self.slot_resized[b]
-        if self.aux_stream is not None and not self.r2_late:
+        if self.aux_stream is not None:
             job.enqueue_prompts(prompt_masks, (self.oh, self.ow))                                         # R2, beside K1+R1
         # the dominant kernel is the first launch of the step: bracket it with events on the launching stream
         if record_k1:
@@ -596,7 +597,7 @@ def main():
     cpus = sharding.bind_to_gpu_cpus(local_rank) if (world > 1 and not os.environ.get("SOLA_BENCH_NO_AFFINITY")) else []
 
     w = Workload(device, seed=1234 + 2 + 1000 * rank, n_tracks=n_tracks, n_frames=n_frames, fused=not args.no_fuse, st_native=args.st_native,
-                 overlap=args.overlap, aux=not args.no_aux, r2_late=args.r2_late)
+                 overlap=args.overlap, aux=not args.no_aux)
     w.make_jobs()
     torch.cuda.synchronize()
 
@@ -755,7 +756,9 @@ def main():
                       "step time not covered by K1+R1 (tail not hidden + gaps)": max_ms / args.steps - k1_ms,
                       "streams": "2 (--overlap: tail of video k under K1+R1 of video k+1)"} if w.overlap else
                      {"dominant (K1+R1 fused)" if w.fused else "dominant (K1)": k1_ms, "K2 N x N (int pipe, carry-save, TMA-staged)": k2_ms,
-                      "everything else incl. label counts and gaps": max_ms / args.steps - k1_ms - k2_ms}),
+                      "everything else incl. label counts and gaps": max_ms / args.steps - k1_ms - k2_ms,
+                      "streams": ("2: R2 runs beside K1+R1; K2 gather, label counts and read-backs beside K2 N x N (both kernel times are "
+                                  "measured with those neighbours running)") if w.aux_stream is not None else "1"}),
         "gpu_launches": int(launches),
         "gpu_launches_jf_region": int(launches_jf),
         "e2e": e2e,
@@ -810,7 +813,7 @@ def main():
             if "roofline_jf" in line:       # the ncu target (tools/ncu_targets.py jf_region / jf_boundary) runs rank 0's sweep of this bench
                 line["roofline_jf"]["traffic"] = tj.get("jf_fused_kernel", {}).get("dram_bytes_per_launch")
                 line["roofline_jf_boundary"]["traffic"] = tj.get("jf_fused_kernel[boundary]", {}).get("dram_bytes_per_launch")
-    ncu_path = os.path.join(ROOT, "profiles", "r2_ncu_summary.json")                       # committed `ncu --set full` summaries
+    ncu_path = os.path.join(ROOT, "profiles", "r3_ncu_summary.json")                       # committed `ncu --set full` summaries
     if os.path.isfile(ncu_path) and "roofline_jf_boundary" in line:
         with open(ncu_path) as f:
             cap = json.load(f).get("jf_boundary", {})

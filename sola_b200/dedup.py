@@ -374,7 +374,6 @@ class VideoDedupJob:
             with torch.cuda.stream(aux):
                 resized.words.record_stream(aux)
                 side()
-                self._join.record(aux)
         # K2 N x N on the resized planes: after generate_tokens_grid.py:248-250 only the 540x960 masklets exist, so a
         # masklet-vs-masklet IoU (seg_utils.compute_masklet_iou) in that flow compares those
         if self.timing_events is not None:
@@ -384,13 +383,22 @@ class VideoDedupJob:
         if self.timing_events is not None:
             eb.record()
             self.timing_events.append((ea, eb))
-        hi.copy_(inter, non_blocking=True)
-        hc.copy_(counts.reshape(3, N, T), non_blocking=True)
         if aux is not None:
-            main.wait_event(self._join)
+            # the read-backs leave on the aux stream as well, so the launching stream goes straight from K2 to the next video's
+            # K1+R1; this job's outputs (resized planes, counts) must not be overwritten before finish() — callers alternate two sets
+            self._join.record(main)
+            aux.wait_event(self._join)
+            with torch.cuda.stream(aux):
+                inter.record_stream(aux)
+                counts.record_stream(aux)
+                hi.copy_(inter, non_blocking=True)
+                hc.copy_(counts.reshape(3, N, T), non_blocking=True)
+                self.event.record(aux)
         else:
+            hi.copy_(inter, non_blocking=True)
+            hc.copy_(counts.reshape(3, N, T), non_blocking=True)
             side()
-        self.event.record(main)
+            self.event.record(main)
         self.counts = counts
 
     def finish(self, miou_thresh_st: Optional[float] = None) -> dict:

@@ -3,13 +3,13 @@ the launch list of the bench's timed region, the `ncu --page raw` CSV of every f
 (`<tag>_ncu_summary.json`), and `dominant_kernel_traffic.json` — the DRAM traffic bench.py reports as roofline.traffic, stamped with the
 kernel's register count so that a stale entry is detectable (tests/test_profiles_consistency.py compares it with the built library, and
 this script FAILS if a capture's register count differs from the library's).
-usage: python tools/refresh_profiles.py [round-tag, default r2]"""
+usage: python tools/refresh_profiles.py [round-tag, default r2] [source directory under gpurun_out/, default = the tag]"""
 import csv, json, os, re, shutil, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
-G, P = os.path.join(ROOT, "gpurun_out", tag), os.path.join(ROOT, "profiles")
+G, P = os.path.join(ROOT, "gpurun_out", sys.argv[2] if len(sys.argv) > 2 else tag), os.path.join(ROOT, "profiles")
 
 KEYS = {
     "gpu__time_duration.sum": "duration",

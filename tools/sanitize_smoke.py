@@ -66,5 +66,17 @@ rle.decode_rle_masklets_merged([enc2, enc2])
 job.set_gt_masklets(S.pack_masks(torch.stack([synth.blob_masklet(8, 540, 960, 4 + k, device="cuda") for k in range(2)])))
 job.enqueue(logits.cuda(), torch.from_numpy(np.stack([p["segmentation"] for p in pr])).cuda())
 assert "labels" in job.finish()
+# region-only build of the J&F kernel on a mixed sweep (aligned and word-shifted planes), the job with its optional streams
+P.JFSweepPlan([(p_, g_) for _, _, p_, g_ in units], with_boundary=False).run()
+flat = torch.zeros(units[0][2].words.numel() + 1, dtype=torch.int32, device="cuda")
+flat[1:] = units[0][2].words.reshape(-1)
+P.jf_boundary_counts(P.PackedMasks(flat[1:].view(units[0][2].words.shape), units[0][2].H, units[0][2].W), units[0][3], with_boundary=False)
+job2 = dedup.VideoDedupJob([{"prompt_id": p["prompt_id"], "frame_idx": p["frame_idx"]} for p in pr], 8, mode="grid",
+                           aux_stream=torch.cuda.Stream(), tail_stream=torch.cuda.Stream(priority=-1))
+job2.set_gt_masklets(job.gt_planes)
+for _ in range(2):
+    job2.enqueue(logits.cuda(), torch.from_numpy(np.stack([p["segmentation"] for p in pr])).cuda())
+    assert "labels" in job2.finish()
+S.frame_counts_packed(tracks[:7], tracks[7:12])            # odd track count: the track tile's clamped slot
 torch.cuda.synchronize()
 print("sanitize smoke ok")
