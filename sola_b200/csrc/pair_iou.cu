@@ -363,26 +363,21 @@ pair_iou_gather_kernel(const uint32_t* __restrict__ tracks, const uint32_t* __re
   for (int k = 0; k < GT_TILE; ++k) pt[k] = tracks + ((long long)min(i0 + k, N - 1) * T + f) * FW;
   int ni[GT_TILE] = {0, 0, 0, 0}, na[GT_TILE] = {0, 0, 0, 0}, np = 0;
   if (VEC == 4) {
-    // carry-save counters (csa.cuh): 9 POPC per 16-byte quad instead of 36 — the kernel was POPC-bound (ncu r2: xu pipe 71 %)
+    // (carry-save counters were measured here too: 59 vs 54 us — at 4050 quads per plane the kernel is latency-bound, not POPC-bound)
     const int nq = FW >> 2;
-    Csa cp{0u, 0u, 0}, ci[GT_TILE], ca[GT_TILE];
-#pragma unroll
-    for (int k = 0; k < GT_TILE; ++k) ci[k] = ca[k] = Csa{0u, 0u, 0};
+#pragma unroll 2
     for (int q = threadIdx.x; q < nq; q += GT_THREADS) {
       const uint4 p = __ldg(reinterpret_cast<const uint4*>(pp) + q);
       uint4 t[GT_TILE];
 #pragma unroll
       for (int k = 0; k < GT_TILE; ++k) t[k] = __ldg(reinterpret_cast<const uint4*>(pt[k]) + q);
-      csa_add4(cp, p.x, p.y, p.z, p.w);
+      np += __popc(p.x) + __popc(p.y) + __popc(p.z) + __popc(p.w);
 #pragma unroll
       for (int k = 0; k < GT_TILE; ++k) {
-        csa_quad(ci[k], p, t[k]);
-        csa_add4(ca[k], t[k].x, t[k].y, t[k].z, t[k].w);
+        ni[k] += __popc(p.x & t[k].x) + __popc(p.y & t[k].y) + __popc(p.z & t[k].z) + __popc(p.w & t[k].w);
+        na[k] += __popc(t[k].x) + __popc(t[k].y) + __popc(t[k].z) + __popc(t[k].w);
       }
     }
-    np = csa_total(cp);
-#pragma unroll
-    for (int k = 0; k < GT_TILE; ++k) { ni[k] = csa_total(ci[k]); na[k] = csa_total(ca[k]); }
   } else {
     for (int w = threadIdx.x; w < FW; w += GT_THREADS) {
       const uint32_t p = pp[w];

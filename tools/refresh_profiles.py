@@ -32,13 +32,18 @@ KEYS = {
 SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 
 
+def _norm(name):
+    """c++filt prints bool template arguments as words, ncu as 0 / 1."""
+    return re.sub(r"\bfalse\b", "0", re.sub(r"\btrue\b", "1", name))
+
+
 def library_registers():
     from sola_b200 import _build
     res = subprocess.run(["cuobjdump", "-res-usage", _build.build()], capture_output=True, text=True).stdout
     out = {}
     for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+)", res):
         dn = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
-        out[re.sub(r"^void\s+", "", dn).split("(")[0]] = int(m.group(2))
+        out[_norm(re.sub(r"^void\s+", "", dn).split("(")[0])] = int(m.group(2))
     return out
 
 
@@ -76,7 +81,7 @@ def main():
         lines, s = summarise(os.path.join(G, f))
         with open(os.path.join(P, f"{tag}_ncu_{name}_raw.csv"), "w") as out:
             out.write("\n".join(lines) + "\n")
-        base = s["kernel"].split("(")[0]
+        base = _norm(re.sub(r"^void\s+", "", s["kernel"]).split("(")[0])
         lib_regs = next((r for k, r in regs.items() if k.replace("sola::", "") == base.replace("sola::", "")), None)
         s["library_registers"] = lib_regs
         if lib_regs is not None and "registers" in s and int(s["registers"]) != lib_regs:
