@@ -134,7 +134,8 @@ static int launch_raw_counts(const T* a, const T* b, long long n_frames, long lo
 
 // ---- packed planes, batched: inter[Na][Nb][T], area_a[Na][T], area_b[Nb][T] ----------------------------------
 constexpr int NB_TILE = 4;     // objects (B planes) per CTA
-constexpr int NA_TILE = 2;     // tracks (A planes) per CTA: every B word fetched from L2 serves NA_TILE tracks
+constexpr int NA_TILE = 2;     // tracks (A planes) per CTA: every B word fetched from L2 serves NA_TILE tracks (4 tracks need 96+
+                               // registers and measured slower, 89-112 vs 83 us: profiles/r3_build_constants.json)
 #ifndef LABEL_MIN_CTAS
 #define LABEL_MIN_CTAS 4
 #endif

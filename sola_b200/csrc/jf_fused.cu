@@ -28,6 +28,7 @@
 //            case when pred ≈ gt) stop after 7 rows.
 // Everything is exact integer arithmetic; pad bits (x >= W) stay zero through every step.
 #include "tma.cuh"
+#include "csa.cuh"
 #include "jf_unit.h"
 #include <string.h>
 
@@ -324,10 +325,14 @@ jf_fused_kernel(const sola_jf_unit* __restrict__ units, int n_units, const sola_
       if (q_hi > q_lo) {
         const uint4* P4 = reinterpret_cast<const uint4*>(rawP);
         const uint4* G4 = reinterpret_cast<const uint4*>(rawG);
+        // carry-save counters (csa.cuh): 3 POPC per 16-byte quad pair instead of 12 — the xu pipe was 58 % busy (ncu); +9 % on 360p
+        // frames, +2 % on the mixed sweep, neutral elsewhere (profiles/r3_build_constants.json)
+        Csa cp{0u, 0u, 0}, cg{0u, 0u, 0}, ci{0u, 0u, 0};
         for (int i = q_lo + tid; i < q_hi; i += JF_THREADS) {
           const uint4 p = P4[i], q = G4[i];
-          count(p.x, q.x); count(p.y, q.y); count(p.z, q.z); count(p.w, q.w);
+          csa_add4(cp, p.x, p.y, p.z, p.w); csa_add4(cg, q.x, q.y, q.z, q.w); csa_quad(ci, p, q);
         }
+        n_p += csa_total(cp); n_g += csa_total(cg); n_i += csa_total(ci);
         const int head = 4 * q_lo - off, tail = off + n_words - 4 * q_hi;          // 0..3 words each
         if (tid < head) count(rawP[off + tid], rawG[off + tid]);
         else if (tid >= 32 && tid - 32 < tail) count(rawP[4 * q_hi + tid - 32], rawG[4 * q_hi + tid - 32]);

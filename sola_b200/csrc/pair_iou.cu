@@ -26,7 +26,7 @@ namespace sola {
 constexpr int PT = 64;            // tile side (tracks)
 constexpr int KQ = 8;             // uint4 per row per stage -> 32 words = 128 B per row per stage
 constexpr int STAGE_WORDS = KQ * 4;
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = 4;         // ring depth; 5 and 6 stages measured 2 % slower with the 16-warp layout (profiles/r3_build_constants.json)
 constexpr int ST_THREADS = 512;   // consumer threads: 16 warps (ty) x 32 lanes (tx), each a strided 4 x 2 micro-tile of pairs
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
