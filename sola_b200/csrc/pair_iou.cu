@@ -26,6 +26,7 @@ namespace sola {
 constexpr int PT = 64;            // tile side (tracks)
 constexpr int KQ = 8;             // uint4 per row per stage -> 32 words = 128 B per row per stage
 constexpr int STAGE_WORDS = KQ * 4;
+constexpr int K2_CTAS_PER_SM_TOTAL = 4;   // CTAs launched per SM over all tiles (two are resident at a time); 2 / 6 / 8 measured the same within 1 %
 constexpr int NSTAGE = 4;         // ring depth; 5 and 6 stages measured 2 % slower with the 16-warp layout (profiles/r3_build_constants.json)
 constexpr int ST_THREADS = 512;   // consumer threads: 16 warps (ty) x 32 lanes (tx), each a strided 4 x 2 micro-tile of pairs
 
@@ -436,7 +437,7 @@ static int launch_pair_iou_st(const uint32_t* packed, int N, long long words_per
     const int n_tiles = (all_tiles - part + n_parts - 1) / n_parts;          // tiles part, part + n_parts, ...
     if (n_tiles > 0) {
       const long long stages = (words_per_track + STAGE_WORDS - 1) / STAGE_WORDS;
-      long long splits = ((long long)num_sms() * 4 + n_tiles - 1) / n_tiles;
+      long long splits = ((long long)num_sms() * K2_CTAS_PER_SM_TOTAL + n_tiles - 1) / n_tiles;
       if (splits > stages) splits = stages;
       const long long min_splits = (stages + (1 << 20) - 1) >> 20;     // keep int32 partial sums (4 * acc4 + ...) below 2^31
       if (splits < min_splits) splits = min_splits;
@@ -500,7 +501,7 @@ int sola_pair_iou_st_rows(const uint32_t* const* row_ptrs, int N, long long word
   const long long stage_lo = all_stages * part / n_parts, stage_hi = all_stages * (part + 1) / n_parts;
   const long long stages = stage_hi - stage_lo;
   if (stages <= 0) return SOLA_OK;
-  long long splits = ((long long)num_sms() * 4 + n_tiles - 1) / n_tiles;
+  long long splits = ((long long)num_sms() * K2_CTAS_PER_SM_TOTAL + n_tiles - 1) / n_tiles;
   if (splits > stages) splits = stages;
   const long long min_splits = (stages + (1 << 20) - 1) >> 20;
   if (splits < min_splits) splits = min_splits;
@@ -550,7 +551,7 @@ int sola_pair_iou_st_peer(const uint32_t* const* bases_host, int world, int n_lo
   const long long stage_lo = all_stages * part / n_parts, stage_hi = all_stages * (part + 1) / n_parts;
   const long long stages = stage_hi - stage_lo;
   if (stages <= 0) return SOLA_OK;
-  long long splits = ((long long)num_sms() * 4 + n_tiles - 1) / n_tiles;
+  long long splits = ((long long)num_sms() * K2_CTAS_PER_SM_TOTAL + n_tiles - 1) / n_tiles;
   if (splits > stages) splits = stages;
   const long long min_splits = (stages + (1 << 20) - 1) >> 20;
   if (splits < min_splits) splits = min_splits;
