@@ -191,7 +191,8 @@ typedef struct sola_jf_unit {
 typedef struct sola_jf_plan {
   long long n_items, total_frames;      /* work items (frame x row band) and output columns of the sweep */
   int raw_cap, bm_cap, mask_steps;      /* shared-memory layout of the launch */
-  int reserved;                         /* in: 0 (automatic) or the CTAs per SM to plan for (1..3); out: the class chosen */
+  int reserved;                         /* in: 0 (automatic) or the CTAs per SM to plan for (1..3); out: the class chosen — 4 = the
+                                           region-only build (every unit has radius < 0: small tiles, four CTAs per SM) */
 } sola_jf_plan;           /* 32 bytes */
 /* host-only: plans the row-band split of every unit (HOST array, updated in place) and the launch's shared-memory layout */
 int sola_jf_sweep_plan(sola_jf_unit* units_host, int n_units, sola_jf_plan* plan_out);

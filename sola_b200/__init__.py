@@ -9,5 +9,5 @@ from .packed import (PackedMasks, binarize_pack_stability, binarize_pack_resize,
                      frame_counts_packed, pairwise_inter_matrix, gathered_inter, resize_bilinear_bin,
                      resize_nearest, or_merge, boundary_counts, jf_boundary_counts, JFSweepPlan)
 
-__version__ = "0.2.0"
+__version__ = "0.2.1"
 from .api import pairwise_iou_matrix, gathered_iou, greedy_filter, jf_batch  # noqa: F401,E402

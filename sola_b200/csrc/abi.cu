@@ -30,7 +30,7 @@ int check_launch(const char* what) {
 extern "C" {
 
 // major*10000 + minor*100 + patch
-int sola_version(void) { return 200; }
+int sola_version(void) { return 201; }
 
 const char* sola_last_error_string(void) { return sola::g_err; }
 
