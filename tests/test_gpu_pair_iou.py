@@ -35,6 +35,25 @@ def test_pairwise_matrix_vs_numpy(N, T, H, W):
     assert abs(iou[1, 2] - ref) < 1e-6
 
 
+@pytest.mark.parametrize("N,words,p_zero", [(64, 1000, 0.7), (70, 36, 0.5), (129, 260, 0.9), (200, 68, 0.0), (16, 4100, 0.97)])
+def test_pairwise_zero_quad_skipping(N, words, p_zero):
+    """The N x N kernel skips all-zero 16-byte operand quads per (row, quad), decided once per warp by a ballot: planes whose quads are
+    zeroed at random (and whole rows / whole stages of zeros) must give the exact matrix — diagonal and off-diagonal tiles, a K tail that
+    is not a multiple of the 32-word stage, every skip pattern inside a stage."""
+    import sola_b200 as S
+    rng = np.random.default_rng(N * 7 + words)
+    w = rng.integers(0, 2**32, size=(N, words), dtype=np.uint64).astype(np.uint32)
+    quads = (words + 3) // 4
+    keep = rng.random((N, quads)) >= p_zero
+    keep[1] = False                                            # a track with no pixel at all
+    keep[:, quads // 2: quads // 2 + 9] = False               # whole stages of zeros for every track
+    w *= np.repeat(keep, 4, axis=1)[:, :words].astype(np.uint32)
+    bits = np.unpackbits(w.view(np.uint8).reshape(N, -1), axis=1, bitorder="little").astype(np.int64)
+    exp = bits @ bits.T
+    got = S.packed.pairwise_inter_matrix_words(torch.from_numpy(w.view(np.int32)).cuda()).cpu().numpy()
+    np.testing.assert_array_equal(got, exp)
+
+
 def test_pairwise_unaligned_rows_fallback():
     import sola_b200 as S
     rng = np.random.default_rng(1)
