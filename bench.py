@@ -452,17 +452,8 @@ def jf_region(device, rank, world, reps, peak):
             plan.run(buf)
             host.copy_(buf, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            c = host.numpy()
-            Js, Fs, Fbs = [], [], []
-            tot = np.zeros(3, np.int64)
-            for k in range(plan.n_units):
-                u = c[:, plan.offsets[k]: plan.offsets[k] + plan.frames[k]]
-                Js.append(float(evaluator.J_from_counts(u[0], u[1], u[2])))
-                Fs.append(float(evaluator.F_from_counts(u[0], u[1], u[2])))
-                if with_boundary:
-                    Fbs.append(evaluator.F_boundary_from_counts(u[3], u[4], u[5], u[6]))
-                tot += u[:3].sum(axis=1, dtype=np.int64)
-            return Js, Fs, Fbs, tot
+            J, F, Fb, tot = evaluator.sweep_metrics_from_counts(host.numpy(), plan.offsets, plan.frames, with_boundary)
+            return J.tolist(), F.tolist(), (Fb.tolist() if with_boundary else []), tot
 
         for _ in range(3):
             Js, Fs, Fbs, tot = sweep_once()

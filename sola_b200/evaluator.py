@@ -50,6 +50,54 @@ def F_boundary_from_counts(n_fg, n_gt, fg_match, gt_match) -> float:
     return float(np.mean(f))
 
 
+def sweep_metrics_from_counts(counts, offsets, frames, with_boundary: bool = False):
+    """The three formulas above for EVERY unit of a sweep at once.  counts: (7, total_frames) host array as the fused kernel writes
+    it; unit u occupies columns offsets[u] : offsets[u] + frames[u].  Returns (J, F, F_boundary | None, int_totals) — float64 arrays of
+    one value per unit, bit-equal to calling J_from_counts / F_from_counts / F_boundary_from_counts unit by unit: the per-frame ratios
+    are elementwise float64 operations (evaluated here in one pass over all frames), the volume sums are exact integers
+    (np.add.reduceat), and the per-unit frame means still go through np.mean on the unit's own contiguous slice, so the summation
+    order is the reference's.  A per-unit Python loop over small arrays costs 25-45 us per unit — more than the kernel's share."""
+    c = np.asarray(counts)
+    offsets = np.asarray(offsets, dtype=np.int64)
+    frames = np.asarray(frames, dtype=np.int64)
+    n = len(frames)
+    J, F = np.zeros(n, np.float64), np.zeros(n, np.float64)
+    Fb = np.zeros(n, np.float64) if with_boundary else None
+    live = np.nonzero(frames > 0)[0]
+    i, p, g = (c[k].astype(np.int64) for k in range(3))
+    union = p + g - i
+    with np.errstate(divide="ignore", invalid="ignore"):
+        Js = np.where(union == 0, 1.0, i / np.where(union == 0, 1, union))
+        if with_boundary:
+            a, b, fm, gm = (c[k].astype(np.int64) for k in range(3, 7))
+            pr = np.where(a == 0, 1.0, np.where(b == 0, 0.0, fm / np.where(a == 0, 1, a)))
+            rc = np.where(a == 0, np.where(b == 0, 1.0, 0.0), np.where(b == 0, 1.0, gm / np.where(b == 0, 1, b)))
+            fb = np.where(pr + rc == 0, 0.0, 2 * pr * rc / np.where(pr + rc == 0, 1.0, pr + rc))
+    sums = np.zeros((3, n), np.int64)
+    if len(live):
+        # reduceat needs strictly usable start indices: reduce over the live units only (empty units keep sum 0)
+        order = live[np.argsort(offsets[live], kind="stable")]
+        starts = offsets[order]
+        assert np.all(starts[1:] >= starts[:-1] + frames[order][:-1]) and starts[-1] + frames[order][-1] <= c.shape[1], "units overlap / exceed the table"
+        contiguous = np.all(starts[1:] == starts[:-1] + frames[order][:-1])
+        for k, v in enumerate((i, p, g)):
+            if contiguous:
+                sums[k, order] = np.add.reduceat(v[: starts[-1] + frames[order][-1]], starts)
+            else:
+                sums[k, order] = [int(v[s: s + t].sum()) for s, t in zip(starts, frames[order])]
+    tp, fp, fn = sums[0], sums[1] - sums[0], sums[2] - sums[0]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tpf = tp.astype(np.float64)                       # exact: volume sums < 2**53
+        prec, rec = tpf / (tp + fp), tpf / (tp + fn)
+        F = np.where(tp == 0, 0.0, 2 * prec * rec / (prec + rec))
+    for u in range(n):
+        o, t = int(offsets[u]), int(frames[u])
+        J[u] = np.mean(Js[o: o + t]) if t else np.float64("nan")
+        if with_boundary:
+            Fb[u] = np.mean(fb[o: o + t]) if t else np.float64("nan")
+    return J, F, Fb, sums.sum(axis=1)
+
+
 # ---- per-call drop-ins -----------------------------------------------------------------------------------------
 
 _last_counts = None       # (key, counts): the reference calls compute_J then compute_F on the SAME two tensors (evaluator.py:201-202)
@@ -159,20 +207,17 @@ class JFSweep:
         live = [pg for pg in self._pairs if pg is not None]
         plan = P.JFSweepPlan(live, with_boundary=self.with_boundary, bound_th=self.bound_th)
         flat = plan.run().cpu().numpy() if live else np.zeros((7, 0), np.int32)
+        Js, Fs, Fbs, totals = sweep_metrics_from_counts(flat, plan.offsets, plan.frames, self.with_boundary)
         results, k = [], 0
-        totals = np.zeros(3, dtype=np.int64)
         for key, pg in zip(self._keys, self._pairs):
             if pg is None:
                 results.append((key, {"J": 0.0, "F": 0.0, "JF": 0.0}))
                 continue
-            pos, T = plan.offsets[k], plan.frames[k]
-            k += 1
-            u = flat[:, pos:pos + T]
-            J, F = float(J_from_counts(u[0], u[1], u[2])), float(F_from_counts(u[0], u[1], u[2]))
+            J, F = float(Js[k]), float(Fs[k])
             rec = {"J": J, "F": F, "JF": (J + F) / 2}
             if self.with_boundary:
-                rec["F_boundary"] = F_boundary_from_counts(u[3], u[4], u[5], u[6])
-            totals += u[:3].sum(axis=1, dtype=np.int64)
+                rec["F_boundary"] = float(Fbs[k])
+            k += 1
             results.append((key, rec))
         self._keys, self._pairs = [], []
         return results, totals

@@ -294,3 +294,38 @@ def test_label_metrics_from_counts_match_reference_formulas():
         for g in range(G):
             p, r, u = O.compute_mask_metrics(torch.from_numpy(tracks[i]).float(), torch.from_numpy(gts[g]).float())
             assert (float(p), float(r), float(u)) == (float(lab["precision"][i, g]), float(lab["recall"][i, g]), float(lab["iou"][i, g]))
+
+
+def test_sweep_metrics_vectorised_equal_the_per_unit_formulas():
+    """evaluator.sweep_metrics_from_counts (all units of a sweep in one pass) is bit-equal to J_from_counts / F_from_counts /
+    F_boundary_from_counts unit by unit — empty unions, empty boundaries, zero volumes, empty units, volumes above 2**24."""
+    from sola_b200 import evaluator as E
+    rng = np.random.default_rng(5)
+    for trial in range(40):
+        n = int(rng.integers(1, 30))
+        frames = rng.integers(0, 150, size=n) if trial % 3 else rng.integers(1, 9, size=n)
+        offs = np.concatenate([[0], np.cumsum(frames)[:-1]])
+        tot = int(frames.sum())
+        hi = 2_000_000 if trial % 5 == 0 else 50
+        pa, ga = rng.integers(0, hi, tot), rng.integers(0, hi, tot)
+        inter = (np.minimum(pa, ga) * rng.random(tot)).astype(np.int64)
+        for arr in (pa, ga):
+            z = rng.random(tot) < 0.2
+            arr[z] = 0
+            inter[z] = 0
+        a, b = rng.integers(0, 300, tot), rng.integers(0, 300, tot)
+        a[rng.random(tot) < 0.2] = 0
+        b[rng.random(tot) < 0.2] = 0
+        c = np.stack([inter, pa, ga, a, b, (a * rng.random(tot)).astype(np.int64), (b * rng.random(tot)).astype(np.int64)]).astype(np.int32)
+        if n > 2 and trial % 4 == 0:
+            c[:, offs[1]: offs[1] + frames[1]] = 0                  # a unit with tp == 0 and empty unions everywhere
+        J, F, Fb, totals = E.sweep_metrics_from_counts(c, offs, frames, True)
+        assert np.array_equal(totals, c[:3].sum(axis=1, dtype=np.int64))
+        for u in range(n):
+            o, t = int(offs[u]), int(frames[u])
+            if t == 0:
+                continue
+            sl = c[:, o: o + t]
+            assert J[u] == E.J_from_counts(sl[0], sl[1], sl[2])
+            assert F[u] == E.F_from_counts(sl[0], sl[1], sl[2])
+            assert Fb[u] == E.F_boundary_from_counts(sl[3], sl[4], sl[5], sl[6])
