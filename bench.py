@@ -271,12 +271,15 @@ def checks(w: Workload, out) -> dict:
         assert np.array_equal(r_area, area), "diag(inter) != sum of R1 areas (checksum of checksums)"
     assert (c[0] <= c[1]).all() and (c[1] <= c[2]).all(), "stability counts not nested"
     assert (inter <= np.minimum(area[:, None], area[None, :])).all()
-    # sub-sample vs the oracle: 2 tracks x 3 frames of planes, their stability scores, and the label metrics of track 0 vs GT 0
-    sub = w.logits[:2, :3].float().cpu()
-    planes = w.packed.words[:2, :3].cpu().numpy().view(np.uint32)
+    # sub-sample vs the oracle: tracks 0, 1 and the last two x 6 frames spread over the video — planes and stability scores —, and the
+    # label metrics of track 0 vs GT 0 over all frames (the GPU test suite holds the full-size entry-by-entry comparisons)
+    ti = sorted({0, min(1, w.N - 1), max(w.N - 2, 0), w.N - 1})
+    fi = sorted({0, 1, w.T // 3, w.T // 2, max(w.T - 2, 0), w.T - 1})
+    sub = w.logits[ti][:, fi].float().cpu()
+    planes = w.packed.words[ti][:, fi].cpu().numpy().view(np.uint32)
     assert np.array_equal(planes, O.pack_bits(sub.numpy() > 0)), "K1 planes differ from the oracle on the sub-sample"
     s = O.get_stability_score(sub.numpy())
-    assert np.array_equal(np.nan_to_num(s, nan=-1), np.nan_to_num(out["stability"][:2, :3], nan=-1)), "stability differs"
+    assert np.array_equal(np.nan_to_num(s, nan=-1), np.nan_to_num(out["stability"][ti][:, fi], nan=-1)), "stability differs"
     lab = out["labels"]
     rz0 = w.S.unpack_masks(w.S.resize_bilinear_bin(w.packed[0]), torch.float32).cpu()
     p_, r_, i_ = O.compute_mask_metrics(rz0, w.gt_masks[0].float().cpu())
