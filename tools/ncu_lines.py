@@ -14,6 +14,9 @@ for r in rows:
     elif r[0] == "Line No":
         hdr = r
     elif hdr and r[0].isdigit():
+        if len(r) != len(hdr):                      # a source line with unescaped quotes (inline asm) splits into extra fields: the
+            k = len(r) - len(hdr)                   # numeric columns are still the LAST ones, so realign from the end
+            r = [r[0], ",".join(r[1:2 + k])] + r[2 + k:]
         d = dict(zip(hdr, r))
         ie = int(float((d.get("Instructions Executed") or "0").replace("-", "0") or 0))
         if ie:
